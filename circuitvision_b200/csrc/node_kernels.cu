@@ -1,0 +1,753 @@
+// Node / connection analysis on device and the native-resolution CCL kernel.
+// Reference behaviour: /root/reference/src/circuit_analyzer.py:1286-1605 and helpers (see include/cv_b200.h).
+// Everything is batched over images (blockIdx.y / blockIdx.z = image) and HBM-bound integer work:
+// coalesced 16-byte accesses where rows are contiguous, shared-memory halo tiles for the stencils,
+// warp ballots for run detection, union-find with atomicMin for labelling.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <limits.h>
+
+#include "../../include/cv_b200.h"
+#include "common.cuh"
+#include "node_prims.cuh"
+
+namespace cvb {
+
+// ------------------------------------------------------------------------------------------------
+// a12: emptied = mask.copy(); emptied[box] = 0
+// ------------------------------------------------------------------------------------------------
+__global__ void k_copy16(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n16,
+                         const uint8_t* __restrict__ src8, uint8_t* __restrict__ dst8, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t k = i; k < n16; k += stride) dst[k] = __ldg(src + k);
+  for (size_t k = n16 * 16 + i; k < n; k += stride) dst8[k] = src8[k];
+}
+
+__global__ void k_zero_boxes(uint8_t* __restrict__ emptied, int H, int W, const cv_box* __restrict__ boxes,
+                             const int32_t* __restrict__ box_offsets) {
+  int b = blockIdx.y;
+  int i = box_offsets[b] + blockIdx.x;
+  if (i >= box_offsets[b + 1]) return;
+  cv_box bx = boxes[i];
+  if (!(bx.flags & CV_BOX_ZERO_IN_MASK)) return;
+  int y0 = max(0, bx.ymin), y1 = min(H, bx.ymax);
+  int x0 = max(0, bx.xmin), x1 = min(W, bx.xmax);
+  if (y0 >= y1 || x0 >= x1) return;
+  uint8_t* img = emptied + (size_t)b * H * W;
+  int bw = x1 - x0;
+  int total = bw * (y1 - y0);
+  for (int t = threadIdx.x; t < total; t += blockDim.x) {
+    int yy = t / bw, xx = t - yy * bw;
+    img[(size_t)(y0 + yy) * W + x0 + xx] = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// a13: cv2.resize(emptied, (w', 600)) INTER_LINEAR, bit-exact fixed point
+// ------------------------------------------------------------------------------------------------
+__global__ void k_resize(const uint8_t* __restrict__ src, int H, int W, uint8_t* __restrict__ dst, int h, int w) {
+  int b = blockIdx.z;
+  int dx = blockIdx.x * blockDim.x + threadIdx.x;
+  int dy = blockIdx.y * blockDim.y + threadIdx.y;
+  if (dx >= w || dy >= h) return;
+  const uint8_t* s = src + (size_t)b * H * W;
+  ResizeTap tx = resize_tap(dx, w, W, true);
+  ResizeTap ty = resize_tap(dy, h, H, false);
+  const uint8_t* r0 = s + (size_t)ty.i0 * W;
+  const uint8_t* r1 = s + (size_t)ty.i1 * W;
+  int a = resize_hpass(r0[tx.i0], r0[tx.i1], tx);
+  int c = resize_hpass(r1[tx.i0], r1[tx.i1], tx);
+  dst[(size_t)b * h * w + (size_t)dy * w + dx] = resize_vpass(a, c, ty);
+}
+
+// ------------------------------------------------------------------------------------------------
+// a14: GaussianBlur 5x5 (8.8 fixed point, reflect101) -> 5x5 max -> 5x5 min, one shared-memory tile pass.
+// Also accumulates the image sum that get_contours' mean>127 test needs (a15).
+// ------------------------------------------------------------------------------------------------
+#define ENH_T 32
+__global__ void __launch_bounds__(256) k_enhance(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int h,
+                                                 int w, unsigned long long* __restrict__ sums) {
+  __shared__ uint8_t s_src[ENH_T + 12][ENH_T + 12];
+  __shared__ uint16_t s_h[ENH_T + 12][ENH_T + 8];
+  __shared__ uint8_t s_bl[ENH_T + 8][ENH_T + 8];
+  __shared__ uint8_t s_di[ENH_T + 4][ENH_T + 4];
+  __shared__ unsigned int s_sum;
+  int b = blockIdx.z;
+  const uint8_t* img = src + (size_t)b * h * w;
+  int tx0 = blockIdx.x * ENH_T, ty0 = blockIdx.y * ENH_T;
+  int tid = threadIdx.x;
+  if (tid == 0) s_sum = 0;
+  for (int t = tid; t < (ENH_T + 12) * (ENH_T + 12); t += 256) {
+    int ly = t / (ENH_T + 12), lx = t - ly * (ENH_T + 12);
+    int gy = reflect101(ty0 + ly - 6, h), gx = reflect101(tx0 + lx - 6, w);
+    s_src[ly][lx] = img[(size_t)gy * w + gx];
+  }
+  __syncthreads();
+  // The tile was loaded through reflect101, so s_src[r][c] already holds img[reflect(gy)][reflect(gx)] for
+  // the halo coordinates; the 5-tap windows below therefore see BORDER_REFLECT_101 without further index math.
+  for (int t = tid; t < (ENH_T + 12) * (ENH_T + 8); t += 256) {
+    int ly = t / (ENH_T + 8), lx = t - ly * (ENH_T + 8);
+    s_h[ly][lx] = (uint16_t)gauss5_h(s_src[ly][lx], s_src[ly][lx + 1], s_src[ly][lx + 2], s_src[ly][lx + 3],
+                                     s_src[ly][lx + 4]);
+  }
+  __syncthreads();
+  for (int t = tid; t < (ENH_T + 8) * (ENH_T + 8); t += 256) {
+    int ly = t / (ENH_T + 8), lx = t - ly * (ENH_T + 8);
+    s_bl[ly][lx] = gauss5_v(s_h[ly][lx], s_h[ly + 1][lx], s_h[ly + 2][lx], s_h[ly + 3][lx], s_h[ly + 4][lx]);
+  }
+  __syncthreads();
+  // dilate (two 3x3 iterations == 5x5 max over in-image pixels)
+  for (int t = tid; t < (ENH_T + 4) * (ENH_T + 4); t += 256) {
+    int ly = t / (ENH_T + 4), lx = t - ly * (ENH_T + 4);
+    int gy = ty0 + ly - 2, gx = tx0 + lx - 2;
+    int m = 0;
+#pragma unroll
+    for (int dy = -2; dy <= 2; dy++)
+#pragma unroll
+      for (int dx = -2; dx <= 2; dx++) {
+        int yy = gy + dy, xx = gx + dx;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) m = max(m, (int)s_bl[ly + 2 + dy][lx + 2 + dx]);
+      }
+    s_di[ly][lx] = (uint8_t)m;
+  }
+  __syncthreads();
+  unsigned int local = 0;
+  for (int t = tid; t < ENH_T * ENH_T; t += 256) {
+    int ly = t / ENH_T, lx = t - ly * ENH_T;
+    int gy = ty0 + ly, gx = tx0 + lx;
+    if (gy < h && gx < w) {
+      int m = 255;
+#pragma unroll
+      for (int dy = -2; dy <= 2; dy++)
+#pragma unroll
+        for (int dx = -2; dx <= 2; dx++) {
+          int yy = gy + dy, xx = gx + dx;
+          if (yy >= 0 && yy < h && xx >= 0 && xx < w) m = min(m, (int)s_di[ly + 2 + dy][lx + 2 + dx]);
+        }
+      dst[(size_t)b * h * w + (size_t)gy * w + gx] = (uint8_t)m;
+      local += m;
+    }
+  }
+  for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((tid & 31) == 0) atomicAdd(&s_sum, local);
+  __syncthreads();
+  if (tid == 0) atomicAdd(&sums[b], (unsigned long long)s_sum);
+}
+
+// a15 prelude: mean>127 inversion, 255->1 mutation of the returned array, binary image for contouring
+__global__ void k_binarize(const uint8_t* __restrict__ enh_raw, uint8_t* __restrict__ enhanced_out,
+                           uint8_t* __restrict__ bin, int n_per_image, const unsigned long long* __restrict__ sums,
+                           cv_image_result* __restrict__ results) {
+  int b = blockIdx.y;
+  bool inv = sums[b] > 127ull * (unsigned long long)n_per_image;  // cv2.mean(img)[0] > 127
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) results[b].inverted = inv ? 1 : 0;
+  if (i >= n_per_image) return;
+  size_t p = (size_t)b * n_per_image + i;
+  uint8_t v = enh_raw[p];
+  enhanced_out[p] = inv ? v : (v == 255 ? (uint8_t)1 : v);
+  bin[p] = inv ? (uint8_t)(v != 255) : (uint8_t)(v != 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// union-find connected-component labelling.  Parent of x is L[x] - OFF (OFF = 1 lets 0 mean background
+// in the caller-visible label image; OFF = 0 is used internally where background is labelled as well).
+// ------------------------------------------------------------------------------------------------
+template <int OFF>
+__device__ __forceinline__ int uf_find(const int* L, int x) {
+  int y = __ldcg(L + x) - OFF;
+  while (y != x) {
+    x = y;
+    y = __ldcg(L + x) - OFF;
+  }
+  return x;
+}
+
+template <int OFF>
+__device__ __forceinline__ void uf_union(int* L, int a, int b) {
+  bool done;
+  do {
+    a = uf_find<OFF>(L, a);
+    b = uf_find<OFF>(L, b);
+    if (a < b) {
+      int old = atomicMin(L + b, a + OFF) - OFF;
+      done = (old == b);
+      b = old;
+    } else if (b < a) {
+      int old = atomicMin(L + a, b + OFF) - OFF;
+      done = (old == a);
+      a = old;
+    } else {
+      done = true;
+    }
+  } while (!done);
+}
+
+// One warp = 32 consecutive pixels of one row.  Initial label = start of the pixel's horizontal run inside
+// the warp segment (ballot + clz), so that only run boundaries need union operations afterwards.
+template <int OFF, bool WITH_BG>
+__global__ void __launch_bounds__(256) k_ccl_init(const uint8_t* __restrict__ bin, int* __restrict__ L, int h, int w) {
+  int b = blockIdx.z;
+  int x = blockIdx.x * 32 + threadIdx.x;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (y >= h) return;
+  bool in = x < w;
+  size_t base = (size_t)b * h * w;
+  int p = y * w + x;
+  bool f = in && bin[base + p] != 0;
+  unsigned fgbits = __ballot_sync(0xffffffffu, f);
+  unsigned bgbits = __ballot_sync(0xffffffffu, in && !f);
+  if (!in) return;
+  unsigned mine = f ? fgbits : bgbits;
+  unsigned below = ~mine & ((1u << threadIdx.x) - 1u);
+  int start = below ? (32 - __clz(below)) : 0;
+  int lbl = p - (int)threadIdx.x + start;
+  if (f || WITH_BG) L[base + p] = lbl + OFF;
+  else L[base + p] = 0;  // only reachable with OFF == 1: background = 0
+}
+
+template <int OFF, bool WITH_BG, int CONN>
+__global__ void __launch_bounds__(256) k_ccl_merge(const uint8_t* __restrict__ bin, int* __restrict__ Lall, int h,
+                                                   int w) {
+  int b = blockIdx.z;
+  int x = blockIdx.x * 32 + threadIdx.x;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (y >= h || x >= w) return;
+  const uint8_t* im = bin + (size_t)b * h * w;
+  int* L = Lall + (size_t)b * h * w;
+  int p = y * w + x;
+  bool f = im[p] != 0;
+  if (!f && !WITH_BG) return;
+  bool hasL = x > 0, hasU = y > 0, hasR = x + 1 < w;
+  // "same" = neighbour exists and has the same class (fg/bg) as p
+  bool left = hasL && ((im[p - 1] != 0) == f);
+  bool up = hasU && ((im[p - w] != 0) == f);
+  bool ul = hasU && hasL && ((im[p - w - 1] != 0) == f);
+  if (left && (threadIdx.x == 0)) uf_union<OFF>(L, p, p - 1);  // stitch runs across the warp boundary
+  if (up) {
+    if (!(left && ul)) uf_union<OFF>(L, p, p - w);
+  } else if (f && CONN == 8) {
+    bool ur = hasU && hasR && (im[p - w + 1] != 0);
+    if (ul && !left) uf_union<OFF>(L, p, p - w - 1);
+    if (ur) uf_union<OFF>(L, p, p - w + 1);
+  }
+}
+
+template <int OFF, bool WITH_BG>
+__global__ void __launch_bounds__(256) k_ccl_flatten(const uint8_t* __restrict__ bin, int* __restrict__ Lall,
+                                                     int n_per_image, int* __restrict__ ncomp) {
+  int b = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool isroot = false;
+  if (i < n_per_image) {
+    int* L = Lall + (size_t)b * n_per_image;
+    bool f = bin[(size_t)b * n_per_image + i] != 0;
+    if (f || WITH_BG) {
+      int r = uf_find<OFF>(L, i);
+      if (r != i) L[i] = r + OFF;  // roots keep pointing at themselves, so concurrent finds stay valid
+      isroot = f && (r == i);
+    }
+  }
+  if (ncomp) {
+    unsigned m = __ballot_sync(0xffffffffu, isroot);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(ncomp + b, __popc(m));
+  }
+}
+
+// background regions that touch the image frame (4-connected to cv2's implicit zero border)
+__global__ void k_frame_flags(const uint8_t* __restrict__ bin, const int* __restrict__ Lall, uint8_t* __restrict__ frame,
+                              int h, int w) {
+  int b = blockIdx.y;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int per = 2 * w + 2 * h;
+  if (t >= per) return;
+  int x, y;
+  if (t < w) { x = t; y = 0; }
+  else if (t < 2 * w) { x = t - w; y = h - 1; }
+  else if (t < 2 * w + h) { x = 0; y = t - 2 * w; }
+  else { x = w - 1; y = t - 2 * w - h; }
+  size_t base = (size_t)b * h * w;
+  int p = y * w + x;
+  if (bin[base + p] == 0) frame[base + Lall[base + p]] = 1;
+}
+
+// External components (cv2 RETR_EXTERNAL) listed in cv2's order = descending raster index of the first pixel.
+// One CTA per image.
+#define CVB_MAX_ROWS 1024
+__global__ void __launch_bounds__(1024) k_list_external(const uint8_t* __restrict__ bin, const int* __restrict__ Lall,
+                                                        const uint8_t* __restrict__ frame, int h, int w,
+                                                        int* __restrict__ cand, int max_external,
+                                                        cv_image_result* __restrict__ results) {
+  __shared__ int s_cnt[CVB_MAX_ROWS];
+  __shared__ int s_total;
+  int b = blockIdx.x;
+  size_t base = (size_t)b * h * w;
+  const uint8_t* im = bin + base;
+  const int* L = Lall + base;
+  const uint8_t* fr = frame + base;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto is_ext = [&](int x, int y) -> bool {
+    if (x >= w) return false;
+    int p = y * w + x;
+    if (im[p] == 0 || L[p] != p) return false;
+    return x == 0 || fr[L[p - 1]] != 0;
+  };
+  for (int y = warp; y < h; y += 32) {
+    int cnt = 0;
+    for (int x0 = 0; x0 < w; x0 += 32) cnt += __popc(__ballot_sync(0xffffffffu, is_ext(x0 + lane, y)));
+    if (lane == 0) s_cnt[y] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int y = h - 1; y >= 0; y--) {
+      int c = s_cnt[y];
+      s_cnt[y] = run;  // number of externals in rows below
+      run += c;
+    }
+    s_total = run;
+  }
+  __syncthreads();
+  int nchunks = (w + 31) / 32;
+  for (int y = warp; y < h; y += 32) {
+    int run = s_cnt[y];
+    for (int c = nchunks - 1; c >= 0; c--) {
+      bool e = is_ext(c * 32 + lane, y);
+      unsigned bits = __ballot_sync(0xffffffffu, e);
+      if (e) {
+        unsigned right = (lane == 31) ? 0u : (bits >> (lane + 1));
+        int idx = run + __popc(right);
+        if (idx < max_external) cand[(size_t)b * max_external + idx] = y * w + c * 32 + lane;
+      }
+      run += __popc(bits);
+    }
+  }
+  if (threadIdx.x == 0) {
+    int tot = s_total;
+    if (tot > max_external) {
+      results[b].status |= CV_STATUS_EXTERNAL_OVERFLOW;
+      tot = max_external;
+    }
+    results[b].n_external = tot;
+  }
+}
+
+struct CandStat {
+  int32_t nverts, xmin, ymin, xmax, ymax, pad;
+  long long a00, a01;
+};
+
+// a15: follow every external border once without storing it: vertex count, extents, polygon sums
+__global__ void k_trace_stats(const uint8_t* __restrict__ bin, int h, int w, const int* __restrict__ cand,
+                              int max_external, const cv_image_result* __restrict__ results,
+                              CandStat* __restrict__ stats) {
+  int b = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= results[b].n_external) return;
+  int p = cand[(size_t)b * max_external + i];
+  ContourStats st = trace_outer_simple<uint8_t>(bin + (size_t)b * h * w, w, h, p % w, p / w, nullptr, 0);
+  CandStat cs;
+  cs.nverts = st.nverts;
+  cs.xmin = st.xmin; cs.ymin = st.ymin; cs.xmax = st.xmax; cs.ymax = st.ymax; cs.pad = 0;
+  cs.a00 = st.a00; cs.a01 = st.a01;
+  stats[(size_t)b * max_external + i] = cs;
+}
+
+// area filter (contourArea / (h*w) > 0.0004) + ids + point-pool offsets; one CTA per image
+__global__ void __launch_bounds__(1024) k_filter_contours(const int* __restrict__ cand, const CandStat* __restrict__ stats,
+                                                          int max_external, int h, int w, double area_thr,
+                                                          cv_contour* __restrict__ contours, int max_contours,
+                                                          int max_points, cv_image_result* __restrict__ results) {
+  __shared__ int s_wk[32], s_wp[32];
+  __shared__ int s_run_k, s_run_p;
+  int b = blockIdx.x;
+  int nE = results[b].n_external;
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { s_run_k = 0; s_run_p = 0; }
+  __syncthreads();
+  int status = 0;
+  for (int c0 = 0; c0 < nE; c0 += 1024) {
+    int i = c0 + threadIdx.x;
+    CandStat cs;
+    int keep = 0, np = 0;
+    if (i < nE) {
+      cs = stats[(size_t)b * max_external + i];
+      keep = area_passes(cs.a00, h, w, area_thr) ? 1 : 0;
+      np = keep ? cs.nverts : 0;
+    }
+    // block exclusive scan of (keep, np)
+    int k = keep, q = np;
+    for (int o = 1; o < 32; o <<= 1) {
+      int tk = __shfl_up_sync(0xffffffffu, k, o), tq = __shfl_up_sync(0xffffffffu, q, o);
+      if (lane >= o) { k += tk; q += tq; }
+    }
+    if (lane == 31) { s_wk[warp] = k; s_wp[warp] = q; }
+    __syncthreads();
+    if (warp == 0) {
+      int a = s_wk[lane], c = s_wp[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        int ta = __shfl_up_sync(0xffffffffu, a, o), tc = __shfl_up_sync(0xffffffffu, c, o);
+        if (lane >= o) { a += ta; c += tc; }
+      }
+      s_wk[lane] = a; s_wp[lane] = c;
+    }
+    __syncthreads();
+    int base_k = s_run_k + (warp ? s_wk[warp - 1] : 0);
+    int base_p = s_run_p + (warp ? s_wp[warp - 1] : 0);
+    int id = base_k + k - keep;
+    int off = base_p + q - np;
+    if (keep) {
+      if (id < max_contours && off + np <= max_points) {
+        int p = cand[(size_t)b * max_external + i];
+        cv_contour ct;
+        ct.start_x = p % w; ct.start_y = p / w;
+        ct.offset = off; ct.nverts = cs.nverts;
+        ct.xmin = cs.xmin; ct.ymin = cs.ymin; ct.xmax = cs.xmax; ct.ymax = cs.ymax;
+        ct.a00 = cs.a00; ct.a01 = cs.a01;
+        ct.new_id = -1; ct.ncomp = 0; ct.has_source = 0;
+        int cy;
+        ct.centroid_y = centroid_y(cs.a00, cs.a01, &cy) ? cy : INT_MIN;
+        contours[(size_t)b * max_contours + id] = ct;
+      } else {
+        status |= (id >= max_contours) ? CV_STATUS_CONTOUR_OVERFLOW : CV_STATUS_POINT_OVERFLOW;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) { s_run_k = base_k + k; s_run_p = base_p + q; }
+    __syncthreads();
+  }
+  if (status) atomicOr(&results[b].status, status);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int nk = s_run_k, npnt = s_run_p;
+    // on overflow the stored prefix is still self-consistent: ids/offsets are monotone
+    if (nk > max_contours) nk = max_contours;
+    results[b].n_contours = nk;
+    results[b].n_points = npnt > max_points ? max_points : npnt;
+  }
+}
+
+// a15: second walk of the kept borders, now writing the SIMPLE vertex lists
+__global__ void k_trace_points(const uint8_t* __restrict__ bin, int h, int w, const cv_contour* __restrict__ contours,
+                               int max_contours, int max_points, const cv_image_result* __restrict__ results,
+                               int32_t* __restrict__ points) {
+  int b = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= results[b].n_contours) return;
+  const cv_contour& ct = contours[(size_t)b * max_contours + i];
+  if (ct.offset + ct.nverts > max_points) return;
+  trace_outer_simple<uint8_t>(bin + (size_t)b * h * w, w, h, ct.start_x, ct.start_y,
+                              points + ((size_t)b * max_points + ct.offset) * 2, ct.nverts);
+}
+
+// ------------------------------------------------------------------------------------------------
+// a16: box <-> contour contact.  One CTA per image; each warp takes one box of the current chunk of 32
+// boxes and walks the contours in id order (AABB pre-test, then a ballot scan of the vertex list for the
+// first vertex that is "near").  Hits are staged in shared memory and flushed in box-major order so the
+// pair list has the reference's append order.
+// ------------------------------------------------------------------------------------------------
+#define CVB_HITS_PER_BOX 64
+__global__ void __launch_bounds__(1024) k_contact(const cv_box* __restrict__ boxes, const int32_t* __restrict__ box_offsets,
+                                                  const cv_contour* __restrict__ contours, int max_contours,
+                                                  const int32_t* __restrict__ points, int max_points,
+                                                  cv_pair* __restrict__ pairs, int max_pairs,
+                                                  cv_image_result* __restrict__ results) {
+  __shared__ cv_pair s_hits[32][CVB_HITS_PER_BOX];
+  __shared__ int s_nh[32];
+  __shared__ int s_base[33];
+  __shared__ int s_written;
+  int b = blockIdx.x;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int bo = box_offsets[b], nb = box_offsets[b + 1] - bo;
+  int nK = results[b].n_contours;
+  const cv_contour* cts = contours + (size_t)b * max_contours;
+  const int32_t* pts = points + (size_t)b * max_points * 2;
+  if (threadIdx.x == 0) s_written = 0;
+  __syncthreads();
+  int status = 0;
+  for (int c0 = 0; c0 < nb; c0 += 32) {
+    int bi = c0 + warp;
+    int nh = 0;
+    if (bi < nb) {
+      cv_box bx = boxes[bo + bi];
+      if (bx.flags & CV_BOX_IS_COMPONENT) {
+        for (int k = 0; k < nK; k++) {
+          const cv_contour& ct = cts[k];
+          int cx = ct.xmin, cy = ct.ymin, cxm = ct.xmax + 1, cym = ct.ymax + 1;  // rect x+w, y+h
+          if (bx.rxmax < cx || bx.rxmin > cxm || bx.rymax < cy || bx.rymin > cym) continue;
+          int n = ct.nverts;
+          const int32_t* cp = pts + (size_t)ct.offset * 2;
+          int hit = -1, hx = 0, hy = 0;
+          for (int v0 = 0; v0 < n && hit < 0; v0 += 32) {
+            int v = v0 + lane;
+            bool near = false;
+            int px = 0, py = 0;
+            if (v < n) {
+              px = cp[2 * v]; py = cp[2 * v + 1];
+              near = point_near_box(px, py, bx.rxmin, bx.rymin, bx.rxmax, bx.rymax, bx.thresh);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, near);
+            if (m) {
+              int src = __ffs(m) - 1;
+              hit = v0 + src;
+              hx = __shfl_sync(0xffffffffu, px, src);
+              hy = __shfl_sync(0xffffffffu, py, src);
+            }
+          }
+          if (hit >= 0) {
+            if (nh < CVB_HITS_PER_BOX) {
+              if (lane == 0) { cv_pair pr; pr.contour = k; pr.box = bi; pr.px = hx; pr.py = hy; s_hits[warp][nh] = pr; }
+            } else {
+              status |= CV_STATUS_PAIR_OVERFLOW;
+            }
+            nh++;
+          }
+        }
+      }
+    }
+    if (lane == 0) s_nh[warp] = min(nh, CVB_HITS_PER_BOX);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int run = s_written;
+      for (int i = 0; i < 32; i++) { s_base[i] = run; run += s_nh[i]; }
+      s_base[32] = run;
+    }
+    __syncthreads();
+    int n_mine = s_nh[warp];
+    for (int j = lane; j < n_mine; j += 32) {
+      int dst = s_base[warp] + j;
+      if (dst < max_pairs) pairs[(size_t)b * max_pairs + dst] = s_hits[warp][j];
+      else status |= CV_STATUS_PAIR_OVERFLOW;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_written = s_base[32];
+    __syncthreads();
+  }
+  if (status) atomicOr(&results[b].status, status);
+  __syncthreads();
+  if (threadIdx.x == 0) results[b].n_pairs = min(s_written, max_pairs);
+}
+
+// ------------------------------------------------------------------------------------------------
+// a16 tail + a17: uid de-duplication, ground selection, renumbering (circuit_analyzer.py:1418-1582).
+// Tiny and sequential: one thread per image.  The pair list is compacted in place (dropped duplicates).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_assemble(const cv_box* __restrict__ boxes, const int32_t* __restrict__ box_offsets,
+                           cv_contour* __restrict__ contours, int max_contours, cv_pair* __restrict__ pairs,
+                           int max_pairs, cv_image_result* __restrict__ results, int B) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  cv_contour* cts = contours + (size_t)b * max_contours;
+  cv_pair* pr = pairs + (size_t)b * max_pairs;
+  const cv_box* bx = boxes + box_offsets[b];
+  int nK = results[b].n_contours, nP = results[b].n_pairs;
+  // de-duplicate (node, persistent_uid): keep the first occurrence in append order
+  int out = 0;
+  for (int i = 0; i < nP; i++) {
+    cv_pair p = pr[i];
+    int g = bx[p.box].uid_group;
+    bool dup = false;
+    if (g != p.box) {  // only boxes that share a uid with an earlier box can be duplicates
+      for (int j = 0; j < out && !dup; j++) dup = (pr[j].contour == p.contour) && (bx[pr[j].box].uid_group == g);
+    }
+    if (!dup) {
+      pr[out++] = p;
+      cts[p.contour].ncomp++;
+      if (bx[p.box].flags & CV_BOX_IS_SOURCE) cts[p.contour].has_source = 1;
+    }
+  }
+  results[b].n_pairs = out;
+  int n_valid = 0, max_conn = 0;
+  for (int k = 0; k < nK; k++)
+    if (cts[k].ncomp > 0) { n_valid++; max_conn = max(max_conn, cts[k].ncomp); }
+  results[b].ground = -1;
+  results[b].n_nodes = 0;
+  if (n_valid == 0) return;
+  // ground: source-connected valid node with the largest centroid_y (stable => lowest id on ties) :1475-1497
+  int ground = -1;
+  long long best = LLONG_MIN;
+  bool any_src = false;
+  for (int k = 0; k < nK; k++)
+    if (cts[k].ncomp > 0 && cts[k].has_source) {
+      long long cy = cts[k].centroid_y == INT_MIN ? (LLONG_MIN + 1) : (long long)cts[k].centroid_y;
+      if (!any_src || cy > best) { best = cy; ground = k; }
+      any_src = true;
+    }
+  if (!any_src) {  // :1499-1524 fallback among the nodes with the most components
+    int n_max = 0, first_max = -1;
+    for (int k = 0; k < nK; k++)
+      if (cts[k].ncomp == max_conn) { if (first_max < 0) first_max = k; n_max++; }
+    if (n_max > 1) {
+      bool any = false;
+      for (int k = 0; k < nK; k++)
+        if (cts[k].ncomp == max_conn) {
+          long long cy = cts[k].centroid_y == INT_MIN ? (LLONG_MIN + 1) : (long long)cts[k].centroid_y;
+          if (!any || cy > best) { best = cy; ground = k; }
+          any = true;
+        }
+    } else {
+      ground = first_max;
+    }
+  }
+  results[b].ground = ground;
+  cts[ground].new_id = 0;
+  int nxt = 1;
+  for (int k = 0; k < nK; k++) {  // :1556-1568
+    if (k == ground || cts[k].ncomp == 0) continue;
+    if (cts[k].ncomp >= 2 || (nxt == 1 && n_valid == 2)) cts[k].new_id = nxt++;
+  }
+  results[b].n_nodes = nxt;
+}
+
+__global__ void k_init_results(cv_image_result* results, unsigned long long* sums, int B) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  cv_image_result r;
+  r.n_external = r.n_contours = r.n_points = r.n_pairs = r.n_nodes = 0;
+  r.ground = -1; r.inverted = 0; r.status = 0;
+  results[b] = r;
+  sums[b] = 0;
+}
+
+}  // namespace cvb
+
+using namespace cvb;
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static cv_nodes_caps resolve_caps(const cv_nodes_caps* caps) {
+  cv_nodes_caps c;
+  c.max_external = 32768; c.max_contours = 2560; c.max_points = 262144; c.max_pairs = 8192;
+  if (caps) {
+    if (caps->max_external > 0) c.max_external = caps->max_external;
+    if (caps->max_contours > 0) c.max_contours = caps->max_contours;
+    if (caps->max_points > 0) c.max_points = caps->max_points;
+    if (caps->max_pairs > 0) c.max_pairs = caps->max_pairs;
+  }
+  return c;
+}
+
+extern "C" int cv_nodes_resized_width(int H, int W) {
+  if (H <= 0 || W <= 0) return 0;
+  double aspect = (double)W / (double)H;   // circuit_analyzer.py:800
+  return (int)(600.0 * aspect);            // :803 int(new_height * aspect_ratio)
+}
+
+struct NodesWs {
+  uint8_t* enh_raw; uint8_t* bin; uint8_t* frame; int* labels; int* cand; CandStat* stats; unsigned long long* sums;
+  size_t total;
+};
+
+static NodesWs carve_nodes_ws(void* base, int B, int h, int w, const cv_nodes_caps& c) {
+  NodesWs ws;
+  size_t n = (size_t)B * h * w, off = 0;
+  char* p = (char*)base;
+  ws.enh_raw = (uint8_t*)(p + off); off += align256(n);
+  ws.bin = (uint8_t*)(p + off); off += align256(n);
+  ws.frame = (uint8_t*)(p + off); off += align256(n);
+  ws.labels = (int*)(p + off); off += align256(n * 4);
+  ws.cand = (int*)(p + off); off += align256((size_t)B * c.max_external * 4);
+  ws.stats = (CandStat*)(p + off); off += align256((size_t)B * c.max_external * sizeof(CandStat));
+  ws.sums = (unsigned long long*)(p + off); off += align256((size_t)B * 8);
+  ws.total = off;
+  return ws;
+}
+
+extern "C" size_t cv_nodes_workspace_bytes(int B, int H, int W, const cv_nodes_caps* caps) {
+  int w = cv_nodes_resized_width(H, W);
+  if (B <= 0 || w <= 0) return 0;
+  return carve_nodes_ws(nullptr, B, 600, w, resolve_caps(caps)).total;
+}
+
+extern "C" int cv_nodes_analyze(const uint8_t* masks, int B, int H, int W, const cv_box* boxes,
+                                const int32_t* box_offsets, int max_boxes_per_image, uint8_t* emptied,
+                                uint8_t* resized, uint8_t* enhanced, cv_contour* contours, int32_t* points,
+                                cv_pair* pairs, cv_image_result* results, const cv_nodes_caps* caps, void* workspace,
+                                size_t workspace_bytes, void* stream_) {
+  cvb_reset_launches();
+  if (!masks || !emptied || !resized || !enhanced || !contours || !points || !pairs || !results || !box_offsets ||
+      !workspace || B <= 0 || H <= 0 || W <= 0)
+    return cvb_fail(CV_ERR_INVALID, "cv_nodes_analyze: null pointer or non-positive size");
+  const int h = 600;
+  const int w = cv_nodes_resized_width(H, W);
+  if (w <= 0) return cvb_fail(CV_ERR_INVALID, "cv_nodes_analyze: resized width is 0 (extreme aspect ratio)");
+  if (h > CVB_MAX_ROWS) return cvb_fail(CV_ERR_INVALID, "cv_nodes_analyze: internal row limit");
+  if ((long long)h * w >= (1ll << 30)) return cvb_fail(CV_ERR_INVALID, "cv_nodes_analyze: resized image too large");
+  cv_nodes_caps c = resolve_caps(caps);
+  NodesWs ws = carve_nodes_ws(workspace, B, h, w, c);
+  if (workspace_bytes < ws.total) return cvb_fail(CV_ERR_INVALID, "cv_nodes_analyze: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream_;
+  const size_t n_full = (size_t)B * H * W;
+  const int n_small = h * w;
+
+  CVB_LAUNCH(k_init_results, dim3((B + 127) / 128), dim3(128), 0, st, results, ws.sums, B);
+  {  // a12
+    bool al = (((uintptr_t)masks | (uintptr_t)emptied) & 15) == 0;
+    size_t n16 = al ? n_full / 16 : 0;
+    size_t want = (n16 + 255) / 256;
+    int grid = (int)(want < 1 ? 1 : (want > 148 * 16 ? 148 * 16 : want));
+    CVB_LAUNCH(k_copy16, dim3(grid), dim3(256), 0, st, (const uint4*)masks, (uint4*)emptied, n16, masks, emptied, n_full);
+    if (max_boxes_per_image > 0 && boxes)
+      CVB_LAUNCH(k_zero_boxes, dim3(max_boxes_per_image, B), dim3(256), 0, st, emptied, H, W, boxes, box_offsets);
+  }
+  // a13
+  CVB_LAUNCH(k_resize, dim3((w + 31) / 32, (h + 7) / 8, B), dim3(32, 8), 0, st, emptied, H, W, resized, h, w);
+  // a14 + a15 prelude
+  CVB_LAUNCH(k_enhance, dim3((w + ENH_T - 1) / ENH_T, (h + ENH_T - 1) / ENH_T, B), dim3(256), 0, st, resized, ws.enh_raw,
+             h, w, ws.sums);
+  CVB_LAUNCH(k_binarize, dim3((n_small + 255) / 256, B), dim3(256), 0, st, ws.enh_raw, enhanced, ws.bin, n_small,
+             ws.sums, results);
+  // a15: labelling (8-connected foreground, 4-connected background) -> external components -> borders
+  CVB_CHECK(cudaMemsetAsync(ws.frame, 0, (size_t)B * n_small, st));
+  dim3 cg((w + 31) / 32, (h + 7) / 8, B), cb(32, 8);
+  CVB_LAUNCH((k_ccl_init<0, true>), cg, cb, 0, st, ws.bin, ws.labels, h, w);
+  CVB_LAUNCH((k_ccl_merge<0, true, 8>), cg, cb, 0, st, ws.bin, ws.labels, h, w);
+  CVB_LAUNCH((k_ccl_flatten<0, true>), dim3((n_small + 255) / 256, B), dim3(256), 0, st, ws.bin, ws.labels, n_small,
+             (int*)nullptr);
+  CVB_LAUNCH(k_frame_flags, dim3((2 * w + 2 * h + 255) / 256, B), dim3(256), 0, st, ws.bin, ws.labels, ws.frame, h, w);
+  CVB_LAUNCH(k_list_external, dim3(B), dim3(1024), 0, st, ws.bin, ws.labels, ws.frame, h, w, ws.cand, c.max_external,
+             results);
+  CVB_LAUNCH(k_trace_stats, dim3((c.max_external + 63) / 64, B), dim3(64), 0, st, ws.bin, h, w, ws.cand, c.max_external,
+             results, ws.stats);
+  CVB_LAUNCH(k_filter_contours, dim3(B), dim3(1024), 0, st, ws.cand, ws.stats, c.max_external, h, w, 0.0004, contours,
+             c.max_contours, c.max_points, results);
+  CVB_LAUNCH(k_trace_points, dim3((c.max_contours + 63) / 64, B), dim3(64), 0, st, ws.bin, h, w, contours, c.max_contours,
+             c.max_points, results, points);
+  // a16, a17
+  if (boxes) {
+    CVB_LAUNCH(k_contact, dim3(B), dim3(1024), 0, st, boxes, box_offsets, contours, c.max_contours, points, c.max_points,
+               pairs, c.max_pairs, results);
+    CVB_LAUNCH(k_assemble, dim3((B + 31) / 32), dim3(32), 0, st, boxes, box_offsets, contours, c.max_contours, pairs,
+               c.max_pairs, results, B);
+  }
+  return CV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// native-resolution CCL (BASELINE cfg 4)
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t cv_ccl_workspace_bytes(int B, int H, int W) {
+  (void)B; (void)H; (void)W;
+  return 256;  // labels are resolved in place in the caller's label image
+}
+
+extern "C" int cv_ccl_label(const uint8_t* masks, int B, int H, int W, int connectivity, int32_t* labels,
+                            int32_t* n_components, void* workspace, size_t workspace_bytes, void* stream_) {
+  cvb_reset_launches();
+  (void)workspace; (void)workspace_bytes;
+  if (!masks || !labels || B <= 0 || H <= 0 || W <= 0)
+    return cvb_fail(CV_ERR_INVALID, "cv_ccl_label: null pointer or non-positive size");
+  if (connectivity != 4 && connectivity != 8) return cvb_fail(CV_ERR_INVALID, "cv_ccl_label: connectivity must be 4 or 8");
+  if ((long long)H * W >= (1ll << 31) - 2) return cvb_fail(CV_ERR_INVALID, "cv_ccl_label: image too large for int32 labels");
+  if (B > 65535) return cvb_fail(CV_ERR_INVALID, "cv_ccl_label: batch too large");
+  cudaStream_t st = (cudaStream_t)stream_;
+  int n = H * W;
+  if (n_components) CVB_CHECK(cudaMemsetAsync(n_components, 0, (size_t)B * 4, st));
+  dim3 cg((W + 31) / 32, (H + 7) / 8, B), cb(32, 8);
+  CVB_LAUNCH((k_ccl_init<1, false>), cg, cb, 0, st, masks, labels, H, W);
+  if (connectivity == 8) CVB_LAUNCH((k_ccl_merge<1, false, 8>), cg, cb, 0, st, masks, labels, H, W);
+  else CVB_LAUNCH((k_ccl_merge<1, false, 4>), cg, cb, 0, st, masks, labels, H, W);
+  CVB_LAUNCH((k_ccl_flatten<1, false>), dim3((n + 255) / 256, B), dim3(256), 0, st, masks, labels, n, n_components);
+  return CV_OK;
+}

@@ -1,0 +1,116 @@
+/* circuitvision_b200 — C ABI of the B200-native hot path (libcv_b200.so).
+ *
+ * The reference (JKc66/CircuitVision) is pure Python and has no FFI: its boundary for this path is the pair
+ * of Python call signatures
+ *     src/sam2_infer.py:191-275        SAM2ImageWrapper.forward (+ SAM2Transforms :29-128, MultiKernelRefinement :130-189)
+ *     src/circuit_analyzer.py:321-386  CircuitAnalyzer.segment_with_sam2
+ *     src/circuit_analyzer.py:1286-1605 CircuitAnalyzer.get_node_connections
+ * which circuitvision_b200/sam2_infer.py and circuitvision_b200/circuit_analyzer.py keep unchanged.  This header
+ * is the C ABI *underneath* those classes: plain C symbols, int status returns (0 = ok, message via
+ * cv_last_error()), caller-owned DEVICE pointers unless a parameter says "host", explicit CUDA stream passed as
+ * void* (cudaStream_t), no torch / C++ types.  INTEGRATION.md shows the ctypes binding.
+ */
+#ifndef CV_B200_H
+#define CV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CV_OK 0
+#define CV_ERR_INVALID 1
+#define CV_ERR_CUDA 2
+#define CV_ERR_CAPACITY 3
+
+/* thread-local description of the last non-zero status returned on this thread */
+const char* cv_last_error(void);
+/* library / build identification: "circuitvision_b200 <version> sm_100a" */
+const char* cv_version(void);
+/* 1 when the current device is compute capability 10.x */
+int cv_device_is_sm100(int device);
+
+/* ------------------------------------------------------------------ node / connection analysis
+ * replaces circuit_analyzer.py:1286-1605 (get_node_connections) and helpers :787-809, :461-477, :289-311,
+ * :388-412, :811-846 for a batch of B masks of identical size H x W.                                      */
+
+#define CV_BOX_ZERO_IN_MASK 1 /* class not in ('crossover','junction','circuit','vss')  (:1326) */
+#define CV_BOX_IS_COMPONENT 2 /* class not in non_components                           (:51,:1381) */
+#define CV_BOX_IS_SOURCE 4    /* class in source_components                            (:52,:1408) */
+
+typedef struct cv_box {
+  int32_t xmin, ymin, xmax, ymax;     /* int()-truncated mask-space coords            (:1339-1340) */
+  int32_t rxmin, rymin, rxmax, rymax; /* resized-space coords int(v*scale)            (:466-469)  */
+  int32_t flags;                      /* CV_BOX_*                                                  */
+  int32_t thresh;                     /* contact threshold 20 / 8 / 6                 (:1404-1415) */
+  int32_t uid_group;                  /* index (within the image) of the first box with the same persistent_uid */
+  int32_t reserved;
+} cv_box;
+
+typedef struct cv_contour {
+  int32_t start_x, start_y;           /* raster-first pixel = first vertex                          */
+  int32_t offset, nverts;             /* slice of the image's point pool                            */
+  int32_t xmin, ymin, xmax, ymax;     /* inclusive extents; cv2.boundingRect = (xmin,ymin,xmax-xmin+1,ymax-ymin+1) */
+  int64_t a00, a01;                   /* polygon sums: contourArea = |a00|/2, m01/m00 = a01/(3*a00) */
+  int32_t new_id;                     /* id in new_nodes_list, or -1 when dropped     (:1547-1582) */
+  int32_t ncomp;                      /* attached components after uid de-duplication               */
+  int32_t has_source;                 /* any attached component is a source                         */
+  int32_t centroid_y;                 /* int(m01/m00), INT32_MIN when m00 == 0                      */
+} cv_contour;
+
+typedef struct cv_pair {              /* one accepted (node, component) attachment, in reference order */
+  int32_t contour, box, px, py;
+} cv_pair;
+
+#define CV_STATUS_EXTERNAL_OVERFLOW 1
+#define CV_STATUS_CONTOUR_OVERFLOW 2
+#define CV_STATUS_POINT_OVERFLOW 4
+#define CV_STATUS_PAIR_OVERFLOW 8
+
+typedef struct cv_image_result {
+  int32_t n_external;  /* external components before the area filter */
+  int32_t n_contours;  /* kept contours (ids 0..n-1, cv2 order)      */
+  int32_t n_points;    /* vertices stored in the point pool          */
+  int32_t n_pairs;
+  int32_t n_nodes;     /* len(new_nodes_list)                        */
+  int32_t ground;      /* old contour id chosen as node 0, or -1     */
+  int32_t inverted;    /* get_contours took the mean>127 branch      */
+  int32_t status;      /* CV_STATUS_* bits; non-zero => results for this image are incomplete */
+} cv_image_result;
+
+typedef struct cv_nodes_caps {
+  int32_t max_external; /* candidates per image before the area filter (default 32768) */
+  int32_t max_contours; /* kept contours per image              (default 2560)  */
+  int32_t max_points;   /* vertices per image                   (default 262144) */
+  int32_t max_pairs;    /* attachments per image                (default 8192)  */
+} cv_nodes_caps;
+
+/* resized width the reference uses: int(600 * (W / H)) */
+int cv_nodes_resized_width(int H, int W);
+/* bytes of device scratch cv_nodes_analyze needs for this problem size */
+size_t cv_nodes_workspace_bytes(int B, int H, int W, const cv_nodes_caps* caps);
+
+/* All pointers are device pointers.  boxes: concatenated per image, box_offsets[B+1].
+ * outputs: emptied [B,H,W] u8 ; resized [B,600,w'] u8 (pre-enhance, used for final_node_viz) ;
+ *          enhanced [B,600,w'] u8 (exactly the array the reference returns, incl. its 255->1 mutation) ;
+ *          contours [B,max_contours] ; points [B,max_points,2] i32 ; pairs [B,max_pairs] ; results [B].      */
+int cv_nodes_analyze(const uint8_t* masks, int B, int H, int W, const cv_box* boxes, const int32_t* box_offsets,
+                     int max_boxes_per_image, uint8_t* emptied, uint8_t* resized, uint8_t* enhanced,
+                     cv_contour* contours, int32_t* points, cv_pair* pairs, cv_image_result* results,
+                     const cv_nodes_caps* caps, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Native-resolution connected-component labelling (BASELINE.json cfg 4; SURVEY §8(d): not a reference code
+ * path — oracle is cv2.connectedComponents up to renaming).  labels[p] = 1 + min linear index of p's component,
+ * 0 for background.  connectivity 4 or 8.  n_components[B] optional (may be NULL).                        */
+size_t cv_ccl_workspace_bytes(int B, int H, int W);
+int cv_ccl_label(const uint8_t* masks, int B, int H, int W, int connectivity, int32_t* labels,
+                 int32_t* n_components, void* workspace, size_t workspace_bytes, void* stream);
+/* Number of kernels the last cv_* call on this thread launched (for bench.py's gpu_launches). */
+int cv_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CV_B200_H */
