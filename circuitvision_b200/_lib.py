@@ -53,6 +53,9 @@ def _declare(lib):
     lib.cv_ccl_workspace_bytes.argtypes = [i32, i32, i32]
     lib.cv_ccl_workspace_bytes.restype = sz
     lib.cv_ccl_label.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, sz, vp]
+    lib.cv_profile_enable.argtypes = [i32]
+    lib.cv_profile_get.argtypes = [i32, C.c_char_p, i32, C.POINTER(C.c_longlong), C.POINTER(C.c_double),
+                                   C.POINTER(C.c_double)]
     for name, fn in _OPTIONAL_DECLS.items():
         if hasattr(lib, name):
             fn(getattr(lib, name))
@@ -86,3 +89,15 @@ def require_device(device_index: int = 0):
         raise CvError("circuitvision_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
     if not load().cv_device_is_sm100(device_index):
         raise CvError("circuitvision_b200 kernels are built for sm_100a (B200) only")
+
+
+def profile_table():
+    """[{name, launches, ms, work}] of every kernel timed since the last cv_profile_reset()."""
+    lib = load()
+    out = []
+    for i in range(lib.cv_profile_count()):
+        name = C.create_string_buffer(256)
+        n, ms, w = C.c_longlong(0), C.c_double(0.0), C.c_double(0.0)
+        check(lib.cv_profile_get(i, name, 256, C.byref(n), C.byref(ms), C.byref(w)), "cv_profile_get")
+        out.append(dict(name=name.value.decode(), launches=n.value, ms=ms.value, work=w.value))
+    return out

@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
         list(ex.map(run, jobs))
     if jobs or force or not os.path.exists(LIB):
-        run([NVCC, "-shared", "-o", LIB, *objs, "-lcudart"])
+        run([NVCC, "-shared", "-o", LIB, *objs])  # static cudart (nvcc default)
     return LIB
 
 

@@ -687,13 +687,16 @@ extern "C" int cv_nodes_analyze(const uint8_t* masks, int B, int H, int W, const
     size_t n16 = al ? n_full / 16 : 0;
     size_t want = (n16 + 255) / 256;
     int grid = (int)(want < 1 ? 1 : (want > 148 * 16 ? 148 * 16 : want));
+    cvb_next_work(2.0 * (double)n_full);  // read mask + write emptied
     CVB_LAUNCH(k_copy16, dim3(grid), dim3(256), 0, st, (const uint4*)masks, (uint4*)emptied, n16, masks, emptied, n_full);
     if (max_boxes_per_image > 0 && boxes)
       CVB_LAUNCH(k_zero_boxes, dim3(max_boxes_per_image, B), dim3(256), 0, st, emptied, H, W, boxes, box_offsets);
   }
-  // a13
+  // a13: each destination row reads two source rows (whole 32-byte sectors when down-scaling < 32x) + writes itself
+  cvb_next_work((double)B * h * (2.0 * W + w));
   CVB_LAUNCH(k_resize, dim3((w + 31) / 32, (h + 7) / 8, B), dim3(32, 8), 0, st, emptied, H, W, resized, h, w);
   // a14 + a15 prelude
+  cvb_next_work(2.0 * (double)B * n_small);
   CVB_LAUNCH(k_enhance, dim3((w + ENH_T - 1) / ENH_T, (h + ENH_T - 1) / ENH_T, B), dim3(256), 0, st, resized, ws.enh_raw,
              h, w, ws.sums);
   CVB_LAUNCH(k_binarize, dim3((n_small + 255) / 256, B), dim3(256), 0, st, ws.enh_raw, enhanced, ws.bin, n_small,
@@ -701,8 +704,11 @@ extern "C" int cv_nodes_analyze(const uint8_t* masks, int B, int H, int W, const
   // a15: labelling (8-connected foreground, 4-connected background) -> external components -> borders
   CVB_CHECK(cudaMemsetAsync(ws.frame, 0, (size_t)B * n_small, st));
   dim3 cg((w + 31) / 32, (h + 7) / 8, B), cb(32, 8);
+  cvb_next_work(5.0 * (double)B * n_small);  // 1 B/px mask read + 4 B/px label write
   CVB_LAUNCH((k_ccl_init<0, true>), cg, cb, 0, st, ws.bin, ws.labels, h, w);
+  cvb_next_work(5.0 * (double)B * n_small);
   CVB_LAUNCH((k_ccl_merge<0, true, 8>), cg, cb, 0, st, ws.bin, ws.labels, h, w);
+  cvb_next_work(9.0 * (double)B * n_small);  // mask + label read + label write
   CVB_LAUNCH((k_ccl_flatten<0, true>), dim3((n_small + 255) / 256, B), dim3(256), 0, st, ws.bin, ws.labels, n_small,
              (int*)nullptr);
   CVB_LAUNCH(k_frame_flags, dim3((2 * w + 2 * h + 255) / 256, B), dim3(256), 0, st, ws.bin, ws.labels, ws.frame, h, w);
@@ -745,9 +751,13 @@ extern "C" int cv_ccl_label(const uint8_t* masks, int B, int H, int W, int conne
   int n = H * W;
   if (n_components) CVB_CHECK(cudaMemsetAsync(n_components, 0, (size_t)B * 4, st));
   dim3 cg((W + 31) / 32, (H + 7) / 8, B), cb(32, 8);
+  const double px = (double)B * n;
+  cvb_next_work(5.0 * px);
   CVB_LAUNCH((k_ccl_init<1, false>), cg, cb, 0, st, masks, labels, H, W);
+  cvb_next_work(5.0 * px);
   if (connectivity == 8) CVB_LAUNCH((k_ccl_merge<1, false, 8>), cg, cb, 0, st, masks, labels, H, W);
   else CVB_LAUNCH((k_ccl_merge<1, false, 4>), cg, cb, 0, st, masks, labels, H, W);
+  cvb_next_work(9.0 * px);
   CVB_LAUNCH((k_ccl_flatten<1, false>), dim3((n + 255) / 256, B), dim3(256), 0, st, masks, labels, n, n_components);
   return CV_OK;
 }

@@ -110,6 +110,15 @@ int cv_ccl_label(const uint8_t* masks, int B, int H, int W, int connectivity, in
 /* Number of kernels the last cv_* call on this thread launched (for bench.py's gpu_launches). */
 int cv_last_launch_count(void);
 
+/* Per-kernel device timing for bench.py's roofline line: while enabled, every kernel the library launches is
+ * bracketed by two CUDA events on its own stream.  cv_profile_count() waits for the recorded kernels and returns
+ * the number of distinct kernel names; cv_profile_get(i, ...) returns name, launches, summed milliseconds and
+ * summed algorithmic work (bytes for HBM-bound kernels, flops for tensor kernels; 0 when not annotated). */
+int cv_profile_enable(int on);
+int cv_profile_reset(void);
+int cv_profile_count(void);
+int cv_profile_get(int i, char* name, int name_cap, long long* launches, double* total_ms, double* work);
+
 #ifdef __cplusplus
 }
 #endif

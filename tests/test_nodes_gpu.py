@@ -1,0 +1,153 @@
+"""GPU parity of the node / connection analysis (through the C ABI) against the CPU oracle and against the
+fixtures the unmodified reference produced (tests/golden/node_golden.npz).  Bit-exact: emptied mask, enhanced
+image, node ids, component uid lists, contour vertex arrays."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from circuitvision_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def analyzer():
+    from circuitvision_b200.circuit_analyzer import CircuitAnalyzer
+    return CircuitAnalyzer(use_sam2=False, debug=True, device=0)
+
+
+def _assert_nodes_equal(got, ref, name=""):
+    from oracle.node_oracle import node_signature
+    a, b = node_signature(got), node_signature(ref)
+    assert len(a) == len(b), f"{name}: {len(a)} nodes vs {len(b)}"
+    for (i1, u1, c1), (i2, u2, c2) in zip(a, b):
+        assert i1 == i2, name
+        assert u1 == u2, f"{name}: node {i1} components {u1} vs {u2}"
+        assert np.array_equal(c1, c2), f"{name}: node {i1} contour differs"
+
+
+def test_golden_fixtures_from_unmodified_reference(analyzer, golden, golden_cases):
+    z, meta = golden
+    for name, (mask, boxes) in golden_cases.items():
+        g = meta[name]
+        nodes, emptied, enhanced, cviz, fviz, pviz = analyzer.get_node_connections(None, mask, boxes)
+        assert _sha(emptied) == g["emptied_sha256"], name
+        assert list(enhanced.shape) == g["enhanced_shape"], name
+        assert _sha(enhanced) == g["enhanced_sha256"], name
+        assert len(nodes) == len(g["nodes"]), name
+        for n, gn in zip(nodes, g["nodes"]):
+            assert n["id"] == gn["id"], name
+            assert [c["persistent_uid"] for c in n["components"]] == gn["uids"], name
+            assert [[c["xmin"], c["ymin"], c["xmax"], c["ymax"]] for c in n["components"]] == gn["comp_xyxy"], name
+            assert np.array_equal(n["contour"].reshape(-1, 2), z[f"{name}/contour{gn['id']}"]), name
+            assert n["contour"].dtype == np.int32 and n["contour"].shape[1:] == (1, 2)
+        assert cviz.shape == enhanced.shape + (3,) and fviz.shape == cviz.shape and pviz.shape == cviz.shape
+
+
+def test_oracle_parity_fresh_seeds(analyzer):
+    from oracle import node_oracle
+    for seed in range(100, 112):
+        mask, boxes, _ = synth.make_schematic(seed, 1024)
+        ref_nodes, ref_emp, ref_enh, ref_res, ref_pts = node_oracle.get_node_connections(mask, boxes)
+        nodes, emptied, enhanced, *_ = analyzer.get_node_connections(None, mask, boxes)
+        assert np.array_equal(emptied, ref_emp) and np.array_equal(enhanced, ref_enh), seed
+        _assert_nodes_equal(nodes, ref_nodes, f"seed {seed}")
+
+
+def test_oracle_parity_random_blobs_and_shapes(analyzer):
+    """Hand-drawn-like masks: nested rings, spurs, single pixels, non-square crops, float boxes."""
+    from oracle import node_oracle
+    rng = np.random.default_rng(7)
+    classes = ["resistor", "voltage.dc", "diode", "text", "junction", "terminal", "gnd", "transistor.bjt"]
+    for i, (h, w) in enumerate([(493, 712), (720, 1280), (600, 600), (333, 1000), (1500, 700), (64, 64)]):
+        mask = synth.random_blob_mask(50 + i, h, w, p=0.5, smooth=2 + (i % 3))
+        boxes = []
+        for k in range(14):
+            x0, y0 = float(rng.uniform(-10, w - 20)), float(rng.uniform(-10, h - 20))
+            bw, bh = float(rng.uniform(5, w / 4)), float(rng.uniform(5, h / 4))
+            cls = classes[int(rng.integers(len(classes)))]
+            boxes.append({"class": cls, "xmin": x0, "ymin": y0, "xmax": x0 + bw, "ymax": y0 + bh,
+                          "persistent_uid": f"{cls}_{k % 11}"})  # some duplicate uids
+        ref_nodes, ref_emp, ref_enh, _, _ = node_oracle.get_node_connections(mask, boxes)
+        nodes, emptied, enhanced, *_ = analyzer.get_node_connections(None, mask, boxes)
+        assert np.array_equal(emptied, ref_emp), (h, w)
+        assert np.array_equal(enhanced, ref_enh), (h, w)
+        _assert_nodes_equal(nodes, ref_nodes, f"blob {h}x{w}")
+
+
+def test_batch_equals_stack_of_singles(analyzer):
+    from oracle import node_oracle
+    seeds = list(range(200, 216))
+    masks, boxes = synth.make_batch(seeds, 1024)
+    r = analyzer.get_node_connections_batch(masks, boxes)
+    assert r.launches > 0
+    emp = r.emptied.cpu().numpy()
+    enh = r.enhanced.cpu().numpy()
+    for b, s in enumerate(seeds):
+        ref_nodes, ref_emp, ref_enh, _, ref_pts = node_oracle.get_node_connections(masks[b], boxes[b])
+        assert np.array_equal(emp[b], ref_emp) and np.array_equal(enh[b], ref_enh), s
+        _assert_nodes_equal(r.nodes(b), ref_nodes, f"batch seed {s}")
+        assert r.connection_points(b) == [tuple(p) for p in ref_pts]
+
+
+def test_mask_none_and_input_not_mutated(analyzer):
+    ctx = np.zeros((50, 70, 3), np.uint8)
+    out = analyzer.get_node_connections(ctx, None, [])
+    assert out[0] == [] and all(o.shape == (50, 70, 3) for o in out[1:])
+    mask, boxes, _ = synth.make_schematic(3, 1024)
+    m0 = mask.copy()
+    b0 = [dict(b) for b in boxes]
+    analyzer.get_node_connections(None, mask, boxes)
+    assert np.array_equal(mask, m0) and boxes == b0
+
+
+def test_full_size_4096_properties(analyzer):
+    """BASELINE cfg-4 size: properties that do not need the oracle — idempotence of box masking, emptied is a
+    subset of the mask, every node contour lies on foreground of the enhanced image, ids are 0..n-1."""
+    import torch
+    masks, boxes = synth.make_batch([900, 901], 4096)
+    r = analyzer.get_node_connections_batch(masks, boxes)
+    emp = r.emptied.cpu().numpy()
+    assert ((emp != 0) <= (masks != 0)).all()
+    r2 = analyzer.get_node_connections_batch(emp.copy(), boxes)
+    assert torch.equal(r2.emptied.cpu(), torch.from_numpy(emp))
+    enh = r.enhanced.cpu().numpy()
+    for b in range(2):
+        nodes = r.nodes(b)
+        assert [n["id"] for n in nodes] == list(range(len(nodes)))
+        for n in nodes:
+            pts = n["contour"].reshape(-1, 2)
+            assert (enh[b][pts[:, 1], pts[:, 0]] != 0).all()
+    # oracle on one of them (cv2 finishes a 4096² image in tens of ms)
+    from oracle import node_oracle
+    ref_nodes, ref_emp, ref_enh, _, _ = node_oracle.get_node_connections(masks[0], boxes[0])
+    assert np.array_equal(emp[0], ref_emp) and np.array_equal(enh[0], ref_enh)
+    _assert_nodes_equal(r.nodes(0), ref_nodes, "4096")
+
+
+@pytest.mark.parametrize("conn", [4, 8])
+def test_native_ccl_matches_cv2(conn):
+    import torch
+    from circuitvision_b200.nodes import ccl_label
+    from oracle.node_oracle import ccl_labels_min_index
+    imgs = [synth.random_blob_mask(5, 257, 300, p=0.5, smooth=0), synth.random_blob_mask(6, 257, 300, p=0.55, smooth=2)]
+    d = torch.from_numpy(np.stack(imgs)).cuda()
+    lab, cnt = ccl_label(d, conn)
+    lab = lab.cpu().numpy()
+    for i, m in enumerate(imgs):
+        ref = ccl_labels_min_index(m, conn)
+        assert np.array_equal(lab[i], ref)
+        assert int(cnt[i]) == len(np.unique(ref)) - 1
+    m, _, _ = synth.make_schematic(77, 4096)
+    d = torch.from_numpy(m[None]).cuda()
+    lab, cnt = ccl_label(d, conn)
+    assert np.array_equal(lab[0].cpu().numpy(), ccl_labels_min_index(m, conn))
+    # edge cases: all background / all foreground / single row
+    for arr in (np.zeros((1, 9, 33), np.uint8), np.full((1, 9, 33), 255, np.uint8), np.full((1, 1, 70), 3, np.uint8)):
+        lab, cnt = ccl_label(torch.from_numpy(arr).cuda(), conn)
+        assert np.array_equal(lab[0].cpu().numpy(), ccl_labels_min_index(arr[0], conn))
