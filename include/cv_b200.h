@@ -110,6 +110,15 @@ int cv_ccl_label(const uint8_t* masks, int B, int H, int W, int connectivity, in
 /* Number of kernels the last cv_* call on this thread launched (for bench.py's gpu_launches). */
 int cv_last_launch_count(void);
 
+/* ------------------------------------------------------------------ tensor-core building blocks
+ * bf16 GEMM on tcgen05 + TMA with fp32 accumulation in TMEM:  C[M,N] = act(A[M,K] * W[N,K]^T + bias) + residual.
+ * Replaces every nn.Linear / 1x1 nn.Conv2d on the SAM 2.1 path (sam2_infer.py:226-232,252 via the sam2 package).
+ * A, W: bf16 device pointers with row pitch lda/ldw (elements, multiples of 8); N % 32 == 0; K % 8 == 0.
+ * act: 0 none, 1 exact-erf GELU, 2 ReLU.  out_f32 and/or out_bf16 (either may be NULL, not both).            */
+int cv_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, const float* bias,
+                 int act, const float* residual, long long ld_res, float* out_f32, long long ld_f32, void* out_bf16,
+                 long long ld_bf16, void* stream);
+
 /* Per-kernel device timing for bench.py's roofline line: while enabled, every kernel the library launches is
  * bracketed by two CUDA events on its own stream.  cv_profile_count() waits for the recorded kernels and returns
  * the number of distinct kernel names; cv_profile_get(i, ...) returns name, launches, summed milliseconds and
