@@ -55,6 +55,8 @@ def _declare(lib):
     lib.cv_ccl_label.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, sz, vp]
     ll = C.c_longlong
     lib.cv_gemm_bf16.argtypes = [vp, ll, vp, ll, i32, i32, i32, vp, i32, vp, ll, vp, ll, vp, ll, vp]
+    lib.cv_attention_bf16.argtypes = [vp, ll, i32, i32, vp, ll, i32, i32, vp, ll, i32, i32, i32, i32, i32, i32, i32,
+                                      i32, C.c_float, vp, ll, vp]
     lib.cv_profile_enable.argtypes = [i32]
     lib.cv_profile_get.argtypes = [i32, C.c_char_p, i32, C.POINTER(C.c_longlong), C.POINTER(C.c_double),
                                    C.POINTER(C.c_double)]

@@ -1,0 +1,303 @@
+// Block-diagonal ("windowed") flash attention on tcgen05 + TMA, head_dim 96, bf16 operands, fp32 softmax.
+// One kernel serves every attention of the Hiera trunk: tokens are stored window-major, a query
+// row of window w attends exactly the keys of window w, with Wq query tokens and Wkv key tokens per window
+// (Wq == Wkv for ordinary blocks, Wq = Wkv/4 for Q-pooled blocks, Wq = Wkv = tokens-per-image for global blocks).
+// Zero-pad tokens inside a window are ordinary keys (the reference does not mask them).
+//
+// CTA = one 128-row query tile of one head.  Warp roles: warp0 TMA producer, warp1 MMA issuer (one thread),
+// warp2 TMEM allocator, warps 4-7 softmax (thread = query row).  Per 128-key tile:
+//   S = Q K^T  (tcgen05.mma 128x128x96, S in TMEM)  ->  softmax warps read S, write P (bf16) into shared memory
+//   in the K-major 128B-swizzled layout  ->  O_tile = P V (tcgen05.mma 128x96x128, V consumed MN-major straight
+//   from its row-major tile)  ->  softmax warps fold O_tile into fp32 registers with the online-softmax rescale.
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace cvb {
+
+constexpr int ATT_D = 96;
+constexpr int ATT_BM = 128;
+constexpr int ATT_BN = 128;
+constexpr int ATT_THREADS = 256;
+constexpr int ATT_TILE_BYTES = 2 * ATT_BM * 128;  // two 64-column atoms of 128 rows x 128 B
+constexpr int ATT_SMEM = 1024 + ATT_TILE_BYTES * (1 /*Q*/ + 2 /*K*/ + 2 /*V*/ + 1 /*P*/) + 256;
+
+struct AttnParams {
+  int Mq, Mkv, Wq, Wkv, heads;
+  int qcol0, kcol0, vcol0;  // column of head 0 inside the Q / K / V tensor maps
+  float scale_log2;         // softmax scale * log2(e)
+  __nv_bfloat16* out;       // [Mq, heads*96]
+  long long ld_out;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+k_attn_tc(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+          const __grid_constant__ CUtensorMap tv, AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + ATT_TILE_BYTES;      // [2]
+  uint8_t* sV = sK + 2 * ATT_TILE_BYTES;  // [2]
+  uint8_t* sP = sV + 2 * ATT_TILE_BYTES;
+  uint64_t* bars = (uint64_t*)(sP + ATT_TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_BM;
+  const int head = blockIdx.y;
+  const int r_last = min(q0 + ATT_BM - 1, p.Mq - 1);
+  const int kv_start = (q0 / p.Wq) * p.Wkv;
+  const int kv_end = (r_last / p.Wq + 1) * p.Wkv;
+  const int n_tiles = (kv_end - kv_start + ATT_BN - 1) / ATT_BN;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tq);
+    tc::prefetch_tmap(&tk);
+    tc::prefetch_tmap(&tv);
+  }
+  if (warp == 1 && lane == 0) {
+    tc::mbar_init(q_full, 1);
+    for (int i = 0; i < 2; i++) {
+      tc::mbar_init(&kv_full[i], 1);
+      tc::mbar_init(&kv_empty[i], 1);
+    }
+    tc::mbar_init(s_full, 1);
+    tc::mbar_init(p_full, 4);  // one arrival per softmax warp
+    tc::mbar_init(o_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc<256>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tc::mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
+      tc::tma_load_2d(sQ, &tq, q_full, p.qcol0 + head * ATT_D, q0);
+      tc::tma_load_2d(sQ + ATT_BM * 128, &tq, q_full, p.qcol0 + head * ATT_D + 64, q0);
+      for (int j = 0; j < n_tiles; j++) {
+        int s = j & 1;
+        tc::mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(&kv_full[s], 2 * ATT_TILE_BYTES);
+        int row = kv_start + j * ATT_BN;
+        uint8_t* k = sK + s * ATT_TILE_BYTES;
+        uint8_t* v = sV + s * ATT_TILE_BYTES;
+        tc::tma_load_2d(k, &tk, &kv_full[s], p.kcol0 + head * ATT_D, row);
+        tc::tma_load_2d(k + ATT_BN * 128, &tk, &kv_full[s], p.kcol0 + head * ATT_D + 64, row);
+        tc::tma_load_2d(v, &tv, &kv_full[s], p.vcol0 + head * ATT_D, row);
+        tc::tma_load_2d(v + ATT_BN * 128, &tv, &kv_full[s], p.vcol0 + head * ATT_D + 64, row);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = tc::idesc_bf16(ATT_BM, ATT_BN, false, false);
+      constexpr uint32_t idesc_pv = tc::idesc_bf16(ATT_BM, ATT_D, false, true);  // B = V, MN-major
+      const uint32_t q_addr = tc::smem_u32(sQ), p_addr = tc::smem_u32(sP);
+      auto issue_qk = [&](int j) {
+        uint32_t k_addr = tc::smem_u32(sK + (j & 1) * ATT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; k++) {
+          uint32_t off = (k >> 2) * (ATT_BM * 128) + (k & 3) * 32;
+          tc::mma_f16_ss(tmem_S, tc::desc_kmajor(q_addr + off), tc::desc_kmajor(k_addr + off), idesc_qk, k > 0 ? 1u : 0u);
+        }
+        tc::mma_commit(s_full);
+      };
+      tc::mbar_wait(q_full, 0);
+      tc::mbar_wait(&kv_full[0], 0);
+      tc::tc_fence_after();
+      issue_qk(0);
+      for (int j = 0; j < n_tiles; j++) {
+        tc::mbar_wait(p_full, j & 1);
+        tc::tc_fence_after();
+        uint32_t v_addr = tc::smem_u32(sV + (j & 1) * ATT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < ATT_BN / 16; k++) {
+          // A = P: K-major, 64 keys per atom.  B = V: MN-major, 16 key rows (2048 B) per k-step,
+          // LBO = distance between the two 64-wide d atoms, SBO = 8 key rows.
+          uint64_t a = tc::desc_kmajor(p_addr + (k >> 2) * (ATT_BM * 128) + (k & 3) * 32);
+          uint64_t b = tc::smem_desc_sw128(v_addr + k * 2048, ATT_BN * 128, 1024);
+          tc::mma_f16_ss(tmem_O, a, b, idesc_pv, k > 0 ? 1u : 0u);
+        }
+        tc::mma_commit(o_full);
+        tc::mma_commit(&kv_empty[j & 1]);
+        if (j + 1 < n_tiles) {
+          tc::mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+          tc::tc_fence_after();
+          issue_qk(j + 1);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;  // row inside the tile == TMEM lane
+    const int grow = q0 + r;
+    const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
+    // keys visible to this row: [w*Wkv, (w+1)*Wkv)
+    const long long wq = (long long)(grow / p.Wq);
+    const int vis_lo = (int)(wq * p.Wkv) - kv_start;
+    const int vis_hi = vis_lo + p.Wkv;
+    float m = -INFINITY, l = 0.f, alpha_pending = 0.f;
+    float O[ATT_D];
+#pragma unroll
+    for (int i = 0; i < ATT_D; i++) O[i] = 0.f;
+    uint8_t* prow = sP + r * 128;
+    auto fold_o = [&](float alpha) {
+#pragma unroll
+      for (int c = 0; c < ATT_D / 32; c++) {
+        uint32_t v[32];
+        tc::tmem_ld_32x32(tmem_O + lane_sel + c * 32, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i++) O[c * 32 + i] = O[c * 32 + i] * alpha + __uint_as_float(v[i]);
+      }
+    };
+    for (int j = 0; j < n_tiles; j++) {
+      const int c_lo = vis_lo - j * ATT_BN, c_hi = vis_hi - j * ATT_BN;  // visible columns of this tile
+      const bool full = (c_lo <= 0) && (c_hi >= ATT_BN);
+      tc::mbar_wait(s_full, j & 1);
+      tc::tc_fence_after();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < ATT_BN / 32; c++) {
+        uint32_t v[32];
+        tc::tmem_ld_32x32(tmem_S + lane_sel + c * 32, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          int col = c * 32 + i;
+          float x = __uint_as_float(v[i]) * p.scale_log2;
+          if (!full && (col < c_lo || col >= c_hi)) x = -INFINITY;
+          mx = fmaxf(mx, x);
+        }
+      }
+      const float m_new = fmaxf(m, mx);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = ex2(m - m_use);  // m = -inf -> 0
+      if (j > 0) {
+        tc::mbar_wait(o_full, (j - 1) & 1);  // PV(j-1) finished: O tile valid, P buffer free
+        tc::tc_fence_after();
+        fold_o(alpha_pending);
+      }
+      float rowsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < ATT_BN / 32; c++) {
+        uint32_t v[32];
+        tc::tmem_ld_32x32(tmem_S + lane_sel + c * 32, v);
+        tc::tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          int col = c * 32 + i;
+          float x0 = __uint_as_float(v[i]) * p.scale_log2 - m_use;
+          float x1 = __uint_as_float(v[i + 1]) * p.scale_log2 - m_use;
+          float p0 = ex2(x0), p1 = ex2(x1);
+          if (!full) {
+            if (col < c_lo || col >= c_hi) p0 = 0.f;
+            if (col + 1 < c_lo || col + 1 >= c_hi) p1 = 0.f;
+          }
+          rowsum += p0 + p1;
+          __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
+          pk[i >> 1] = *(uint32_t*)&b;
+        }
+        // 32 columns = 4 chunks of 16 bytes; K-major SW128: atom = col/64, chunk' = chunk ^ (row % 8)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          int col = c * 32 + q * 8;
+          int atom = col >> 6, chunk = (col & 63) >> 3;
+          uint8_t* dst = prow + atom * (ATT_BM * 128) + ((chunk ^ (r & 7)) << 4);
+          *(uint4*)dst = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+        }
+      }
+      l = l * alpha + rowsum;
+      m = m_new;
+      alpha_pending = alpha;
+      tc::fence_proxy_async_smem();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(p_full);
+    }
+    tc::mbar_wait(o_full, (n_tiles - 1) & 1);
+    tc::tc_fence_after();
+    fold_o(alpha_pending);
+    if (grow < p.Mq) {
+      const float inv = 1.f / l;
+      __nv_bfloat16* o = p.out + (long long)grow * p.ld_out + head * ATT_D;
+#pragma unroll
+      for (int i = 0; i < ATT_D; i += 8) {
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          __nv_bfloat162 b = __floats2bfloat162_rn(O[i + 2 * k] * inv, O[i + 2 * k + 1] * inv);
+          w[k] = *(uint32_t*)&b;
+        }
+        *(uint4*)(o + i) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<256>(tmem_base);
+  }
+}
+
+// q/k/v: bf16 matrices [Mq|Mkv, ld*] whose columns [col0 + h*96, col0 + (h+1)*96) hold head h.
+int attn_tc_launch(const __nv_bfloat16* q, long long ldq, int qcols, int qcol0, const __nv_bfloat16* k, long long ldk,
+                   int kcols, int kcol0, const __nv_bfloat16* v, long long ldv, int vcols, int vcol0, int Mq, int Mkv,
+                   int Wq, int Wkv, int heads, float scale, __nv_bfloat16* out, long long ld_out, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_attn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e != cudaSuccess) return cvb_fail_cuda(e, "cudaFuncSetAttribute(k_attn_tc)");
+    attr_set = true;
+  }
+  if (Mq <= 0 || Mkv <= 0 || Wq <= 0 || Wkv <= 0 || heads <= 0) return cvb_fail(CV_ERR_INVALID, "attention: bad sizes");
+  if ((long long)(Mq / Wq) * Wkv > Mkv || (Mq % Wq)) return cvb_fail(CV_ERR_INVALID, "attention: window counts of Q and K/V differ");
+  if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ld_out % 8) || (qcol0 % 8) || (kcol0 % 8) || (vcol0 % 8))
+    return cvb_fail(CV_ERR_INVALID, "attention: pitches / column offsets must be multiples of 8 elements");
+  CUtensorMap tq, tk, tv;
+  if (!tc_host::make_tmap_bf16(&tq, q, (uint64_t)Mq, (uint64_t)qcols, (uint64_t)ldq, ATT_BM) ||
+      !tc_host::make_tmap_bf16(&tk, k, (uint64_t)Mkv, (uint64_t)kcols, (uint64_t)ldk, ATT_BN) ||
+      !tc_host::make_tmap_bf16(&tv, v, (uint64_t)Mkv, (uint64_t)vcols, (uint64_t)ldv, ATT_BN))
+    return cvb_fail(CV_ERR_CUDA, "cuTensorMapEncodeTiled failed (attention operands)");
+  AttnParams p;
+  p.Mq = Mq; p.Mkv = Mkv; p.Wq = Wq; p.Wkv = Wkv; p.heads = heads;
+  p.qcol0 = qcol0; p.kcol0 = kcol0; p.vcol0 = vcol0;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.out = out; p.ld_out = ld_out;
+  // algorithmic flops: every query row against the keys of its own window, QK^T and PV
+  cvb_next_work(4.0 * (double)Mq * (double)Wkv * ATT_D * heads);
+  CVB_LAUNCH(k_attn_tc, dim3((Mq + ATT_BM - 1) / ATT_BM, heads), dim3(ATT_THREADS), ATT_SMEM, st, tq, tk, tv, p);
+  return CV_OK;
+}
+
+}  // namespace cvb
+
+using namespace cvb;
+
+extern "C" int cv_attention_bf16(const void* qkv_q, long long ldq, int qcols, int qcol0, const void* qkv_k,
+                                 long long ldk, int kcols, int kcol0, const void* qkv_v, long long ldv, int vcols,
+                                 int vcol0, int Mq, int Mkv, int Wq, int Wkv, int heads, int head_dim, float scale,
+                                 void* out, long long ld_out, void* stream) {
+  cvb_reset_launches();
+  if (!qkv_q || !qkv_k || !qkv_v || !out) return cvb_fail(CV_ERR_INVALID, "cv_attention_bf16: null pointer");
+  if (head_dim != ATT_D) return cvb_fail(CV_ERR_INVALID, "cv_attention_bf16: only head_dim 96 (SAM 2.1 tiny/small) is built");
+  return attn_tc_launch((const __nv_bfloat16*)qkv_q, ldq, qcols, qcol0, (const __nv_bfloat16*)qkv_k, ldk, kcols, kcol0,
+                        (const __nv_bfloat16*)qkv_v, ldv, vcols, vcol0, Mq, Mkv, Wq, Wkv, heads, scale,
+                        (__nv_bfloat16*)out, ld_out, (cudaStream_t)stream);
+}

@@ -119,6 +119,14 @@ int cv_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int
                  int act, const float* residual, long long ld_res, float* out_f32, long long ld_f32, void* out_bf16,
                  long long ld_bf16, void* stream);
 
+/* Block-diagonal flash attention on tcgen05 (head_dim 96): tokens are window-major; query row i (window i / Wq)
+ * attends the Wkv keys of the same window.  Covers Hiera's windowed, Q-pooled (Wq = Wkv/4) and global
+ * (Wq = Wkv = tokens per image) attention (sam2 package, called from sam2_infer.py:226).  q/k/v are bf16 matrices
+ * with row pitch ld* whose columns [col0 + h*96, col0 + (h+1)*96) hold head h; out is [Mq, heads*96] bf16.     */
+int cv_attention_bf16(const void* q, long long ldq, int qcols, int qcol0, const void* k, long long ldk, int kcols,
+                      int kcol0, const void* v, long long ldv, int vcols, int vcol0, int Mq, int Mkv, int Wq, int Wkv,
+                      int heads, int head_dim, float scale, void* out, long long ld_out, void* stream);
+
 /* Per-kernel device timing for bench.py's roofline line: while enabled, every kernel the library launches is
  * bracketed by two CUDA events on its own stream.  cv_profile_count() waits for the recorded kernels and returns
  * the number of distinct kernel names; cv_profile_get(i, ...) returns name, launches, summed milliseconds and
