@@ -17,6 +17,7 @@ struct GemmEpilogue {
   int res_before_act = 0;            // 0: act(acc+bias)+res   1: act(acc+bias+res)
   const float* res = nullptr;        // fp32 residual, read at the destination row/column
   long long ld_res = 0;
+  long long res_row_mod = 0;         // > 0: residual row = dest row % res_row_mod (per-image broadcast tables)
   float* out_f32 = nullptr;
   long long ld_f32 = 0;
   __nv_bfloat16* out_bf16 = nullptr;
@@ -209,7 +210,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
             }
             int oc = ocol0 + sub_col;
             if (e.res) {
-              float4 r = *(const float4*)(e.res + d * e.ld_res + oc);
+              long long rr = e.res_row_mod > 0 ? d % e.res_row_mod : d;
+              float4 r = *(const float4*)(e.res + rr * e.ld_res + oc);
               x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
             }
             if (e.res_before_act) {

@@ -1,0 +1,966 @@
+// Definitions of the CUDA-core kernels declared in sam2_kernels.cuh.  Reference behaviour: SURVEY.md §B.2/B.3
+// (sam2 package modules as called from /root/reference/src/sam2_infer.py:220-275) and sam2_infer.py:29-189.
+#include "sam2_kernels.cuh"
+
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cvb {
+
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------ im2col
+// One thread per (token, tap-row): writes the 7 taps x 3 channels of kernel row ky.  K index = c*49 + ky*7 + kx
+// (nn.Conv2d weight [Cout, 3, 7, 7] flattened), hi part at [0,PE_K), lo part at [PE_K, 2*PE_K).
+template <bool U8>
+__global__ void __launch_bounds__(256) k_im2col(const void* __restrict__ img_, int B, int S, float m0, float m1, float m2,
+                                                float s0, float s1, float s2, int swap_rb,
+                                                __nv_bfloat16* __restrict__ out) {
+  const int G = S / 4;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * G * G * 8;  // 7 tap rows + 1 padding writer
+  if (idx >= total) return;
+  int ky = (int)(idx & 7);
+  long long tok = idx >> 3;
+  int x = (int)(tok % G);
+  int y = (int)((tok / G) % G);
+  int b = (int)(tok / ((long long)G * G));
+  __nv_bfloat16* o = out + tok * (2 * PE_K);
+  if (ky == 7) {  // zero the K padding 147..151 of both halves
+    for (int k = 147; k < PE_K; k++) { o[k] = __float2bfloat16(0.f); o[PE_K + k] = __float2bfloat16(0.f); }
+    return;
+  }
+  int iy = y * 4 - 3 + ky;
+  const float mean[3] = {m0, m1, m2}, istd[3] = {s0, s1, s2};
+  for (int c = 0; c < 3; c++) {
+    for (int kx = 0; kx < 7; kx++) {
+      int ix = x * 4 - 3 + kx;
+      float v = 0.f;
+      if (iy >= 0 && iy < S && ix >= 0 && ix < S) {
+        if (U8) {
+          const uint8_t* im = (const uint8_t*)img_;
+          int cc = swap_rb ? 2 - c : c;
+          // ToTensor (/255) then Normalize: (p/255 - mean) / std   (sam2_infer.py:41-46)
+          v = ((float)im[(((long long)b * S + iy) * S + ix) * 3 + cc] / 255.0f - mean[c]) * istd[c];
+        } else {
+          const float* im = (const float*)img_;
+          v = im[(((long long)b * 3 + c) * S + iy) * S + ix];
+        }
+      }
+      __nv_bfloat16 hi = __float2bfloat16(v);
+      __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+      int k = c * 49 + ky * 7 + kx;
+      o[k] = hi;
+      o[PE_K + k] = lo;
+    }
+  }
+}
+
+int launch_im2col_u8(const uint8_t* img, int B, int S, const float* mean, const float* inv_std, int swap_rb,
+                     __nv_bfloat16* out, cudaStream_t st) {
+  long long total = (long long)B * (S / 4) * (S / 4) * 8;
+  cvb_next_work((double)B * S * S * 3 + (double)B * (S / 4) * (S / 4) * 2 * PE_K * 2);
+  CVB_LAUNCH((k_im2col<true>), dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, img, B, S, mean[0], mean[1],
+             mean[2], inv_std[0], inv_std[1], inv_std[2], swap_rb, out);
+  return CV_OK;
+}
+int launch_im2col_f32(const float* img, int B, int S, __nv_bfloat16* out, cudaStream_t st) {
+  long long total = (long long)B * (S / 4) * (S / 4) * 8;
+  cvb_next_work((double)B * S * S * 12 + (double)B * (S / 4) * (S / 4) * 2 * PE_K * 2);
+  CVB_LAUNCH((k_im2col<false>), dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, img, B, S, 0.f, 0.f, 0.f, 1.f,
+             1.f, 1.f, 0, out);
+  return CV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ antialias resize
+struct AATap { int lo, n; float center, invscale; };
+__device__ __forceinline__ AATap aa_tap(int i, float scale, int in_size) {
+  // upsample_bilinear2d_aa: support = max(scale, 1), taps [center - support + 0.5, center + support + 0.5)
+  float support = scale >= 1.f ? scale : 1.f;
+  float center = scale * (i + 0.5f);
+  AATap t;
+  t.invscale = scale >= 1.f ? 1.f / scale : 1.f;
+  t.lo = max((int)(center - support + 0.5f), 0);
+  t.n = min((int)(center + support + 0.5f), in_size) - t.lo;
+  t.center = center;
+  return t;
+}
+__device__ __forceinline__ float aa_w(const AATap& t, int j) {
+  float x = fabsf((j + t.lo - t.center + 0.5f) * t.invscale);
+  return x < 1.f ? 1.f - x : 0.f;
+}
+
+__global__ void __launch_bounds__(256) k_aa_width(const uint8_t* __restrict__ img, int H, int W, int S, float scale, int swap_rb,
+                                                  float* __restrict__ tmp) {
+  int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (x >= S || y >= H) return;
+  AATap t = aa_tap(x, scale, W);
+  float tot = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int j = 0; j < t.n; j++) tot += aa_w(t, j);
+  for (int j = 0; j < t.n; j++) {
+    float w = aa_w(t, j) / tot;
+    const uint8_t* p = img + ((long long)y * W + t.lo + j) * 3;
+    a0 += w * ((float)p[swap_rb ? 2 : 0] / 255.0f);
+    a1 += w * ((float)p[1] / 255.0f);
+    a2 += w * ((float)p[swap_rb ? 0 : 2] / 255.0f);
+  }
+  float* o = tmp + ((long long)y * S + x) * 3;
+  o[0] = a0; o[1] = a1; o[2] = a2;
+}
+
+__global__ void __launch_bounds__(256) k_aa_height(const float* __restrict__ tmp, int H, int S, float scale, float m0, float m1,
+                                                   float m2, float s0, float s1, float s2, float* __restrict__ out) {
+  int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (x >= S || y >= S) return;
+  AATap t = aa_tap(y, scale, H);
+  float tot = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int j = 0; j < t.n; j++) tot += aa_w(t, j);
+  for (int j = 0; j < t.n; j++) {
+    float w = aa_w(t, j) / tot;
+    const float* p = tmp + ((long long)(t.lo + j) * S + x) * 3;
+    a0 += w * p[0]; a1 += w * p[1]; a2 += w * p[2];
+  }
+  long long pl = (long long)S * S, o = (long long)y * S + x;
+  out[o] = (a0 - m0) * s0;
+  out[pl + o] = (a1 - m1) * s1;
+  out[2 * pl + o] = (a2 - m2) * s2;
+}
+
+int launch_preprocess_aa(const uint8_t* img, int H, int W, int S, const float* mean, const float* inv_std, int swap_rb,
+                         float* tmp, float* out, cudaStream_t st) {
+  float sx = (float)W / (float)S, sy = (float)H / (float)S;
+  CVB_LAUNCH(k_aa_width, dim3((S + 63) / 64, (H + 3) / 4), dim3(256), 0, st, img, H, W, S, sx, swap_rb, tmp);
+  CVB_LAUNCH(k_aa_height, dim3((S + 63) / 64, (S + 3) / 4), dim3(256), 0, st, tmp, H, S, sy, mean[0], mean[1], mean[2],
+             inv_std[0], inv_std[1], inv_std[2], out);
+  return CV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm rows
+// One warp per destination row.  C % 4 == 0, C <= 1536.
+__global__ void __launch_bounds__(256) k_ln_rows(const float* __restrict__ X, int C, const float* __restrict__ gamma,
+                                                 const float* __restrict__ beta, float eps, int H, int W, int ws,
+                                                 int nwx, int nwy, long long n_dst, __nv_bfloat16* __restrict__ ob,
+                                                 float* __restrict__ of) {
+  long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= n_dst) return;
+  int lane = threadIdx.x & 31;
+  long long src = r;
+  if (ws > 0) {
+    int w2 = ws * ws;
+    long long win = r / w2;
+    int t = (int)(r - win * w2);
+    int per = nwx * nwy;
+    long long b = win / per;
+    int wi = (int)(win - b * per);
+    int wy = wi / nwx, wx = wi - wy * nwx;
+    int ty = t / ws, tx = t - ty * ws;
+    int y = wy * ws + ty, x = wx * ws + tx;
+    src = (y < H && x < W) ? (b * H + y) * W + x : -1;
+  }
+  const int nv = C >> 2;  // float4 per row
+  if (src < 0) {
+    for (int i = lane; i < nv; i += 32) {
+      if (ob) *(uint2*)(ob + r * C + i * 4) = make_uint2(0u, 0u);
+      if (of) *(float4*)(of + r * C + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return;
+  }
+  float4 v[12];
+  const float4* xr = (const float4*)(X + src * C);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 12; k++) {
+    int i = lane + k * 32;
+    if (i < nv) {
+      v[k] = xr[i];
+      s += v[k].x + v[k].y + v[k].z + v[k].w;
+    }
+  }
+  float mean = 0.f, rstd = 1.f;
+  if (gamma) {
+    mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+      int i = lane + k * 32;
+      if (i < nv) {
+        float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+        q += a * a + b * b + c * c + d * d;
+      }
+    }
+    rstd = rsqrtf(warp_sum(q) / C + eps);
+  }
+#pragma unroll
+  for (int k = 0; k < 12; k++) {
+    int i = lane + k * 32;
+    if (i < nv) {
+      float4 o = v[k];
+      if (gamma) {
+        float4 g = ((const float4*)gamma)[i], bb = ((const float4*)beta)[i];
+        o.x = (o.x - mean) * rstd * g.x + bb.x;
+        o.y = (o.y - mean) * rstd * g.y + bb.y;
+        o.z = (o.z - mean) * rstd * g.z + bb.z;
+        o.w = (o.w - mean) * rstd * g.w + bb.w;
+      }
+      if (of) *(float4*)(of + r * C + i * 4) = o;
+      if (ob) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        *(uint2*)(ob + r * C + i * 4) = make_uint2(*(uint32_t*)&lo, *(uint32_t*)&hi);
+      }
+    }
+  }
+}
+
+int launch_ln_rows(const float* X, long long n_src_rows, int C, const float* gamma, const float* beta, float eps, int B,
+                   int H, int W, int ws, __nv_bfloat16* out_bf16, float* out_f32, cudaStream_t st) {
+  if ((C & 3) || C > 1536) return cvb_fail(CV_ERR_INVALID, "ln_rows: C must be a multiple of 4 and <= 1536");
+  int nwx = 0, nwy = 0;
+  long long n_dst = n_src_rows;
+  if (ws > 0) {
+    nwx = (W + ws - 1) / ws;
+    nwy = (H + ws - 1) / ws;
+    n_dst = (long long)B * nwx * nwy * ws * ws;
+  }
+  cvb_next_work((double)n_src_rows * C * 4 + (double)n_dst * C * (out_bf16 ? 2 : 0) + (double)n_dst * C * (out_f32 ? 4 : 0));
+  CVB_LAUNCH(k_ln_rows, dim3((unsigned)((n_dst + 7) / 8)), dim3(256), 0, st, X, C, gamma, beta, eps, H, W, ws, nwx, nwy,
+             n_dst, out_bf16, out_f32);
+  return CV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ pooling
+__global__ void __launch_bounds__(256) k_pool_q(const __nv_bfloat16* __restrict__ qkv, long long ld, int ws, int Cq,
+                                                long long n_dst, __nv_bfloat16* __restrict__ qp) {
+  const int chunks = Cq >> 3;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_dst * chunks) return;
+  long long r = idx / chunks;
+  int c = (int)(idx - r * chunks) * 8;
+  int hw = ws >> 1, h2 = hw * hw;
+  long long win = r / h2;
+  int t = (int)(r - win * h2);
+  int py = t / hw, px = t - py * hw;
+  long long base = win * ws * ws;
+  __nv_bfloat162 m[4];
+  bool first = true;
+  for (int dy = 0; dy < 2; dy++)
+    for (int dx = 0; dx < 2; dx++) {
+      long long sr = base + (2 * py + dy) * ws + 2 * px + dx;
+      uint4 u = *(const uint4*)(qkv + sr * ld + c);
+      const __nv_bfloat162* p = (const __nv_bfloat162*)&u;
+      for (int k = 0; k < 4; k++) m[k] = first ? p[k] : __hmax2(m[k], p[k]);
+      first = false;
+    }
+  *(uint4*)(qp + r * Cq + c) = *(uint4*)m;
+}
+
+int launch_pool_q(const __nv_bfloat16* qkv, long long ld, int n_windows, int ws, int Cq, __nv_bfloat16* qp,
+                  cudaStream_t st) {
+  if ((ws & 1) || (Cq & 7)) return cvb_fail(CV_ERR_INVALID, "pool_q: odd window or Cq%8 != 0");
+  long long n_dst = (long long)n_windows * (ws / 2) * (ws / 2);
+  long long total = n_dst * (Cq / 8);
+  cvb_next_work((double)n_dst * Cq * 2 * 5);
+  CVB_LAUNCH(k_pool_q, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, qkv, ld, ws, Cq, n_dst, qp);
+  return CV_OK;
+}
+
+__global__ void __launch_bounds__(256) k_pool_shortcut(const float* __restrict__ S, int H, int W, int ws, int nwx, int nwy,
+                                                       int C, long long n_dst, float* __restrict__ R) {
+  const int chunks = C >> 2;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_dst * chunks) return;
+  long long r = idx / chunks;
+  int c = (int)(idx - r * chunks) * 4;
+  int H2 = H >> 1, W2 = W >> 1;
+  int x2 = (int)(r % W2);
+  int y2 = (int)((r / W2) % H2);
+  long long b = r / ((long long)W2 * H2);
+  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  for (int dy = 0; dy < 2; dy++)
+    for (int dx = 0; dx < 2; dx++) {
+      int y = 2 * y2 + dy, x = 2 * x2 + dx;
+      int wy = y / ws, ty = y - wy * ws, wx = x / ws, tx = x - wx * ws;
+      long long sr = ((b * nwy + wy) * nwx + wx) * (long long)(ws * ws) + ty * ws + tx;
+      float4 v = *(const float4*)(S + sr * C + c);
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+  *(float4*)(R + r * C + c) = m;
+}
+
+int launch_pool_shortcut(const float* S, int B, int H, int W, int ws, int C, float* R, cudaStream_t st) {
+  int nwx = (W + ws - 1) / ws, nwy = (H + ws - 1) / ws;
+  long long n_dst = (long long)B * (H / 2) * (W / 2);
+  long long total = n_dst * (C / 4);
+  cvb_next_work((double)n_dst * C * 4 * 5);
+  CVB_LAUNCH(k_pool_shortcut, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, S, H, W, ws, nwx, nwy, C, n_dst, R);
+  return CV_OK;
+}
+
+__global__ void __launch_bounds__(256) k_add_nearest2(float* __restrict__ Y, const float* __restrict__ L, int H, int W,
+                                                      int C, long long total) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int chunks = C >> 2;
+  long long r = idx / chunks;
+  int c = (int)(idx - r * chunks) * 4;
+  int x = (int)(r % W), y = (int)((r / W) % H);
+  long long b = r / ((long long)W * H);
+  long long lr = (b * (H / 2) + y / 2) * (W / 2) + x / 2;
+  float4 a = *(float4*)(Y + r * C + c);
+  float4 l = *(const float4*)(L + lr * C + c);
+  a.x += l.x; a.y += l.y; a.z += l.z; a.w += l.w;
+  *(float4*)(Y + r * C + c) = a;
+}
+
+int launch_add_nearest2(float* Y, const float* L, int B, int H, int W, int C, cudaStream_t st) {
+  long long total = (long long)B * H * W * (C / 4);
+  cvb_next_work((double)B * H * W * C * 4 * 2.25);
+  CVB_LAUNCH(k_add_nearest2, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, Y, L, H, W, C, total);
+  return CV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ token-side linear (fp32)
+// 64 x 64 output tile per CTA, 16 x 16 threads, 4 x 4 micro-tile, K tiles of 16.
+__global__ void __launch_bounds__(256) k_tok_linear(const float* __restrict__ A, long long lda, const float* __restrict__ Wt,
+                                                    const float* __restrict__ bias, int R, int N, int K, int act,
+                                                    const float* __restrict__ res, long long ld_res, float* __restrict__ Cm,
+                                                    long long ldc) {
+  __shared__ float sA[16][64 + 1];
+  __shared__ float sW[16][64 + 1];
+  int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  int r0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      int rr = i >> 4, kk = i & 15;
+      int gr = r0 + rr, gk = k0 + kk;
+      sA[kk][rr] = (gr < R && gk < K) ? A[(long long)gr * lda + gk] : 0.f;
+      int gn = n0 + rr;
+      sW[kk][rr] = (gn < N && gk < K) ? Wt[(long long)gn * K + gk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; kk++) {
+      float a[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) { a[i] = sA[kk][ty * 4 + i]; w[i] = sW[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  for (int i = 0; i < 4; i++) {
+    int gr = r0 + ty * 4 + i;
+    if (gr >= R) continue;
+    for (int j = 0; j < 4; j++) {
+      int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float x = acc[i][j] + (bias ? bias[gn] : 0.f);
+      if (act == 1) x = gelu_exact(x);
+      else if (act == 2) x = fmaxf(x, 0.f);
+      else if (act == 3) x = 1.f / (1.f + expf(-x));
+      if (res) x += res[(long long)gr * ld_res + gn];
+      Cm[(long long)gr * ldc + gn] = x;
+    }
+  }
+}
+
+int launch_tok_linear(const float* A, long long lda, const float* W, const float* bias, int R, int N, int K, int act,
+                      const float* res, long long ld_res, float* C, long long ldc, cudaStream_t st) {
+  cvb_next_work(2.0 * R * (double)N * K);
+  CVB_LAUNCH(k_tok_linear, dim3((N + 63) / 64, (R + 63) / 64), dim3(256), 0, st, A, lda, W, bias, R, N, K, act, res, ld_res,
+             C, ldc);
+  return CV_OK;
+}
+
+// Y = LN(X + add) * g + b ; one warp per row, C % 32 == 0, C <= 512
+__global__ void __launch_bounds__(256) k_tok_add_ln(const float* __restrict__ X, const float* __restrict__ add, int mod,
+                                                    const float* __restrict__ g, const float* __restrict__ b, float eps,
+                                                    int R, int C, float* __restrict__ Y) {
+  int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= R) return;
+  int lane = threadIdx.x & 31;
+  float v[16];
+  int n = C >> 5;
+  float s = 0.f;
+  for (int k = 0; k < n; k++) {
+    int c = lane + k * 32;
+    float x = X[(long long)r * C + c];
+    if (add) x += add[(long long)(mod > 0 ? r % mod : r) * C + c];
+    v[k] = x;
+    s += x;
+  }
+  float mean = warp_sum(s) / C, q = 0.f;
+  for (int k = 0; k < n; k++) { float d = v[k] - mean; q += d * d; }
+  float rstd = rsqrtf(warp_sum(q) / C + eps);
+  for (int k = 0; k < n; k++) {
+    int c = lane + k * 32;
+    Y[(long long)r * C + c] = (v[k] - mean) * rstd * g[c] + b[c];
+  }
+}
+
+int launch_tok_add_ln(const float* X, const float* add, int add_rows_mod, const float* g, const float* b, float eps, int R,
+                      int C, float* Y, cudaStream_t st) {
+  if ((C & 31) || C > 512) return cvb_fail(CV_ERR_INVALID, "tok_add_ln: C%32 / C<=512");
+  CVB_LAUNCH(k_tok_add_ln, dim3((R + 7) / 8), dim3(256), 0, st, X, add, add_rows_mod, g, b, eps, R, C, Y);
+  return CV_OK;
+}
+
+__global__ void k_tok_add_bcast(const float* __restrict__ X, const float* __restrict__ P, int mod, long long total, int C,
+                                float* __restrict__ Y) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  long long r = i / C;
+  int c = (int)(i - r * C);
+  Y[i] = X[i] + P[(r % mod) * C + c];
+}
+
+int launch_tok_add_bcast(const float* X, const float* P, int mod, int R, int C, float* Y, cudaStream_t st) {
+  long long total = (long long)R * C;
+  CVB_LAUNCH(k_tok_add_bcast, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, X, P, mod, total, C, Y);
+  return CV_OK;
+}
+
+// self attention among T (<= 64) tokens: one CTA per (image, head), 64 threads, thread = query
+__global__ void __launch_bounds__(64) k_tok_self_attn(const float* __restrict__ q, const float* __restrict__ k,
+                                                      const float* __restrict__ v, int T, int heads, int d,
+                                                      float* __restrict__ out) {
+  __shared__ float sk[64][33], sv[64][33];
+  int b = blockIdx.x, h = blockIdx.y, t = threadIdx.x;
+  int C = heads * d;
+  for (int i = threadIdx.x; i < T * d; i += 64) {
+    int tt = i / d, dd = i - tt * d;
+    sk[tt][dd] = k[((long long)b * T + tt) * C + h * d + dd];
+    sv[tt][dd] = v[((long long)b * T + tt) * C + h * d + dd];
+  }
+  __syncthreads();
+  if (t >= T) return;
+  float qv[32];
+  for (int i = 0; i < d; i++) qv[i] = q[((long long)b * T + t) * C + h * d + i];
+  float sc[64];
+  float mx = -INFINITY, scale = rsqrtf((float)d);
+  for (int j = 0; j < T; j++) {
+    float s = 0.f;
+    for (int i = 0; i < d; i++) s = fmaf(qv[i], sk[j][i], s);
+    s *= scale;
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  float l = 0.f;
+  for (int j = 0; j < T; j++) { sc[j] = expf(sc[j] - mx); l += sc[j]; }
+  float inv = 1.f / l;
+  for (int i = 0; i < d; i++) {
+    float o = 0.f;
+    for (int j = 0; j < T; j++) o = fmaf(sc[j], sv[j][i], o);
+    out[((long long)b * T + t) * C + h * d + i] = o * inv;
+  }
+}
+
+int launch_tok_self_attn(const float* q, const float* k, const float* v, int B, int T, int heads, int d, float* out,
+                         cudaStream_t st) {
+  if (T > 64 || d > 32) return cvb_fail(CV_ERR_INVALID, "tok_self_attn: T<=64, d<=32");
+  CVB_LAUNCH(k_tok_self_attn, dim3(B, heads), dim3(64), 0, st, q, k, v, T, heads, d, out);
+  return CV_OK;
+}
+
+// tokens -> image attention, d == 16.  CTA = (key split, head, image): stages its 256 keys/values in shared memory;
+// each warp walks a subset of the T queries and emits a partial (max, sum, O[16]) per (query, split).
+constexpr int T2I_SPLIT_KEYS = 256;
+constexpr int T2I_LD = 20;  // padded row (floats): conflict-free float4 reads
+__global__ void __launch_bounds__(128) k_attn_t2i_part(const float* __restrict__ q, long long q_img_stride,
+                                                       const float* __restrict__ K, const float* __restrict__ V,
+                                                       long long ld_kv, int T, int Nk, int heads, float* __restrict__ part) {
+  __shared__ float sk[T2I_SPLIT_KEYS * T2I_LD];
+  __shared__ float sv[T2I_SPLIT_KEYS * T2I_LD];
+  const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int nsplit = gridDim.x;
+  const int k0 = split * T2I_SPLIT_KEYS;
+  const int nk = min(T2I_SPLIT_KEYS, Nk - k0);
+  for (int i = threadIdx.x; i < nk * 4; i += 128) {
+    int j = i >> 2, c = (i & 3) * 4;
+    long long row = (long long)b * Nk + k0 + j;
+    *(float4*)(sk + j * T2I_LD + c) = *(const float4*)(K + row * ld_kv + h * 16 + c);
+    *(float4*)(sv + j * T2I_LD + c) = *(const float4*)(V + row * ld_kv + h * 16 + c);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = heads * 16;
+  for (int t = warp; t < T; t += 4) {
+    const float* qp = q + (long long)b * q_img_stride + (long long)t * C + h * 16;
+    float qv[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) qv[i] = __ldg(qp + i) * 0.25f;  // 1/sqrt(16)
+    float sc[T2I_SPLIT_KEYS / 32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < T2I_SPLIT_KEYS / 32; u++) {
+      int j = lane + u * 32;
+      float s = -INFINITY;
+      if (j < nk) {
+        s = 0.f;
+        const float4* kr = (const float4*)(sk + j * T2I_LD);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          float4 kk = kr[c];
+          s = fmaf(qv[c * 4], kk.x, s); s = fmaf(qv[c * 4 + 1], kk.y, s);
+          s = fmaf(qv[c * 4 + 2], kk.z, s); s = fmaf(qv[c * 4 + 3], kk.w, s);
+        }
+      }
+      sc[u] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float l = 0.f, o[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) o[i] = 0.f;
+#pragma unroll
+    for (int u = 0; u < T2I_SPLIT_KEYS / 32; u++) {
+      int j = lane + u * 32;
+      if (j < nk) {
+        float pexp = expf(sc[u] - mx);
+        l += pexp;
+        const float4* vr = (const float4*)(sv + j * T2I_LD);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          float4 vv = vr[c];
+          o[c * 4] = fmaf(pexp, vv.x, o[c * 4]); o[c * 4 + 1] = fmaf(pexp, vv.y, o[c * 4 + 1]);
+          o[c * 4 + 2] = fmaf(pexp, vv.z, o[c * 4 + 2]); o[c * 4 + 3] = fmaf(pexp, vv.w, o[c * 4 + 3]);
+        }
+      }
+    }
+    l = warp_sum(l);
+#pragma unroll
+    for (int i = 0; i < 16; i++) o[i] = warp_sum(o[i]);
+    if (lane == 0) {
+      float* p = part + ((((long long)b * heads + h) * T + t) * nsplit + split) * 18;
+      p[0] = mx;
+      p[1] = l;
+#pragma unroll
+      for (int i = 0; i < 16; i++) p[2 + i] = o[i];
+    }
+  }
+}
+
+__global__ void k_attn_t2i_combine(const float* __restrict__ part, int T, int heads, int nsplit, long long total,
+                                   float* __restrict__ out) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (b, h, t, i)
+  if (idx >= total) return;
+  int i = (int)(idx & 15);
+  long long bht = idx >> 4;
+  int t = (int)(bht % T);
+  int h = (int)((bht / T) % heads);
+  long long b = bht / ((long long)T * heads);
+  const float* p = part + bht * nsplit * 18;
+  float mx = -INFINITY;
+  for (int s = 0; s < nsplit; s++) mx = fmaxf(mx, p[s * 18]);
+  float l = 0.f, o = 0.f;
+  for (int s = 0; s < nsplit; s++) {
+    float w = expf(p[s * 18] - mx);
+    l += w * p[s * 18 + 1];
+    o += w * p[s * 18 + 2 + i];
+  }
+  out[(b * T + t) * (heads * 16) + h * 16 + i] = o / l;
+}
+
+size_t attn_t2i_scratch_floats(int B, int T, int heads, int d) {
+  (void)d;
+  return (size_t)B * heads * T * 16 * 18 + 64;
+}
+
+int launch_attn_t2i(const float* q, long long q_img_stride, const float* K, const float* V, long long ld_kv, int B, int T,
+                    int Nk, int heads, int d, float* out, float* scratch, cudaStream_t st) {
+  if (d != 16) return cvb_fail(CV_ERR_INVALID, "attn_t2i: head dim must be 16");
+  int nsplit = (Nk + T2I_SPLIT_KEYS - 1) / T2I_SPLIT_KEYS;
+  if (nsplit > 16) return cvb_fail(CV_ERR_INVALID, "attn_t2i: at most 4096 keys");
+  cvb_next_work(4.0 * B * (double)T * Nk * heads * d);
+  CVB_LAUNCH(k_attn_t2i_part, dim3(nsplit, heads, B), dim3(128), 0, st, q, q_img_stride, K, V, ld_kv, T, Nk, heads, scratch);
+  long long total = (long long)B * heads * T * 16;
+  CVB_LAUNCH(k_attn_t2i_combine, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, scratch, T, heads, nsplit, total,
+             out);
+  return CV_OK;
+}
+
+// image -> tokens attention, d == 16, T <= 64: thread = (query token, head); K/V of the image's tokens in smem
+__global__ void __launch_bounds__(256) k_attn_i2t(const float* __restrict__ Q, long long ld_q, const float* __restrict__ K,
+                                                  const float* __restrict__ V, int Nq, int T, int heads,
+                                                  __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float sm[];
+  const int C = heads * 16;
+  float* sk = sm;
+  float* sv = sm + T * C;
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < T * C; i += 256) {
+    sk[i] = K[(long long)b * T * C + i];
+    sv[i] = V[(long long)b * T * C + i];
+  }
+  __syncthreads();
+  const int per = 256 / heads;
+  const int h = threadIdx.x % heads;
+  const int tq = blockIdx.x * per + threadIdx.x / heads;
+  if (tq >= Nq) return;
+  long long row = (long long)b * Nq + tq;
+  float qv[16];
+  const float4* qp = (const float4*)(Q + row * ld_q + h * 16);
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    float4 x = qp[c];
+    qv[c * 4] = x.x * 0.25f; qv[c * 4 + 1] = x.y * 0.25f; qv[c * 4 + 2] = x.z * 0.25f; qv[c * 4 + 3] = x.w * 0.25f;
+  }
+  float sc[64];
+  float mx = -INFINITY;
+  for (int j = 0; j < T; j++) {
+    const float* kr = sk + j * C + h * 16;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s = fmaf(qv[i], kr[i], s);
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  float l = 0.f, o[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) o[i] = 0.f;
+  for (int j = 0; j < T; j++) {
+    float pexp = expf(sc[j] - mx);
+    l += pexp;
+    const float* vr = sv + j * C + h * 16;
+#pragma unroll
+    for (int i = 0; i < 16; i++) o[i] = fmaf(pexp, vr[i], o[i]);
+  }
+  float inv = 1.f / l;
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(o[2 * i] * inv, o[2 * i + 1] * inv);
+    w[i] = *(uint32_t*)&p2;
+  }
+  uint4* dst = (uint4*)(out + row * C + h * 16);
+  dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+int launch_attn_i2t(const float* Q, long long ld_q, const float* K, const float* V, int B, int Nq, int T, int heads, int d,
+                    __nv_bfloat16* out, cudaStream_t st) {
+  if (d != 16 || T > 64 || (256 % heads)) return cvb_fail(CV_ERR_INVALID, "attn_i2t: d==16, T<=64, 256%heads==0");
+  int per = 256 / heads;
+  size_t smem = (size_t)2 * T * heads * 16 * sizeof(float);
+  cvb_next_work(4.0 * B * (double)T * Nq * heads * d);
+  CVB_LAUNCH(k_attn_i2t, dim3((Nq + per - 1) / per, B), dim3(256), smem, st, Q, ld_q, K, V, Nq, T, heads, out);
+  return CV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm2d + GELU (C == 64)
+__global__ void __launch_bounds__(256) k_ln2d_gelu(const float* __restrict__ X, long long rows, const float* __restrict__ g,
+                                                   const float* __restrict__ b, float eps, __nv_bfloat16* __restrict__ out) {
+  // 16 lanes per row (float4 each), 2 rows per warp
+  long long r = ((long long)blockIdx.x * 256 + threadIdx.x) >> 4;
+  int l = threadIdx.x & 15;
+  bool ok = r < rows;
+  float4 v = ok ? *(const float4*)(X + r * 64 + l * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float s = v.x + v.y + v.z + v.w;
+  for (int o = 8; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  float mean = s * (1.f / 64.f);
+  float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
+  float q = a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+  for (int o = 8; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  // LayerNorm2d (sam2): (x - u) / sqrt(var + eps) * w + b
+  float rstd = 1.f / sqrtf(q * (1.f / 64.f) + eps);
+  if (!ok) return;
+  float4 gg = ((const float4*)g)[l], bb = ((const float4*)b)[l];
+  float y0 = gelu_exact(a0 * rstd * gg.x + bb.x), y1 = gelu_exact(a1 * rstd * gg.y + bb.y);
+  float y2 = gelu_exact(a2 * rstd * gg.z + bb.z), y3 = gelu_exact(a3 * rstd * gg.w + bb.w);
+  __nv_bfloat162 lo = __floats2bfloat162_rn(y0, y1), hi = __floats2bfloat162_rn(y2, y3);
+  *(uint2*)(out + r * 64 + l * 4) = make_uint2(*(uint32_t*)&lo, *(uint32_t*)&hi);
+}
+
+int launch_ln2d_gelu(const float* X, long long rows, int C, const float* g, const float* b, float eps,
+                     __nv_bfloat16* out, cudaStream_t st) {
+  if (C != 64) return cvb_fail(CV_ERR_INVALID, "ln2d_gelu: C must be 64");
+  cvb_next_work((double)rows * 64 * 6);
+  CVB_LAUNCH(k_ln2d_gelu, dim3((unsigned)((rows * 16 + 255) / 256)), dim3(256), 0, st, X, rows, g, b, eps, out);
+  return CV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ mask product
+__global__ void __launch_bounds__(256) k_mask_product(const float* __restrict__ U, const float* __restrict__ hyper, int P,
+                                                      float delta, float* __restrict__ masks, unsigned int* __restrict__ counts) {
+  __shared__ float sh[4 * 32];
+  int b = blockIdx.y;
+  if (threadIdx.x < 128) sh[threadIdx.x] = hyper[(long long)b * 128 + threadIdx.x];
+  __syncthreads();
+  int p = blockIdx.x * 256 + threadIdx.x;
+  unsigned ci = 0, cu = 0;
+  if (p < P) {
+    const float4* u = (const float4*)(U + ((long long)b * P + p) * 32);
+    float m[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      float4 x = u[c];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float* hk = sh + k * 32 + c * 4;
+        m[k] = fmaf(hk[0], x.x, m[k]); m[k] = fmaf(hk[1], x.y, m[k]);
+        m[k] = fmaf(hk[2], x.z, m[k]); m[k] = fmaf(hk[3], x.w, m[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) masks[((long long)b * 4 + k) * P + p] = m[k];
+    ci = m[0] > delta;
+    cu = m[0] > -delta;
+  }
+  unsigned bi = __ballot_sync(0xffffffffu, ci), bu = __ballot_sync(0xffffffffu, cu);
+  if ((threadIdx.x & 31) == 0) {
+    if (bi) atomicAdd(counts + 2 * b, __popc(bi));
+    if (bu) atomicAdd(counts + 2 * b + 1, __popc(bu));
+  }
+}
+
+int launch_mask_product(const float* U, const float* hyper, int B, int P, float delta, float* masks, unsigned int* counts,
+                        cudaStream_t st) {
+  CVB_CHECK(cudaMemsetAsync(counts, 0, (size_t)B * 2 * sizeof(unsigned int), st));
+  cvb_next_work((double)B * P * (32 + 4) * 4);
+  CVB_LAUNCH(k_mask_product, dim3((P + 255) / 256, B), dim3(256), 0, st, U, hyper, P, delta, masks, counts);
+  return CV_OK;
+}
+
+__global__ void __launch_bounds__(256) k_select_mask(const float* __restrict__ masks, const float* __restrict__ iou,
+                                                     const unsigned int* __restrict__ counts, int P, float thresh,
+                                                     float* __restrict__ low, float* __restrict__ iou_out, int* __restrict__ sel) {
+  int b = blockIdx.y;
+  // stability = area_i / area_u (1 when area_u == 0); stable -> token 0, else best-IoU of tokens 1..3 (first max)
+  float ai = (float)counts[2 * b], au = (float)counts[2 * b + 1];
+  float stab = au > 0.f ? ai / au : 1.f;
+  int s = 0;
+  if (!(stab >= thresh)) {
+    const float* io = iou + b * 4;
+    s = 1;
+    if (io[2] > io[s]) s = 2;
+    if (io[3] > io[s]) s = 3;
+  }
+  int p = blockIdx.x * 256 + threadIdx.x;
+  if (p < P) low[(long long)b * P + p] = masks[((long long)b * 4 + s) * P + p];
+  if (p == 0) { iou_out[b] = iou[b * 4 + s]; sel[b] = s; }
+}
+
+int launch_select_mask(const float* masks, const float* iou, const unsigned int* counts, int B, int P, float thresh,
+                       float* low_res, float* iou_out, int* sel, cudaStream_t st) {
+  CVB_LAUNCH(k_select_mask, dim3((P + 255) / 256, B), dim3(256), 0, st, masks, iou, counts, P, thresh, low_res, iou_out, sel);
+  return CV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ tail
+// CTA = 32 x 32 output pixels.  up[42][44]: bilinearly upsampled logits of the tile + halo 5 (zero outside the
+// 1024^2 image: Conv2d padding='same' pads the upsampled map with zeros).  Thread = 4 consecutive pixels of a row.
+constexpr int TL = 32, THALO = 5, TUP = TL + 2 * THALO;
+struct TailConst {
+  float w3[4 * 9], w5[4 * 25], w7[4 * 49], w11[4 * 121];
+  float b[16], cw[16], cb;
+};
+
+__global__ void __launch_bounds__(256) k_tail(const float* __restrict__ low, int src_full, RefineWeights rw, float* __restrict__ high,
+                                              uint8_t* __restrict__ mask, int* __restrict__ extents) {
+  __shared__ float up[TUP][TUP + 2];
+  __shared__ TailConst tc_;
+  const int S = 1024, LS = 256;
+  const int b = blockIdx.z;
+  const int X0 = blockIdx.x * TL, Y0 = blockIdx.y * TL;
+  const float* lo = low + (long long)b * (src_full ? S * S : LS * LS);
+  if (rw.use_refine) {
+    for (int i = threadIdx.x; i < 4 * 9; i += 256) tc_.w3[i] = rw.w[0][i];
+    for (int i = threadIdx.x; i < 4 * 25; i += 256) tc_.w5[i] = rw.w[1][i];
+    for (int i = threadIdx.x; i < 4 * 49; i += 256) tc_.w7[i] = rw.w[2][i];
+    for (int i = threadIdx.x; i < 4 * 121; i += 256) tc_.w11[i] = rw.w[3][i];
+    if (threadIdx.x < 16) {
+      tc_.b[threadIdx.x] = rw.b[threadIdx.x >> 2][threadIdx.x & 3];
+      tc_.cw[threadIdx.x] = rw.cw[threadIdx.x];
+    }
+    if (threadIdx.x == 0) tc_.cb = rw.cb;
+  }
+  for (int i = threadIdx.x; i < TUP * TUP; i += 256) {
+    int uy = i / TUP, ux = i - uy * TUP;
+    int Y = Y0 - THALO + uy, X = X0 - THALO + ux;
+    float v = 0.f;
+    if (Y >= 0 && Y < S && X >= 0 && X < S && src_full) {
+      v = lo[Y * S + X];
+    } else if (Y >= 0 && Y < S && X >= 0 && X < S) {
+      // F.interpolate(bilinear, align_corners=False): src = max(0, (dst + 0.5) * 0.25 - 0.5)
+      float sy = fmaxf(0.f, (Y + 0.5f) * 0.25f - 0.5f), sx = fmaxf(0.f, (X + 0.5f) * 0.25f - 0.5f);
+      int y0 = (int)sy, x0 = (int)sx;
+      int y1 = y0 + (y0 < LS - 1 ? 1 : 0), x1 = x0 + (x0 < LS - 1 ? 1 : 0);
+      float ly = sy - y0, lx = sx - x0;
+      float hy = 1.f - ly, hx = 1.f - lx;
+      v = hy * (hx * lo[y0 * LS + x0] + lx * lo[y0 * LS + x1]) + ly * (hx * lo[y1 * LS + x0] + lx * lo[y1 * LS + x1]);
+    }
+    up[uy][ux] = v;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x >> 3, tx = (threadIdx.x & 7) * 4;  // 32 rows x 8 groups of 4 pixels
+  float res[4];
+  if (rw.use_refine) {
+    float acc[4][4][4];  // [branch][channel][pixel]
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int p = 0; p < 4; p++) acc[a][c][p] = 0.f;
+#pragma unroll 1
+    for (int dy = -5; dy <= 5; dy++) {
+      float row[14];
+#pragma unroll
+      for (int i = 0; i < 14; i++) row[i] = up[ty + THALO + dy][tx + i];
+      // branch 3: k = 11
+#pragma unroll
+      for (int dx = 0; dx < 11; dx++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          float w = tc_.w11[c * 121 + (dy + 5) * 11 + dx];
+#pragma unroll
+          for (int p = 0; p < 4; p++) acc[3][c][p] = fmaf(w, row[dx + p], acc[3][c][p]);
+        }
+      if (dy >= -3 && dy <= 3) {
+#pragma unroll
+        for (int dx = 0; dx < 7; dx++)
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            float w = tc_.w7[c * 49 + (dy + 3) * 7 + dx];
+#pragma unroll
+            for (int p = 0; p < 4; p++) acc[2][c][p] = fmaf(w, row[dx + 2 + p], acc[2][c][p]);
+          }
+      }
+      if (dy >= -2 && dy <= 2) {
+#pragma unroll
+        for (int dx = 0; dx < 5; dx++)
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            float w = tc_.w5[c * 25 + (dy + 2) * 5 + dx];
+#pragma unroll
+            for (int p = 0; p < 4; p++) acc[1][c][p] = fmaf(w, row[dx + 3 + p], acc[1][c][p]);
+          }
+      }
+      if (dy >= -1 && dy <= 1) {
+#pragma unroll
+        for (int dx = 0; dx < 3; dx++)
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            float w = tc_.w3[c * 9 + (dy + 1) * 3 + dx];
+#pragma unroll
+            for (int p = 0; p < 4; p++) acc[0][c][p] = fmaf(w, row[dx + 4 + p], acc[0][c][p]);
+          }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+      float o = tc_.cb;
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) o = fmaf(tc_.cw[a * 4 + c], gelu_exact(acc[a][c][p] + tc_.b[a * 4 + c]), o);
+      res[p] = o;
+    }
+  } else {
+#pragma unroll
+    for (int p = 0; p < 4; p++) res[p] = up[ty + THALO][tx + THALO + p];
+  }
+  const int Y = Y0 + ty, X = X0 + tx;
+  long long o = ((long long)b * S + Y) * S + X;
+  if (high) *(float4*)(high + o) = make_float4(res[0], res[1], res[2], res[3]);
+  if (mask) {
+    uint32_t m = 0;
+    int xmin = INT_MAX, xmax = -1;
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+      if (res[p] > 0.0f) {
+        m |= 0xFFu << (8 * p);
+        xmin = min(xmin, X + p);
+        xmax = max(xmax, X + p);
+      }
+    *(uint32_t*)(mask + o) = m;
+    if (extents) {
+      int ymin = xmax >= 0 ? Y : INT_MAX, ymax = xmax >= 0 ? Y : -1;
+      for (int k = 16; k; k >>= 1) {
+        xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, k));
+        xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, k));
+        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, k));
+        ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, k));
+      }
+      if ((threadIdx.x & 31) == 0 && xmax >= 0) {
+        atomicMin(extents + 4 * b, xmin);
+        atomicMin(extents + 4 * b + 1, ymin);
+        atomicMax(extents + 4 * b + 2, xmax);
+        atomicMax(extents + 4 * b + 3, ymax);
+      }
+    }
+  }
+}
+
+__global__ void k_init_extents(int* e, int B) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) { e[4 * i] = INT_MAX; e[4 * i + 1] = INT_MAX; e[4 * i + 2] = -1; e[4 * i + 3] = -1; }
+}
+
+int launch_tail(const float* low_res, int src_full, int B, const RefineWeights& rw, float* high_res, uint8_t* mask_u8,
+                int* extents, cudaStream_t st) {
+  if (extents) CVB_LAUNCH(k_init_extents, dim3((B + 127) / 128), dim3(128), 0, st, extents, B);
+  cvb_next_work((double)B * (256.0 * 256 * 4 + 1024.0 * 1024 * ((high_res ? 4 : 0) + (mask_u8 ? 1 : 0))));
+  CVB_LAUNCH(k_tail, dim3(1024 / TL, 1024 / TL, B), dim3(256), 0, st, low_res, src_full, rw, high_res, mask_u8, extents);
+  return CV_OK;
+}
+
+// bilinear (align_corners=False) resize of the 1024^2 logits to the caller's (H, W) + threshold (sam2_infer.py:127,
+// circuit_analyzer.py:356)
+__global__ void __launch_bounds__(256) k_resize_threshold(const float* __restrict__ hi, int S, int H, int W, float sy_, float sx_,
+                                                          float* __restrict__ out, uint8_t* __restrict__ mask,
+                                                          int* __restrict__ extents) {
+  int b = blockIdx.z;
+  int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  bool fg = false;
+  if (x < W && y < H) {
+    float sy = fmaxf(0.f, (y + 0.5f) * sy_ - 0.5f), sx = fmaxf(0.f, (x + 0.5f) * sx_ - 0.5f);
+    int y0 = min((int)sy, S - 1), x0 = min((int)sx, S - 1);
+    int y1 = y0 + (y0 < S - 1 ? 1 : 0), x1 = x0 + (x0 < S - 1 ? 1 : 0);
+    float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
+    const float* p = hi + (long long)b * S * S;
+    float v = hy * (hx * p[y0 * S + x0] + lx * p[y0 * S + x1]) + ly * (hx * p[y1 * S + x0] + lx * p[y1 * S + x1]);
+    long long o = ((long long)b * H + y) * W + x;
+    if (out) out[o] = v;
+    fg = v > 0.0f;
+    if (mask) mask[o] = fg ? 255 : 0;
+  }
+  if (extents) {
+    int xmin = fg ? x : INT_MAX, xmax = fg ? x : -1, ymin = fg ? y : INT_MAX, ymax = fg ? y : -1;
+    for (int k = 16; k; k >>= 1) {
+      xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, k));
+      xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, k));
+      ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, k));
+      ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, k));
+    }
+    if ((threadIdx.x & 31) == 0 && xmax >= 0) {
+      atomicMin(extents + 4 * b, xmin);
+      atomicMin(extents + 4 * b + 1, ymin);
+      atomicMax(extents + 4 * b + 2, xmax);
+      atomicMax(extents + 4 * b + 3, ymax);
+    }
+  }
+}
+
+int launch_resize_threshold(const float* high_res, int B, int S, int H, int W, float* out_logits, uint8_t* mask_u8,
+                            int* extents, cudaStream_t st) {
+  if (extents) CVB_LAUNCH(k_init_extents, dim3((B + 127) / 128), dim3(128), 0, st, extents, B);
+  // area_pixel_compute_scale (align_corners=False, no scale_factor): scale = in / out
+  float sy = (float)S / (float)H, sx = (float)S / (float)W;
+  CVB_LAUNCH(k_resize_threshold, dim3((W + 31) / 32, (H + 7) / 8, B), dim3(256), 0, st, high_res, S, H, W, sy, sx,
+             out_logits, mask_u8, extents);
+  return CV_OK;
+}
+
+}  // namespace cvb

@@ -127,6 +127,55 @@ int cv_attention_bf16(const void* q, long long ldq, int qcols, int qcol0, const 
                       int kcol0, const void* v, long long ldv, int vcols, int vcol0, int Mq, int Mkv, int Wq, int Wkv,
                       int heads, int head_dim, float scale, void* out, long long ld_out, void* stream);
 
+/* ------------------------------------------------------------------ SAM 2.1 image path
+ * replaces sam2_infer.py:220-275 (SAM2ImageWrapper.forward: sam2 image_encoder, conv_s0/conv_s1, sam_mask_decoder with
+ * the wrapper's learned prompts, bilinear x4, MultiKernelRefinement :177-189), SAM2Transforms.__call__ (:49-51) and
+ * postprocess_masks (:88-128) + the threshold / extent tail of circuit_analyzer.py:355-370.
+ * The engine owns the device copies of the (load-time folded) weights and its activation workspace.           */
+typedef struct cv_sam2_cfg {
+  int32_t embed_dim, num_heads;  /* stage-1 width and heads (tiny/small 96/1)                        */
+  int32_t stages[4];             /* blocks per stage                                                   */
+  int32_t window_spec[4];        /* window size per stage                                              */
+  int32_t global_blocks[8];      /* indices of global-attention blocks                                 */
+  int32_t n_global;
+  int32_t use_refinement;        /* wrapper built with use_refinement=True (sam2_infer.py:210)         */
+  int32_t max_batch;             /* activation workspace is sized for this many images per call        */
+  int32_t reserved;
+} cv_sam2_cfg;
+typedef struct cv_sam2 cv_sam2;
+
+int cv_sam2_create(const cv_sam2_cfg* cfg, int device, cv_sam2** out);
+int cv_sam2_destroy(cv_sam2* h);
+/* Upload one named weight tensor from HOST memory (dtype 0 = float32, 1 = bfloat16 bits).  The names and layouts
+ * are those produced by circuitvision_b200/sam2_weights.py (fold_state_dict) and listed in DESIGN.md.          */
+int cv_sam2_set_tensor(cv_sam2* h, const char* name, const void* host_data, int dtype, long long numel);
+/* Checks that every tensor the configuration needs is present and allocates the workspace. */
+int cv_sam2_finalize(cv_sam2* h);
+/* Re-sizes the activation workspace for a different max_batch (weights stay resident). */
+int cv_sam2_set_max_batch(cv_sam2* h, int max_batch);
+/* images (device): input_kind 0 = uint8 HWC [B,1024,1024,3] (ToTensor + Normalize fused; swap_rb applies the
+ * channel swap of circuit_analyzer.py:343), 1 = float32 CHW [B,3,1024,1024] already normalised.
+ * outputs (device, each nullable): low_res [B,1,256,256] f32, iou [B] f32, high_res [B,1,1024,1024] f32 (after the
+ * refinement head), mask_u8 [B,out_h,out_w] = (postprocess_masks(high_res, (out_h,out_w)) > 0) * 255,
+ * out_logits [B,out_h,out_w] f32 = postprocess_masks(high_res), extents [B,4] int32 (min x, min y, max x, max y of
+ * the foreground; max < 0 when empty).                                                                        */
+int cv_sam2_forward(cv_sam2* h, const void* images, int input_kind, int swap_rb, int B, float* low_res, float* iou,
+                    float* high_res, uint8_t* mask_u8, int out_h, int out_w, float* out_logits, int* extents,
+                    void* stream);
+int cv_sam2_last_launches(cv_sam2* h);
+/* Parity taps: copy an internal activation buffer (DESIGN.md names them) to caller device memory. */
+int cv_sam2_read_buffer(cv_sam2* h, const char* name, void* dst_device, long long bytes, void* stream);
+/* SAM2Transforms.__call__ for one uint8 HWC image of any size -> float32 CHW [3,1024,1024]; tmp: H*1024*3 floats. */
+int cv_sam2_preprocess(const uint8_t* img_hwc, int H, int W, int swap_rb, float* tmp, float* out_chw, void* stream);
+/* SAM2Transforms.postprocess_masks with hole/sprinkle filters off: bilinear (align_corners=False) resize of
+ * [B,1,S,S] f32 logits to [B,1,H,W]; optional threshold mask + extents as in cv_sam2_forward.                 */
+int cv_sam2_resize_logits(const float* logits, int B, int S, int H, int W, float* out_logits, uint8_t* mask_u8,
+                          int* extents, void* stream);
+/* MultiKernelRefinement.forward (sam2_infer.py:177-189) on [B,1,1024,1024] f32: branch weights w[j] = [4,k_j,k_j]
+ * for k = 3,5,7,11 and b[j] = [4] (device), combiner weight cw[16] (device), bias cb.                         */
+int cv_sam2_refine(const float* x, int B, const float* const* w, const float* const* b, const float* cw, float cb,
+                   float* out, void* stream);
+
 /* Per-kernel device timing for bench.py's roofline line: while enabled, every kernel the library launches is
  * bracketed by two CUDA events on its own stream.  cv_profile_count() waits for the recorded kernels and returns
  * the number of distinct kernel names; cv_profile_get(i, ...) returns name, launches, summed milliseconds and
