@@ -282,6 +282,11 @@ int attn_tc_launch(const __nv_bfloat16* q, long long ldq, int qcols, int qcol0, 
   p.out = out; p.ld_out = ld_out;
   // algorithmic flops: every query row against the keys of its own window, QK^T and PV
   cvb_next_work(4.0 * (double)Mq * (double)Wkv * ATT_D * heads);
+  if (cvb_profile_on()) {
+    char nm[96];
+    snprintf(nm, sizeof(nm), "attn Mq%d Wq%d Wkv%d h%d", Mq, Wq, Wkv, heads);
+    cvb_next_name(nm);
+  }
   CVB_LAUNCH(k_attn_tc, dim3((Mq + ATT_BM - 1) / ATT_BM, heads), dim3(ATT_THREADS), ATT_SMEM, st, tq, tk, tv, p);
   return CV_OK;
 }

@@ -10,6 +10,7 @@
 static thread_local char g_err[512] = "";
 static thread_local int g_launches = 0;
 static thread_local double g_next_work = 0.0;
+static thread_local char g_next_name[96] = "";
 
 int cvb_fail(int code, const char* msg) {
   snprintf(g_err, sizeof(g_err), "%s", msg);
@@ -24,6 +25,7 @@ int cvb_fail_cuda(cudaError_t e, const char* what) {
 void cvb_reset_launches() { g_launches = 0; }
 void cvb_count_launch() { g_launches++; }
 void cvb_next_work(double w) { g_next_work = w; }
+void cvb_next_name(const char* name) { snprintf(g_next_name, sizeof(g_next_name), "%s", name); }
 double cvb_take_work() {
   double w = g_next_work;
   g_next_work = 0.0;
@@ -65,7 +67,8 @@ bool cvb_profile_on() { return g_prof; }
 
 void cvb_profile_begin(const char* name, cudaStream_t st, double work) {
   std::lock_guard<std::mutex> lk(g_mu);
-  g_open.name = name;
+  g_open.name = g_next_name[0] ? g_next_name : name;
+  g_next_name[0] = 0;
   g_open.work = work;
   g_open.e0 = take_event();
   g_open.e1 = take_event();

@@ -17,6 +17,8 @@ void cvb_profile_end(cudaStream_t st);
 // algorithmic work (bytes or flops) of the NEXT launch, consumed by cvb_profile_begin
 void cvb_next_work(double w);
 double cvb_take_work();
+// optional display name of the NEXT launch in the profile table (e.g. a GEMM's shape); consumed by cvb_profile_begin
+void cvb_next_name(const char* name);
 
 #define CVB_CHECK(expr)                                          \
   do {                                                           \

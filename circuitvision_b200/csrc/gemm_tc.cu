@@ -26,6 +26,12 @@ static int launch_bn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16*
   long long tiles = (long long)p.n_tiles_m * p.n_tiles_n;
   int grid = (int)(tiles < num_sms ? tiles : num_sms);
   cvb_next_work(2.0 * (double)M * (double)N * (double)K);
+  if (cvb_profile_on()) {
+    char nm[96];
+    snprintf(nm, sizeof(nm), "gemm M%d N%d K%d bn%d%s%s%s", M, N, K, BN, epi.out_bf16 ? " ->bf16" : "", epi.out_f32 ? " ->f32" : "",
+             epi.res ? " +res" : "");
+    cvb_next_name(nm);
+  }
   CVB_LAUNCH((k_gemm_tc<BN>), dim3(grid), dim3(GEMM_THREADS), smem, st, ta, tw, p, epi);
   return CV_OK;
 }

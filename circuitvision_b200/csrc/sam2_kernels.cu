@@ -231,6 +231,11 @@ int launch_ln_rows(const float* X, long long n_src_rows, int C, const float* gam
     n_dst = (long long)B * nwx * nwy * ws * ws;
   }
   cvb_next_work((double)n_src_rows * C * 4 + (double)n_dst * C * (out_bf16 ? 2 : 0) + (double)n_dst * C * (out_f32 ? 4 : 0));
+  if (cvb_profile_on()) {
+    char nm[96];
+    snprintf(nm, sizeof(nm), "ln_rows R%lld C%d ws%d%s", n_src_rows, C, ws, gamma ? "" : " cast");
+    cvb_next_name(nm);
+  }
   CVB_LAUNCH(k_ln_rows, dim3((unsigned)((n_dst + 7) / 8)), dim3(256), 0, st, X, C, gamma, beta, eps, H, W, ws, nwx, nwy,
              n_dst, out_bf16, out_f32);
   return CV_OK;
