@@ -54,7 +54,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -354,6 +354,17 @@ def main():
     roofline = None
     kern_rows = []
     if table:
+        # the library tags GEMM / attention / LayerNorm launches with their shapes; fold them back per kernel
+        alias = {"gemm ": "k_gemm_tc", "attn ": "k_attn_tc", "ln_rows ": "k_ln_rows"}
+        folded = {}
+        for r in table:
+            name = next((v for k, v in alias.items() if r["name"].startswith(k)), r["name"])
+            f = folded.setdefault(name, {"name": name, "launches": 0, "ms": 0.0, "work": 0.0})
+            f["launches"] += r["launches"]
+            f["ms"] += r["ms"]
+            f["work"] += r["work"]
+        shapes = sorted(table, key=lambda r: -r["ms"])[:8]
+        table = list(folded.values())
         tot = sum(r["ms"] for r in table) or 1.0
         for r in sorted(table, key=lambda r: -r["ms"]):
             kern_rows.append({"name": r["name"], "launches": r["launches"], "ms_per_step": r["ms"] / a.steps,
@@ -361,7 +372,7 @@ def main():
         top = max(table, key=lambda r: r["ms"])
         avg_s = top["ms"] / 1e3 / max(1, top["launches"])
         wpl = top["work"] / max(1, top["launches"])
-        tensor = top["name"].startswith(("k_gemm", "k_attn", "k_fmha"))
+        tensor = top["name"] in ("k_gemm_tc", "k_attn_tc")
         if tensor:
             ach = wpl / avg_s / 1e12
             roofline = {"kernel": top["name"], "bound": "tensor", "achieved": ach, "peak": tens_peak, "unit": "TFLOP/s",
@@ -406,6 +417,8 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
         "kernels": kern_rows[:12],
+        "top_shapes": [{"name": r["name"], "launches": r["launches"], "ms_per_step": r["ms"] / a.steps,
+                        "rate_T_per_s": r["work"] / max(r["ms"], 1e-9) / 1e9} for r in shapes] if table else [],
     }
     print(json.dumps(line))
     if world > 1:

@@ -324,6 +324,16 @@ class SAM2ImageWrapper(nn.Module):
                 self._engine = _Engine(folded, self.sam2_model.variant, self.refinement_layer is not None, dev, self.max_batch)
             return self._engine
 
+    def segment_batch_u8(self, images_u8: torch.Tensor, swap_rb: bool = True) -> torch.Tensor:
+        """Batched, device-resident form of segment_with_sam2's numeric part for crops that are already 1024x1024:
+        images_u8 cuda uint8 [B,1024,1024,3] -> wire masks cuda uint8 [B,1024,1024] {0,255}.  Per-image extents are
+        left in `self.last_extents` ([B,4] int32, device)."""
+        eng = self.engine()
+        r = eng.forward(images_u8, 0, swap_rb, want_high=False, want_low=False, want_mask=True)
+        self.last_launches = eng.launches
+        self.last_extents = r["extents"]
+        return r["mask"]
+
     def forward(self, images, points=None, point_labels=None, masks_prompt=None, multimask_output=False):
         """-> (high_res_masks [B,1,1024,1024], low_res_masks [B,1,256,256], iou_predictions [B,1]); the prompt
         arguments are accepted and ignored exactly as in the reference (:220, they are never read)."""
@@ -371,6 +381,14 @@ def get_modified_sam2(model_cfg_path: str, checkpoint_path: str, device: str = "
         p.requires_grad_(False)
     return model.to(torch.device(device))
 
+
+
+def build_random_init(variant: str = "tiny", device="cuda:0", seed: int = 0, max_batch: int = 8, use_refinement: bool = True):
+    """Random-init wrapper of the named architecture (PyTorch-default init; there are no checkpoints offline)."""
+    torch.manual_seed(seed)
+    m = get_modified_sam2(variant, None, device=str(device), use_refinement_layer=use_refinement)
+    m.set_max_batch(max_batch)
+    return m
 
 
 # ------------------------------------------------------------------------------------------ segment driver
