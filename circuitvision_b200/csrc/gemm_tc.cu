@@ -1,24 +1,363 @@
-// Host launcher + C-ABI test entry of the tcgen05 GEMM (gemm_tc.cuh).
+// Persistent warp-specialised bf16 GEMM on tcgen05 + TMA (interface: gemm_tc.cuh) + its C-ABI test entry.
+//
+// CTA = 384 threads: warp0 TMA producer (one lane), warp1 MMA issuer (one lane), warp2 TMEM allocator, warps 4..11
+// epilogue.  Mainloop: 128 x BN x 64 k-blocks through a 4-stage smem ring (128B-swizzled K-major tiles), accumulators
+// in two TMEM stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Epilogue, per warp and 32-column chunk (thread = accumulator row = TMEM lane):
+//   tcgen05.ld 32 columns -> +bias -> activation -> (+ fp32 residual) -> swizzled per-warp smem buffer
+//   * identity row map: one TMA store (cp.async.bulk.tensor) of the 32x32 box per chunk, double-buffered;
+//   * window-unpartition / pixel-shuffle maps: the buffer is read back row-segment-wise and written with
+//     coalesced 128-byte (fp32) / 64-byte (bf16) stores at the remapped rows.
+// The epilogue configuration is a template parameter pack so that the hot instantiations carry no per-element
+// branches (an earlier all-runtime version was instruction-cache bound: 23 % no_inst stalls in ncu); a value of -1
+// keeps that flag a runtime value for the general C-ABI entry point.
 #include "gemm_tc.cuh"
 
 #include "common.cuh"
+#include "tc05.cuh"
 
 namespace cvb {
 
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_THREADS = 384;
+constexpr int GEMM_EPI_BUF = 4096;  // one 32 x 32 fp32 box
+
 template <int BN>
-static int launch_bn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M, int N, int K,
-                     const GemmEpilogue& epi, int num_sms, cudaStream_t st) {
+constexpr int gemm_smem_bytes() {
+  return 1024 /*align slack*/ + GEMM_STAGES * (GEMM_BM * 128 + BN * 128) + 8 * 2 * GEMM_EPI_BUF + 256;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// exact-erf GELU with erf from Abramowitz & Stegun 7.1.26 (|erf error| <= 1.5e-7, far below the bf16 / fp32-sum noise
+// of the value it is applied to): 2 MUFU + ~14 FMA-pipe instructions instead of erff's ~40.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  float ex;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(z * z * -1.4426950408889634f));
+  const float erf_abs = fmaf(-p, ex, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+
+__device__ __forceinline__ long long gemm_dest_row(const GemmEpilogue& e, int map, long long r) {
+  if (map == GEMM_MAP_UNWINDOW) {
+    int w2 = e.ws * e.ws;
+    long long win = r / w2;
+    int t = (int)(r - win * w2);
+    int per_img = e.nwx * e.nwy;
+    long long b = win / per_img;
+    int wi = (int)(win - b * per_img);
+    int wy = wi / e.nwx, wx = wi - wy * e.nwx;
+    int ty = t / e.ws, tx = t - ty * e.ws;
+    int y = wy * e.ws + ty, x = wx * e.ws + tx;
+    if (y >= e.H || x >= e.W) return -1;
+    return (b * e.H + y) * e.W + x;
+  }
+  return r;
+}
+
+template <int V>
+__device__ __forceinline__ int pick(int runtime) { return V < 0 ? runtime : V; }
+
+__device__ __forceinline__ float apply_act(int act, float x) {
+  if (act == GEMM_ACT_GELU) return gelu_fast(x);
+  if (act == GEMM_ACT_RELU) return fmaxf(x, 0.f);
+  return x;
+}
+
+// ACT / RES / OUT / MAP / RBA: compile-time epilogue configuration, -1 = read from GemmEpilogue at run time.
+// OUT: 0 = fp32, 1 = bf16, 2 = both (runtime-only).
+template <int BN, int ACT, int RES, int OUT, int MAP, int RBA>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+          const __grid_constant__ CUtensorMap tmap_out, GemmProblem p, GemmEpilogue e) {
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
+  constexpr int A_BYTES = GEMM_BM * 128, B_BYTES = BN * 128;
+  constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  constexpr bool TMA_OUT = (MAP == GEMM_MAP_IDENTITY) && (OUT == 0 || OUT == 1);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + GEMM_STAGES * A_BYTES;
+  uint8_t* epi = smem + GEMM_STAGES * (A_BYTES + B_BYTES);  // [8 warps][2][4096], 1024-byte aligned
+  uint64_t* bars = (uint64_t*)(epi + 8 * 2 * GEMM_EPI_BUF);
+  uint64_t* full = bars;                     // [STAGES]
+  uint64_t* empty = bars + GEMM_STAGES;      // [STAGES]
+  uint64_t* tfull = bars + 2 * GEMM_STAGES;  // [2]
+  uint64_t* tempty = tfull + 2;              // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = p.n_tiles_m * p.n_tiles_n;
+  const int n_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmap_a);
+    tc::prefetch_tmap(&tmap_w);
+    if (TMA_OUT) tc::prefetch_tmap(&tmap_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < GEMM_STAGES; i++) {
+      tc::mbar_init(&full[i], 1);
+      tc::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      tc::mbar_init(&tfull[i], 1);
+      tc::mbar_init(&tempty[i], 8);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        int mb = t / p.n_tiles_n, nb = t - mb * p.n_tiles_n;
+        for (int kb = 0; kb < n_kb; kb++) {
+          tc::mbar_wait(&empty[stage], phase ^ 1);
+          tc::mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
+          tc::tma_load_2d(sA + stage * A_BYTES, &tmap_a, &full[stage], kb * GEMM_BK, mb * GEMM_BM);
+          tc::tma_load_2d(sB + stage * B_BYTES, &tmap_w, &full[stage], kb * GEMM_BK, nb * BN);
+          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::idesc_bf16(GEMM_BM, BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc::tc_fence_after();
+        uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < n_kb; kb++) {
+          tc::mbar_wait(&full[stage], phase);
+          tc::tc_fence_after();
+          uint32_t a0 = tc::smem_u32(sA + stage * A_BYTES), b0 = tc::smem_u32(sB + stage * B_BYTES);
+          int ksteps = min(GEMM_BK / 16, (p.K - kb * GEMM_BK + 15) / 16);
+          for (int k = 0; k < ksteps; k++)
+            tc::mma_f16_ss(d_tmem, tc::desc_kmajor(a0 + k * 32), tc::desc_kmajor(b0 + k * 32), idesc,
+                           (kb > 0 || k > 0) ? 1u : 0u);
+          tc::mma_commit(&empty[stage]);
+          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc::mma_commit(&tfull[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: 8 warps; warp handles TMEM lanes 32*(warp%4).. and column chunks c with c%2 == ew/4
+    const int act = pick<ACT>(e.act);
+    const bool has_res = pick<RES>(e.res != nullptr) != 0;
+    const int map = pick<MAP>(e.map_mode);
+    const bool rba = pick<RBA>(e.res_before_act) != 0;
+    const bool out_f32 = (OUT < 0) ? (e.out_f32 != nullptr) : (OUT == 0 || OUT == 2);
+    const bool out_b16 = (OUT < 0) ? (e.out_bf16 != nullptr) : (OUT == 1 || OUT == 2);
+    const int ew = warp - 4;
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access (= warp id mod 4)
+    const int cgroup = ew >> 2;
+    uint8_t* bufs = epi + ew * 2 * GEMM_EPI_BUF;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t nbuf = 0;
+    const int sub_row = lane >> 3, sub_c = lane & 7;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      int mb = t / p.n_tiles_n, nb = t - mb * p.n_tiles_n;
+      const long long row0 = (long long)mb * GEMM_BM + quad * 32;
+      const long long myrow = row0 + lane;
+      long long dest[8];
+      if (!TMA_OUT) {
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+          long long r = row0 + it * 4 + sub_row;
+          dest[it] = (r < p.M) ? gemm_dest_row(e, map, r) : -1;
+        }
+      }
+      tc::mbar_wait(&tfull[acc], acc_phase);
+      tc::tc_fence_after();
+#pragma unroll 1
+      for (int c = cgroup; c < BN / 32; c += 2) {
+        const int col0 = nb * BN + c * 32;
+        uint8_t* buf = bufs + (nbuf & 1) * GEMM_EPI_BUF;
+        nbuf++;
+        // residual for the TMA path: this thread's own row, 32 consecutive floats (issued before the TMEM wait)
+        float4 rv[8];
+        if (TMA_OUT && has_res) {
+          if (myrow < p.M) {
+            long long rr = e.res_row_mod > 0 ? myrow % e.res_row_mod : myrow;
+            const float4* rp = (const float4*)(e.res + rr * e.ld_res + col0);
+#pragma unroll
+            for (int j = 0; j < 8; j++) rv[j] = rp[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        uint32_t v[32];
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32, v);
+        // SHUFFLE2: this 32-column chunk lies inside one (dy,dx) group; bias/out column = co
+        int q = 0, ocol0 = col0;
+        if (map == GEMM_MAP_SHUFFLE2) { q = col0 / e.cout; ocol0 = col0 - q * e.cout; }
+        float4 bv[8];
+        if (e.bias) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) bv[j] = __ldg((const float4*)(e.bias + ocol0) + j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; j++) bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (TMA_OUT) {
+          if (lane == 0) tc::tma_store_wait_read<1>();  // the store that last read `buf` has drained it
+          __syncwarp();
+        }
+        tc::tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bv[j].x;
+          f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bv[j].y;
+          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bv[j].z;
+          f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bv[j].w;
+        }
+        if (TMA_OUT) {
+          if (has_res && rba) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) { f[4 * j] += rv[j].x; f[4 * j + 1] += rv[j].y; f[4 * j + 2] += rv[j].z; f[4 * j + 3] += rv[j].w; }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i++) f[i] = apply_act(act, f[i]);
+          if (has_res && !rba) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) { f[4 * j] += rv[j].x; f[4 * j + 1] += rv[j].y; f[4 * j + 2] += rv[j].z; f[4 * j + 3] += rv[j].w; }
+          }
+          if (OUT == 0) {
+            // fp32 box: 128-byte rows, 128B swizzle (16-byte chunk j of row r lives at chunk j ^ (r & 7))
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+              *(float4*)(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            // bf16 box: 64-byte rows, 64B swizzle (chunk j of row r lives at chunk j ^ ((r >> 1) & 3))
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              uint32_t w[4];
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[8 * j + 2 * k], f[8 * j + 2 * k + 1]);
+                w[k] = *(uint32_t*)&b2;
+              }
+              *(uint4*)(buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+          tc::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && col0 < p.N && row0 < p.M) {
+            tc::tma_store_2d(&tmap_out, buf, col0, (int)row0);
+            tc::tma_store_commit();
+          }
+        } else {
+          if (!rba) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) f[i] = apply_act(act, f[i]);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            *(float4*)(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          __syncwarp();
+          if (col0 < p.N) {
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+              long long d = dest[it];
+              if (d < 0) continue;
+              const int r = it * 4 + sub_row;
+              float4 x = *(const float4*)(buf + r * 128 + ((sub_c ^ (r & 7)) << 4));
+              if (map == GEMM_MAP_SHUFFLE2) {
+                long long img = d / ((long long)e.H * e.W);
+                int rem = (int)(d - img * e.H * e.W);
+                int y = rem / e.W, xx = rem - y * e.W;
+                d = (img * 2 * e.H + 2 * y + (q >> 1)) * 2 * e.W + 2 * xx + (q & 1);
+              }
+              const int oc = ocol0 + sub_c * 4;
+              if (has_res) {
+                long long rr = e.res_row_mod > 0 ? d % e.res_row_mod : d;
+                float4 r4 = *(const float4*)(e.res + rr * e.ld_res + oc);
+                x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
+              }
+              if (rba) { x.x = apply_act(act, x.x); x.y = apply_act(act, x.y); x.z = apply_act(act, x.z); x.w = apply_act(act, x.w); }
+              if (out_f32) *(float4*)(e.out_f32 + d * e.ld_f32 + oc) = x;
+              if (out_b16) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+                uint2 pk;
+                pk.x = *(uint32_t*)&lo;
+                pk.y = *(uint32_t*)&hi;
+                *(uint2*)(e.out_bf16 + d * e.ld_bf16 + oc) = pk;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      // all TMEM reads of this accumulator stage are complete (tmem_ld_wait above): hand it back to the MMA warp
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (TMA_OUT && lane == 0) tc::tma_store_wait<0>();  // global writes complete before the CTA retires
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, int ACT, int RES, int OUT, int MAP, int RBA>
+static int launch_cfg(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M, int N, int K,
+                      const GemmEpilogue& epi, int num_sms, cudaStream_t st) {
   static bool attr_set = false;
   constexpr int smem = gemm_smem_bytes<BN>();
+  auto kern = k_gemm_tc<BN, ACT, RES, OUT, MAP, RBA>;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cvb_fail_cuda(e, "cudaFuncSetAttribute(k_gemm_tc)");
     attr_set = true;
   }
-  CUtensorMap ta, tw;
+  CUtensorMap ta, tw, to;
   if (!tc_host::make_tmap_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM) ||
       !tc_host::make_tmap_bf16(&tw, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, BN))
     return cvb_fail(CV_ERR_CUDA, "cuTensorMapEncodeTiled failed (GEMM operands)");
+  constexpr bool TMA_OUT = (MAP == GEMM_MAP_IDENTITY) && (OUT == 0 || OUT == 1);
+  if (TMA_OUT) {
+    bool ok = OUT == 0 ? tc_host::make_tmap_2d(&to, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, epi.out_f32, (uint64_t)M, (uint64_t)N,
+                                               (uint64_t)epi.ld_f32 * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)
+                       : tc_host::make_tmap_2d(&to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, epi.out_bf16, (uint64_t)M, (uint64_t)N,
+                                               (uint64_t)epi.ld_bf16 * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (!ok) return cvb_fail(CV_ERR_CUDA, "cuTensorMapEncodeTiled failed (GEMM output)");
+  } else {
+    to = ta;
+  }
   GemmProblem p;
   p.M = M; p.N = N; p.K = K;
   p.n_tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
@@ -28,12 +367,36 @@ static int launch_bn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16*
   cvb_next_work(2.0 * (double)M * (double)N * (double)K);
   if (cvb_profile_on()) {
     char nm[96];
-    snprintf(nm, sizeof(nm), "gemm M%d N%d K%d bn%d%s%s%s", M, N, K, BN, epi.out_bf16 ? " ->bf16" : "", epi.out_f32 ? " ->f32" : "",
-             epi.res ? " +res" : "");
+    snprintf(nm, sizeof(nm), "gemm M%d N%d K%d bn%d%s%s%s%s", M, N, K, BN, epi.out_bf16 ? " ->bf16" : "", epi.out_f32 ? " ->f32" : "",
+             epi.res ? " +res" : "", ACT < 0 ? " generic" : "");
     cvb_next_name(nm);
   }
-  CVB_LAUNCH((k_gemm_tc<BN>), dim3(grid), dim3(GEMM_THREADS), smem, st, ta, tw, p, epi);
+  CVB_LAUNCH(kern, dim3(grid), dim3(GEMM_THREADS), smem, st, ta, tw, to, p, epi);
   return CV_OK;
+}
+
+template <int BN>
+static int launch_bn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M, int N, int K,
+                     const GemmEpilogue& e, int num_sms, cudaStream_t st) {
+#define CVB_GEMM_ARGS A, lda, W, ldw, M, N, K, e, num_sms, st
+  const bool res = e.res != nullptr, f32 = e.out_f32 != nullptr, b16 = e.out_bf16 != nullptr;
+  // TMA-store outputs need a 16-byte aligned base and pitch; everything else takes the coalesced-store path
+  const bool tma_ok = f32 ? (((uintptr_t)e.out_f32 & 15) == 0 && (e.ld_f32 % 4) == 0)
+                          : (((uintptr_t)e.out_bf16 & 15) == 0 && (e.ld_bf16 % 8) == 0);
+  if (e.map_mode == GEMM_MAP_IDENTITY && tma_ok && !(f32 && b16)) {
+    if (b16 && !res && e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 0, 1, 0, 0>(CVB_GEMM_ARGS);  // qkv
+    if (b16 && !res && e.act == GEMM_ACT_GELU) return launch_cfg<BN, 1, 0, 1, 0, 0>(CVB_GEMM_ARGS);  // mlp fc1
+    if (f32 && res && e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 1, 0, 0, 0>(CVB_GEMM_ARGS);   // fc2, global proj, tables
+    if (f32 && !res && e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 0, 0, 0, 0>(CVB_GEMM_ARGS);  // shortcut, neck
+  }
+  if (e.map_mode == GEMM_MAP_UNWINDOW && f32 && !b16 && res && e.act == GEMM_ACT_NONE)
+    return launch_cfg<BN, 0, 1, 0, 1, 0>(CVB_GEMM_ARGS);                                             // windowed proj
+  if (e.map_mode == GEMM_MAP_SHUFFLE2 && f32 && !b16 && res) {
+    if (e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 1, 0, 2, 0>(CVB_GEMM_ARGS);                 // upscale 1
+    if (e.act == GEMM_ACT_GELU && e.res_before_act) return launch_cfg<BN, 1, 1, 0, 2, 1>(CVB_GEMM_ARGS);  // upscale 2
+  }
+  return launch_cfg<BN, -1, -1, -1, -1, -1>(CVB_GEMM_ARGS);                                          // anything else
+#undef CVB_GEMM_ARGS
 }
 
 int gemm_tc_launch(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M, int N, int K,
@@ -41,7 +404,10 @@ int gemm_tc_launch(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W
   if (M <= 0 || N <= 0 || K <= 0) return cvb_fail(CV_ERR_INVALID, "gemm: non-positive size");
   if ((N % 32) || (K % 8) || (lda % 8) || (ldw % 8)) return cvb_fail(CV_ERR_INVALID, "gemm: N%32, K%8, lda%8, ldw%8 must be 0");
   if (((uintptr_t)A | (uintptr_t)W) & 15) return cvb_fail(CV_ERR_INVALID, "gemm: operands must be 16-byte aligned");
+  if (!epi.out_f32 && !epi.out_bf16) return cvb_fail(CV_ERR_INVALID, "gemm: no output");
   if (epi.map_mode == GEMM_MAP_SHUFFLE2 && (epi.cout % 32)) return cvb_fail(CV_ERR_INVALID, "gemm: shuffle needs cout%32==0");
+  if (epi.bias && ((uintptr_t)epi.bias & 15)) return cvb_fail(CV_ERR_INVALID, "gemm: bias must be 16-byte aligned");
+  if (epi.res && (((uintptr_t)epi.res & 15) || (epi.ld_res % 4))) return cvb_fail(CV_ERR_INVALID, "gemm: residual alignment");
   if (N % 192 == 0) return launch_bn<192>(A, lda, W, ldw, M, N, K, epi, num_sms, st);
   if (N % 128 == 0) return launch_bn<128>(A, lda, W, ldw, M, N, K, epi, num_sms, st);
   if (N % 96 == 0) return launch_bn<96>(A, lda, W, ldw, M, N, K, epi, num_sms, st);
