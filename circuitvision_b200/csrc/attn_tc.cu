@@ -256,6 +256,254 @@ k_attn_tc(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtens
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ global attention
+// Wq == Wkv (one window = all tokens of an image), Wkv % 128 == 0, Wq % 256 == 0: the three global blocks of stage 3
+// (4096 x 4096 per head) — 85 of the trunk's 86 attention GFLOP per image.
+// CTA = TWO 128-row query tiles of one head sharing every K/V tile; 12 warps:
+//   warp0 TMA producer, warp1 MMA issuer, warp2 TMEM allocator, warps 4-7 softmax of tile 0, warps 8-11 softmax of tile 1.
+// TMEM: S0 | S1 (128 fp32 columns each) and O0 | O1 (96 columns each).  Per key tile and query tile:
+//   S = Q K^T (SS MMA)  ->  softmax warps read S ONCE, write P = 2^(s*scale - m_ref) as packed bf16 over the first 64
+//   columns of S (tcgen05.st)  ->  O += P V with P as the TMEM A operand (TS MMA, V consumed MN-major from smem).
+// The tensor pipe ping-pongs between the two query tiles, so softmax of one overlaps the MMAs of the other.
+// m_ref is a lazily updated reference maximum: P uses the reference carried in from the previous tiles and O / l are
+// rescaled (tcgen05.ld -> mul -> tcgen05.st) only when a tile's maximum exceeds it by more than 2^8 — rare after the
+// first tile, and exact either way because the same reference scales numerator and denominator.
+constexpr int AG_THREADS = 384;
+constexpr int AG_SMEM = 1024 + ATT_TILE_BYTES * (2 /*Q0,Q1*/ + 2 /*K*/ + 2 /*V*/) + 256;
+
+__global__ void __launch_bounds__(AG_THREADS, 1)
+k_attn_global(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+              const __grid_constant__ CUtensorMap tv, AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;                      // [2]
+  uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;   // [2]
+  uint8_t* sV = sK + 2 * ATT_TILE_BYTES;   // [2]
+  uint64_t* bars = (uint64_t*)(sV + 2 * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;         // 1
+  uint64_t* k_full = bars + 1;     // [2]
+  uint64_t* k_empty = bars + 3;    // [2]
+  uint64_t* v_full = bars + 5;     // [2]
+  uint64_t* v_empty = bars + 7;    // [2]
+  uint64_t* s_full = bars + 9;     // [2] per query tile
+  uint64_t* p_full = bars + 11;    // [2]
+  uint64_t* o_full = bars + 13;    // [2]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 2 * ATT_BM;
+  const int head = blockIdx.y;
+  const int kv_start = (q0 / p.Wq) * p.Wkv;
+  const int n_tiles = p.Wkv / ATT_BN;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tq);
+    tc::prefetch_tmap(&tk);
+    tc::prefetch_tmap(&tv);
+  }
+  if (warp == 1 && lane == 0) {
+    tc::mbar_init(q_full, 1);
+    for (int i = 0; i < 2; i++) {
+      tc::mbar_init(&k_full[i], 1);
+      tc::mbar_init(&k_empty[i], 1);
+      tc::mbar_init(&v_full[i], 1);
+      tc::mbar_init(&v_empty[i], 1);
+      tc::mbar_init(&s_full[i], 1);
+      tc::mbar_init(&p_full[i], 4);  // one arrival per softmax warp of the tile
+      tc::mbar_init(&o_full[i], 1);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc<512>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tc::mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+      for (int g = 0; g < 2; g++) {
+        tc::tma_load_2d(sQ + g * ATT_TILE_BYTES, &tq, q_full, p.qcol0 + head * ATT_D, q0 + g * ATT_BM);
+        tc::tma_load_2d(sQ + g * ATT_TILE_BYTES + ATT_BM * 128, &tq, q_full, p.qcol0 + head * ATT_D + 64, q0 + g * ATT_BM);
+      }
+      for (int j = 0; j < n_tiles; j++) {
+        const int s = j & 1;
+        const uint32_t par = ((j >> 1) & 1) ^ 1;
+        const int row = kv_start + j * ATT_BN;
+        tc::mbar_wait(&k_empty[s], par);
+        tc::mbar_arrive_expect_tx(&k_full[s], ATT_TILE_BYTES);
+        uint8_t* k = sK + s * ATT_TILE_BYTES;
+        tc::tma_load_2d(k, &tk, &k_full[s], p.kcol0 + head * ATT_D, row);
+        tc::tma_load_2d(k + ATT_BN * 128, &tk, &k_full[s], p.kcol0 + head * ATT_D + 64, row);
+        tc::mbar_wait(&v_empty[s], par);
+        tc::mbar_arrive_expect_tx(&v_full[s], ATT_TILE_BYTES);
+        uint8_t* v = sV + s * ATT_TILE_BYTES;
+        tc::tma_load_2d(v, &tv, &v_full[s], p.vcol0 + head * ATT_D, row);
+        tc::tma_load_2d(v + ATT_BN * 128, &tv, &v_full[s], p.vcol0 + head * ATT_D + 64, row);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = tc::idesc_bf16(ATT_BM, ATT_BN, false, false);
+      constexpr uint32_t idesc_pv = tc::idesc_bf16(ATT_BM, ATT_D, false, true);  // A = P (TMEM, K-major), B = V MN-major
+      auto issue_qk = [&](int g, int j) {
+        const uint32_t q_addr = tc::smem_u32(sQ + g * ATT_TILE_BYTES);
+        const uint32_t k_addr = tc::smem_u32(sK + (j & 1) * ATT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; k++) {
+          uint32_t off = (k >> 2) * (ATT_BM * 128) + (k & 3) * 32;
+          tc::mma_f16_ss(tmem_base + g * 128, tc::desc_kmajor(q_addr + off), tc::desc_kmajor(k_addr + off), idesc_qk,
+                         k > 0 ? 1u : 0u);
+        }
+        tc::mma_commit(&s_full[g]);
+      };
+      auto issue_pv = [&](int g, int j) {
+        const uint32_t v_addr = tc::smem_u32(sV + (j & 1) * ATT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < ATT_BN / 16; k++) {
+          // A: 16 keys = 8 packed columns of the P region; B: 16 key rows (2048 B) per k-step of the MN-major V tile
+          uint64_t b = tc::smem_desc_sw128(v_addr + k * 2048, ATT_BN * 128, 1024);
+          tc::mma_f16_ts(tmem_base + 256 + g * ATT_D, tmem_base + g * 128 + k * 8, b, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+        }
+        tc::mma_commit(&o_full[g]);
+      };
+      tc::mbar_wait(q_full, 0);
+      tc::mbar_wait(&k_full[0], 0);
+      tc::tc_fence_after();
+      issue_qk(0, 0);
+      issue_qk(1, 0);
+      tc::mma_commit(&k_empty[0]);
+      for (int j = 0; j < n_tiles; j++) {
+        const bool more = j + 1 < n_tiles;
+        tc::mbar_wait(&v_full[j & 1], (j >> 1) & 1);
+        tc::mbar_wait(&p_full[0], j & 1);
+        tc::tc_fence_after();
+        issue_pv(0, j);
+        if (more) {
+          tc::mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+          tc::tc_fence_after();
+          issue_qk(0, j + 1);
+        }
+        tc::mbar_wait(&p_full[1], j & 1);
+        tc::tc_fence_after();
+        issue_pv(1, j);
+        tc::mma_commit(&v_empty[j & 1]);
+        if (more) {
+          issue_qk(1, j + 1);
+          tc::mma_commit(&k_empty[(j + 1) & 1]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int g = (warp - 4) >> 2;  // query tile of this warp
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const int grow = q0 + g * ATT_BM + r;
+    const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
+    const uint32_t tS = tmem_base + lane_sel + g * 128;
+    const uint32_t tO = tmem_base + lane_sel + 256 + g * ATT_D;
+    float m_ref = 0.f, l = 0.f;
+    for (int j = 0; j < n_tiles; j++) {
+      tc::mbar_wait(&s_full[g], j & 1);
+      tc::tc_fence_after();
+      if (j == 0) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < ATT_BN / 32; c++) {
+          uint32_t v[32];
+          tc::tmem_ld_32x32(tS + c * 32, v);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+        m_ref = mx * p.scale_log2;
+      }
+      float tmax = -INFINITY, rowsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < ATT_BN / 32; c++) {
+        uint32_t v[32];
+        tc::tmem_ld_32x32(tS + c * 32, v);
+        tc::tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
+          tmax = fmaxf(tmax, fmaxf(s0, s1));
+          float p0 = ex2(fmaf(s0, p.scale_log2, -m_ref)), p1 = ex2(fmaf(s1, p.scale_log2, -m_ref));
+          rowsum += p0 + p1;
+          __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
+          pk[i >> 1] = *(uint32_t*)&b;
+        }
+        tc::tmem_st_32x16(tS + c * 16, pk);  // P over the already-consumed head of S
+      }
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&p_full[g]);
+      l += rowsum;
+      const float tm = tmax * p.scale_log2;
+      const bool need = tm > m_ref + 8.0f;
+      if (__any_sync(0xffffffffu, need)) {
+        // rescale O and l to the new reference once P V of this tile has been accumulated
+        tc::mbar_wait(&o_full[g], j & 1);
+        tc::tc_fence_after();
+        const float alpha = need ? ex2(m_ref - tm) : 1.0f;
+#pragma unroll
+        for (int c = 0; c < ATT_D / 32; c++) {
+          uint32_t v[32];
+          tc::tmem_ld_32x32(tO + c * 32, v);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tc::tmem_st_32x32(tO + c * 32, v);
+        }
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        l *= alpha;
+        if (need) m_ref = tm;
+      }
+    }
+    tc::mbar_wait(&o_full[g], (n_tiles - 1) & 1);
+    tc::tc_fence_after();
+    if (grow < p.Mq) {
+      const float inv = 1.f / l;
+      __nv_bfloat16* o = p.out + (long long)grow * p.ld_out + head * ATT_D;
+#pragma unroll
+      for (int c = 0; c < ATT_D / 32; c++) {
+        uint32_t v[32];
+        tc::tmem_ld_32x32(tO + c * 32, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint32_t w[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(v[i + 2 * k]) * inv, __uint_as_float(v[i + 2 * k + 1]) * inv);
+            w[k] = *(uint32_t*)&b;
+          }
+          *(uint4*)(o + c * 32 + i) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    } else {
+      // keep the warp-collective TMEM loads aligned for rows past Mq
+#pragma unroll
+      for (int c = 0; c < ATT_D / 32; c++) {
+        uint32_t v[32];
+        tc::tmem_ld_32x32(tO + c * 32, v);
+        tc::tmem_ld_wait();
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // q/k/v: bf16 matrices [Mq|Mkv, ld*] whose columns [col0 + h*96, col0 + (h+1)*96) hold head h.
 int attn_tc_launch(const __nv_bfloat16* q, long long ldq, int qcols, int qcol0, const __nv_bfloat16* k, long long ldk,
                    int kcols, int kcol0, const __nv_bfloat16* v, long long ldv, int vcols, int vcol0, int Mq, int Mkv,
@@ -286,6 +534,16 @@ int attn_tc_launch(const __nv_bfloat16* q, long long ldq, int qcols, int qcol0, 
     char nm[96];
     snprintf(nm, sizeof(nm), "attn Mq%d Wq%d Wkv%d h%d", Mq, Wq, Wkv, heads);
     cvb_next_name(nm);
+  }
+  if (Wq == Wkv && (Wkv % ATT_BN) == 0 && (Wq % (2 * ATT_BM)) == 0 && (Mq % (2 * ATT_BM)) == 0) {
+    static bool attr_set_g = false;
+    if (!attr_set_g) {
+      cudaError_t e = cudaFuncSetAttribute(k_attn_global, cudaFuncAttributeMaxDynamicSharedMemorySize, AG_SMEM);
+      if (e != cudaSuccess) return cvb_fail_cuda(e, "cudaFuncSetAttribute(k_attn_global)");
+      attr_set_g = true;
+    }
+    CVB_LAUNCH(k_attn_global, dim3(Mq / (2 * ATT_BM), heads), dim3(AG_THREADS), AG_SMEM, st, tq, tk, tv, p);
+    return CV_OK;
   }
   CVB_LAUNCH(k_attn_tc, dim3((Mq + ATT_BM - 1) / ATT_BM, heads), dim3(ATT_THREADS), ATT_SMEM, st, tq, tk, tv, p);
   return CV_OK;

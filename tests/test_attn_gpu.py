@@ -61,3 +61,10 @@ def test_attention_matches_fp32(nwin, Wq, Wkv, heads, pooled):
 
 def test_attention_large_logits():
     _run(4, 196, 196, 2, False, seed=3, amp=4.0)
+
+
+def test_global_attention_lazy_rescale():
+    """Two-query-tile global kernel: large logits make tile maxima jump by far more than the 2^8 rescale threshold."""
+    _run(1, 1024, 1024, 2, False, seed=5, amp=4.0)
+    _run(2, 512, 512, 1, False, seed=6, amp=3.0)
+    _run(1, 256, 256, 1, False, seed=7, amp=0.5)
