@@ -25,6 +25,7 @@ struct AttnParams {
   int Mq, Mkv, Wq, Wkv, heads;
   int qcol0, kcol0, vcol0;  // column of head 0 inside the Q / K / V tensor maps
   float scale_log2;         // softmax scale * log2(e)
+  int fp16;                 // q/k/v/P/out are IEEE half instead of bf16
   __nv_bfloat16* out;       // [Mq, heads*96]
   long long ld_out;
 };
@@ -104,8 +105,8 @@ k_attn_tc(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtens
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_qk = tc::idesc_bf16(ATT_BM, ATT_BN, false, false);
-      constexpr uint32_t idesc_pv = tc::idesc_bf16(ATT_BM, ATT_D, false, true);  // B = V, MN-major
+      const uint32_t idesc_qk = tc::idesc_bf16(ATT_BM, ATT_BN, false, false, p.fp16 != 0);
+      const uint32_t idesc_pv = tc::idesc_bf16(ATT_BM, ATT_D, false, true, p.fp16 != 0);  // B = V, MN-major
       const uint32_t q_addr = tc::smem_u32(sQ), p_addr = tc::smem_u32(sP);
       auto issue_qk = [&](int j) {
         uint32_t k_addr = tc::smem_u32(sK + (j & 1) * ATT_TILE_BYTES);
@@ -210,8 +211,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtens
             if (col + 1 < c_lo || col + 1 >= c_hi) p1 = 0.f;
           }
           rowsum += p0 + p1;
-          __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
-          pk[i >> 1] = *(uint32_t*)&b;
+          pk[i >> 1] = tc::pack16(p.fp16, p0, p1);
         }
         // 32 columns = 4 chunks of 16 bytes; K-major SW128: atom = col/64, chunk' = chunk ^ (row % 8)
 #pragma unroll
@@ -241,8 +241,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtens
         uint32_t w[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-          __nv_bfloat162 b = __floats2bfloat162_rn(O[i + 2 * k] * inv, O[i + 2 * k + 1] * inv);
-          w[k] = *(uint32_t*)&b;
+          w[k] = tc::pack16(p.fp16, O[i + 2 * k] * inv, O[i + 2 * k + 1] * inv);
         }
         *(uint4*)(o + i) = make_uint4(w[0], w[1], w[2], w[3]);
       }
@@ -346,8 +345,8 @@ k_attn_global(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_qk = tc::idesc_bf16(ATT_BM, ATT_BN, false, false);
-      constexpr uint32_t idesc_pv = tc::idesc_bf16(ATT_BM, ATT_D, false, true);  // A = P (TMEM, K-major), B = V MN-major
+      const uint32_t idesc_qk = tc::idesc_bf16(ATT_BM, ATT_BN, false, false, p.fp16 != 0);
+      const uint32_t idesc_pv = tc::idesc_bf16(ATT_BM, ATT_D, false, true, p.fp16 != 0);  // A = P (TMEM, K-major), B = V MN-major
       auto issue_qk = [&](int g, int j) {
         const uint32_t q_addr = tc::smem_u32(sQ + g * ATT_TILE_BYTES);
         const uint32_t k_addr = tc::smem_u32(sK + (j & 1) * ATT_TILE_BYTES);
@@ -433,8 +432,7 @@ k_attn_global(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
           tmax = fmaxf(tmax, fmaxf(s0, s1));
           float p0 = ex2(fmaf(s0, p.scale_log2, -m_ref)), p1 = ex2(fmaf(s1, p.scale_log2, -m_ref));
           rowsum += p0 + p1;
-          __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
-          pk[i >> 1] = *(uint32_t*)&b;
+          pk[i >> 1] = tc::pack16(p.fp16, p0, p1);
         }
         tc::tmem_st_32x16(tS + c * 16, pk);  // P over the already-consumed head of S
       }
@@ -480,8 +478,7 @@ k_attn_global(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
           uint32_t w[4];
 #pragma unroll
           for (int k = 0; k < 4; k++) {
-            __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(v[i + 2 * k]) * inv, __uint_as_float(v[i + 2 * k + 1]) * inv);
-            w[k] = *(uint32_t*)&b;
+            w[k] = tc::pack16(p.fp16, __uint_as_float(v[i + 2 * k]) * inv, __uint_as_float(v[i + 2 * k + 1]) * inv);
           }
           *(uint4*)(o + c * 32 + i) = make_uint4(w[0], w[1], w[2], w[3]);
         }
@@ -507,7 +504,7 @@ k_attn_global(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
 // q/k/v: bf16 matrices [Mq|Mkv, ld*] whose columns [col0 + h*96, col0 + (h+1)*96) hold head h.
 int attn_tc_launch(const __nv_bfloat16* q, long long ldq, int qcols, int qcol0, const __nv_bfloat16* k, long long ldk,
                    int kcols, int kcol0, const __nv_bfloat16* v, long long ldv, int vcols, int vcol0, int Mq, int Mkv,
-                   int Wq, int Wkv, int heads, float scale, __nv_bfloat16* out, long long ld_out, cudaStream_t st) {
+                   int Wq, int Wkv, int heads, float scale, __nv_bfloat16* out, long long ld_out, int fp16, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_attn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
@@ -527,6 +524,7 @@ int attn_tc_launch(const __nv_bfloat16* q, long long ldq, int qcols, int qcol0, 
   p.Mq = Mq; p.Mkv = Mkv; p.Wq = Wq; p.Wkv = Wkv; p.heads = heads;
   p.qcol0 = qcol0; p.kcol0 = kcol0; p.vcol0 = vcol0;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.fp16 = fp16;
   p.out = out; p.ld_out = ld_out;
   // algorithmic flops: every query row against the keys of its own window, QK^T and PV
   cvb_next_work(4.0 * (double)Mq * (double)Wkv * ATT_D * heads);
@@ -562,5 +560,5 @@ extern "C" int cv_attention_bf16(const void* qkv_q, long long ldq, int qcols, in
   if (head_dim != ATT_D) return cvb_fail(CV_ERR_INVALID, "cv_attention_bf16: only head_dim 96 (SAM 2.1 tiny/small) is built");
   return attn_tc_launch((const __nv_bfloat16*)qkv_q, ldq, qcols, qcol0, (const __nv_bfloat16*)qkv_k, ldk, kcols, kcol0,
                         (const __nv_bfloat16*)qkv_v, ldv, vcols, vcol0, Mq, Mkv, Wq, Wkv, heads, scale,
-                        (__nv_bfloat16*)out, ld_out, (cudaStream_t)stream);
+                        (__nv_bfloat16*)out, ld_out, 0, (cudaStream_t)stream);
 }

@@ -142,7 +142,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread)
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::idesc_bf16(GEMM_BM, BN, false, false);
+      const uint32_t idesc = tc::idesc_bf16(GEMM_BM, BN, false, false, e.fp16 != 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -219,6 +219,28 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
         // SHUFFLE2: this 32-column chunk lies inside one (dy,dx) group; bias/out column = co
         int q = 0, ocol0 = col0;
         if (map == GEMM_MAP_SHUFFLE2) { q = col0 / e.cout; ocol0 = col0 - q * e.cout; }
+        // remapped path: final destination rows and their residual segments, all loads issued up front (the output may
+        // alias the residual, so the compiler cannot hoist these loads above the stores of an earlier iteration itself)
+        long long dfin[8];
+        float4 rres[8];
+        if (!TMA_OUT) {
+#pragma unroll
+          for (int it = 0; it < 8; it++) {
+            long long d = dest[it];
+            if (d >= 0 && map == GEMM_MAP_SHUFFLE2) {
+              long long img = d / ((long long)e.H * e.W);
+              int rem = (int)(d - img * e.H * e.W);
+              int y = rem / e.W, xx = rem - y * e.W;
+              d = (img * 2 * e.H + 2 * y + (q >> 1)) * 2 * e.W + 2 * xx + (q & 1);
+            }
+            dfin[it] = d;
+            rres[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_res && d >= 0 && col0 < p.N) {
+              long long rr = e.res_row_mod > 0 ? d % e.res_row_mod : d;
+              rres[it] = *(const float4*)(e.res + rr * e.ld_res + ocol0 + sub_c * 4);
+            }
+          }
+        }
         float4 bv[8];
         if (e.bias) {
 #pragma unroll
@@ -262,10 +284,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
             for (int j = 0; j < 4; j++) {
               uint32_t w[4];
 #pragma unroll
-              for (int k = 0; k < 4; k++) {
-                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[8 * j + 2 * k], f[8 * j + 2 * k + 1]);
-                w[k] = *(uint32_t*)&b2;
-              }
+              for (int k = 0; k < 4; k++) w[k] = tc::pack16(e.fp16, f[8 * j + 2 * k], f[8 * j + 2 * k + 1]);
               *(uint4*)(buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
@@ -287,29 +306,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
           if (col0 < p.N) {
 #pragma unroll
             for (int it = 0; it < 8; it++) {
-              long long d = dest[it];
+              const long long d = dfin[it];
               if (d < 0) continue;
               const int r = it * 4 + sub_row;
               float4 x = *(const float4*)(buf + r * 128 + ((sub_c ^ (r & 7)) << 4));
-              if (map == GEMM_MAP_SHUFFLE2) {
-                long long img = d / ((long long)e.H * e.W);
-                int rem = (int)(d - img * e.H * e.W);
-                int y = rem / e.W, xx = rem - y * e.W;
-                d = (img * 2 * e.H + 2 * y + (q >> 1)) * 2 * e.W + 2 * xx + (q & 1);
-              }
               const int oc = ocol0 + sub_c * 4;
-              if (has_res) {
-                long long rr = e.res_row_mod > 0 ? d % e.res_row_mod : d;
-                float4 r4 = *(const float4*)(e.res + rr * e.ld_res + oc);
-                x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
-              }
+              if (has_res) { x.x += rres[it].x; x.y += rres[it].y; x.z += rres[it].z; x.w += rres[it].w; }
               if (rba) { x.x = apply_act(act, x.x); x.y = apply_act(act, x.y); x.z = apply_act(act, x.z); x.w = apply_act(act, x.w); }
               if (out_f32) *(float4*)(e.out_f32 + d * e.ld_f32 + oc) = x;
               if (out_b16) {
-                __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
                 uint2 pk;
-                pk.x = *(uint32_t*)&lo;
-                pk.y = *(uint32_t*)&hi;
+                pk.x = tc::pack16(e.fp16, x.x, x.y);
+                pk.y = tc::pack16(e.fp16, x.z, x.w);
                 *(uint2*)(e.out_bf16 + d * e.ld_bf16 + oc) = pk;
               }
             }

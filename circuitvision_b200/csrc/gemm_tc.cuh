@@ -29,6 +29,7 @@ struct GemmEpilogue {
   // SHUFFLE2: source row (b,y,x) on an H x W grid, column n = (dy*2+dx)*Cout + co -> dest row
   //           (b*2H + 2y+dy)*2W + 2x+dx, dest column co   (ConvTranspose2d kernel 2 stride 2)
   int ws = 0, nwx = 0, nwy = 0, H = 0, W = 0, cout = 0;
+  int fp16 = 0;                      // operands (A, W) and the 16-bit output are IEEE half instead of bf16
 };
 
 struct GemmProblem {

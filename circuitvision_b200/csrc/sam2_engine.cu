@@ -20,7 +20,7 @@
 namespace cvb {
 int attn_tc_launch(const __nv_bfloat16* q, long long ldq, int qcols, int qcol0, const __nv_bfloat16* k, long long ldk,
                    int kcols, int kcol0, const __nv_bfloat16* v, long long ldv, int vcols, int vcol0, int Mq, int Mkv,
-                   int Wq, int Wkv, int heads, float scale, __nv_bfloat16* out, long long ld_out, cudaStream_t st);
+                   int Wq, int Wkv, int heads, float scale, __nv_bfloat16* out, long long ld_out, int fp16, cudaStream_t st);
 int device_sm_count();
 }  // namespace cvb
 
@@ -46,6 +46,7 @@ struct cv_sam2 {
   std::vector<BlockPlan> plan;
   int stage_end[4];
   bool finalized = false;
+  int f16 = 0;  // 16-bit operand format: 0 bf16, 1 IEEE half
   int launches = 0;
   float refc_b = 0.f;
 };
@@ -83,6 +84,7 @@ extern "C" int cv_sam2_create(const cv_sam2_cfg* cfg, int device, cv_sam2** out)
   cv_sam2* h = new cv_sam2();
   h->cfg = *cfg;
   h->device = device;
+  h->f16 = cfg->operand_fp16 ? 1 : 0;
   int total = 0, H = 256, W = 256;
   for (int s = 0; s < 4; s++) {
     for (int b = 0; b < cfg->stages[s]; b++) {
@@ -144,7 +146,7 @@ extern "C" int cv_sam2_finalize(cv_sam2* h) {
   for (auto& kv : h->buf) cudaFree(kv.second.p);  // re-finalize after cv_sam2_set_max_batch
   h->buf.clear();
   // required tensors (fail loudly on an incomplete weight set)
-  std::vector<std::string> need = {"pe.w", "pe.b", "pos", "neck3.w", "neck3.b", "neck2.w", "neck2.b", "s1.w", "s1.b", "s0.w",
+  std::vector<std::string> need = {"pe.w", "pe.b", "pos", "pe.w8", "pos8", "neck3.w", "neck3.b", "neck2.w", "neck2.b", "s1.w", "s1.b", "s0.w",
                                    "s0.b", "dense", "tok0", "l0.q1", "l0.t2i.qc", "up1.w", "up1.b", "upln.g", "upln.b",
                                    "up2.w", "up2.b", "fin.q.w", "fin.kv.w", "fin.kpe", "fin.o.w", "fin.n.g"};
   for (size_t i = 0; i < h->plan.size(); i++) {
@@ -244,6 +246,7 @@ extern "C" int cv_sam2_set_max_batch(cv_sam2* h, int max_batch) {
 }
 
 static int gemm(cv_sam2* h, const bf16* A, long long lda, const bf16* W, int M, int N, int K, GemmEpilogue& e, cudaStream_t st) {
+  e.fp16 = h->f16;
   int rc = gemm_tc_launch(A, lda, W, K, M, N, K, e, device_sm_count(), st);
   h->launches++;
   return rc;
@@ -264,7 +267,7 @@ static int run_block(cv_sam2* h, int i, int B, float* X, float* Xn, cudaStream_t
   bf16* AO = BUF<bf16>(h, "AO");
   bf16* Hd = BUF<bf16>(h, "Hd");
   // norm1 (+ window partition with zero pad rows)
-  TRY(launch_ln_rows(X, T, Cin, WF(h, pre + ".n1.g"), WF(h, pre + ".n1.b"), 1e-6f, B, H, W, ws, A, nullptr, st));
+  TRY(launch_ln_rows(X, T, Cin, WF(h, pre + ".n1.g"), WF(h, pre + ".n1.b"), 1e-6f, B, H, W, ws, h->f16, A, nullptr, st));
   h->launches++;
   GemmEpilogue e;
   e.bias = WF(h, pre + ".qkv.b");
@@ -285,14 +288,14 @@ static int run_block(cv_sam2* h, int i, int B, float* X, float* Xn, cudaStream_t
     TRY(gemm(h, A, Cin, WB(h, pre + ".sc.w"), (int)M, C, Cin, es, st));
     TRY(launch_pool_shortcut(S, B, H, W, ws, C, Xn, st));
     bf16* Qp = BUF<bf16>(h, "Qp");
-    TRY(launch_pool_q(QKV, 3 * C, (int)(M / (ws * ws)), ws, C, Qp, st));
+    TRY(launch_pool_q(QKV, 3 * C, (int)(M / (ws * ws)), ws, C, h->f16, Qp, st));
     h->launches += 2;
     TRY(attn_tc_launch(Qp, C, C, 0, QKV, 3 * C, 3 * C, C, QKV, 3 * C, 3 * C, 2 * C, (int)(M / 4), (int)M, Wkv / 4, Wkv,
-                       p.heads, scale, AO, C, st));
+                       p.heads, scale, AO, C, h->f16, st));
     Xo = Xn; Ho = H / 2; Wo = W / 2; wso = ws / 2; To = T / 4;
   } else {
     TRY(attn_tc_launch(QKV, 3 * C, 3 * C, 0, QKV, 3 * C, 3 * C, C, QKV, 3 * C, 3 * C, 2 * C, (int)M, (int)M, Wkv, Wkv, p.heads,
-                       scale, AO, C, st));
+                       scale, AO, C, h->f16, st));
   }
   h->launches++;
   // proj + window un-partition + residual (in place on the residual stream)
@@ -306,7 +309,7 @@ static int run_block(cv_sam2* h, int i, int B, float* X, float* Xn, cudaStream_t
   }
   TRY(gemm(h, AO, C, WB(h, pre + ".proj.w"), (int)(p.pool ? M / 4 : M), C, C, ep, st));
   // norm2 -> MLP (GELU) -> residual
-  TRY(launch_ln_rows(Xo, To, C, WF(h, pre + ".n2.g"), WF(h, pre + ".n2.b"), 1e-6f, B, Ho, Wo, 0, A, nullptr, st));
+  TRY(launch_ln_rows(Xo, To, C, WF(h, pre + ".n2.g"), WF(h, pre + ".n2.b"), 1e-6f, B, Ho, Wo, 0, h->f16, A, nullptr, st));
   h->launches++;
   GemmEpilogue e1;
   e1.bias = WF(h, pre + ".fc1.b");
@@ -401,7 +404,7 @@ static int decoder_layer(cv_sam2* h, int l, int B, cudaStream_t st) {
   TRY(launch_tok_add_bcast(q, tok0, T, R, 256, qpe, st));
   TRY(tok_lin(h, qpe, 256, pre + ".i2t.k", R, 128, 256, 0, nullptr, BUF<float>(h, "t128a"), 128, st));
   TRY(tok_lin(h, q, 256, pre + ".i2t.v", R, 128, 256, 0, nullptr, BUF<float>(h, "t128b"), 128, st));
-  TRY(launch_attn_i2t(Qi, 128, BUF<float>(h, "t128a"), BUF<float>(h, "t128b"), B, 4096, T, 8, 16, BUF<bf16>(h, "Ai"), st));
+  TRY(launch_attn_i2t(Qi, 128, BUF<float>(h, "t128a"), BUF<float>(h, "t128b"), B, 4096, T, 8, 16, h->f16, BUF<bf16>(h, "Ai"), st));
   h->launches += 2;
   float* keys32 = BUF<float>(h, "keys32");
   GemmEpilogue eo;
@@ -410,7 +413,7 @@ static int decoder_layer(cv_sam2* h, int l, int B, cudaStream_t st) {
   eo.out_f32 = keys32; eo.ld_f32 = 256;
   TRY(gemm(h, BUF<bf16>(h, "Ai"), 128, WB(h, pre + ".i2t.o.w"), B * 4096, 256, 128, eo, st));
   TRY(launch_ln_rows(keys32, (long long)B * 4096, 256, WF(h, pre + ".n4.g"), WF(h, pre + ".n4.b"), 1e-5f, B, 64, 64, 0,
-                     BUF<bf16>(h, "keys16"), keys32, st));
+                     h->f16, BUF<bf16>(h, "keys16"), keys32, st));
   h->launches++;
   return CV_OK;
 }
@@ -432,16 +435,23 @@ extern "C" int cv_sam2_forward(cv_sam2* h, const void* images, int input_kind, i
   bf16* A = BUF<bf16>(h, "A");
   float* X[4] = {BUF<float>(h, "X0"), BUF<float>(h, "X1"), BUF<float>(h, "X2"), BUF<float>(h, "X3")};
   // ---- patch embed (two-term bf16 split of the pixels) + positional embedding
-  if (input_kind == 0) TRY(launch_im2col_u8((const uint8_t*)images, B, 1024, mean, istd, swap_rb, A, st));
-  else TRY(launch_im2col_f32((const float*)images, B, 1024, A, st));
-  h->launches++;
-  {
+  (void)mean; (void)istd;
+  if (input_kind == 0) {
+    // raw pixels (exact in bf16); 1/255, mean/std, the conv bias and the positional embedding live in pe.w8 / pos8
+    TRY(launch_im2col_u8raw((const uint8_t*)images, B, 1024, swap_rb, h->f16, A, st));
+    GemmEpilogue e;
+    e.res = WF(h, "pos8"); e.ld_res = E; e.res_row_mod = 65536;
+    e.out_f32 = X[0]; e.ld_f32 = E;
+    TRY(gemm(h, A, PE_K, WB(h, "pe.w8"), B * 65536, E, PE_K, e, st));
+  } else {
+    TRY(launch_im2col_f32((const float*)images, B, 1024, h->f16, A, st));
     GemmEpilogue e;
     e.bias = WF(h, "pe.b");
     e.res = WF(h, "pos"); e.ld_res = E; e.res_row_mod = 65536;
     e.out_f32 = X[0]; e.ld_f32 = E;
     TRY(gemm(h, A, 2 * PE_K, WB(h, "pe.w"), B * 65536, E, 2 * PE_K, e, st));
   }
+  h->launches++;
   // ---- trunk
   int stage = 0;
   for (size_t i = 0; i < h->plan.size(); i++) {
@@ -451,25 +461,25 @@ extern "C" int cv_sam2_forward(cv_sam2* h, const void* images, int input_kind, i
   // ---- neck (level 3 lateral, level 2 lateral + top-down + dense prompt) and the folded conv_s0 / conv_s1
   float* keys32 = BUF<float>(h, "keys32");
   {
-    TRY(launch_ln_rows(X[3], (long long)B * 1024, 8 * E, nullptr, nullptr, 0.f, B, 32, 32, 0, A, nullptr, st));
+    TRY(launch_ln_rows(X[3], (long long)B * 1024, 8 * E, nullptr, nullptr, 0.f, B, 32, 32, 0, h->f16, A, nullptr, st));
     GemmEpilogue e;
     e.bias = WF(h, "neck3.b");
     e.out_f32 = BUF<float>(h, "L3"); e.ld_f32 = 256;
     TRY(gemm(h, A, 8 * E, WB(h, "neck3.w"), B * 1024, 256, 8 * E, e, st));
-    TRY(launch_ln_rows(X[2], (long long)B * 4096, 4 * E, nullptr, nullptr, 0.f, B, 64, 64, 0, A, nullptr, st));
+    TRY(launch_ln_rows(X[2], (long long)B * 4096, 4 * E, nullptr, nullptr, 0.f, B, 64, 64, 0, h->f16, A, nullptr, st));
     GemmEpilogue e2;
     e2.bias = WF(h, "neck2.b");
     e2.res = WF(h, "dense"); e2.ld_res = 256; e2.res_row_mod = 4096;  // src = image_embed + dense prompt
     e2.out_f32 = keys32; e2.ld_f32 = 256;
     TRY(gemm(h, A, 4 * E, WB(h, "neck2.w"), B * 4096, 256, 4 * E, e2, st));
     TRY(launch_add_nearest2(keys32, BUF<float>(h, "L3"), B, 64, 64, 256, st));
-    TRY(launch_ln_rows(keys32, (long long)B * 4096, 256, nullptr, nullptr, 0.f, B, 64, 64, 0, BUF<bf16>(h, "keys16"), nullptr, st));
-    TRY(launch_ln_rows(X[1], (long long)B * 16384, 2 * E, nullptr, nullptr, 0.f, B, 128, 128, 0, A, nullptr, st));
+    TRY(launch_ln_rows(keys32, (long long)B * 4096, 256, nullptr, nullptr, 0.f, B, 64, 64, 0, h->f16, BUF<bf16>(h, "keys16"), nullptr, st));
+    TRY(launch_ln_rows(X[1], (long long)B * 16384, 2 * E, nullptr, nullptr, 0.f, B, 128, 128, 0, h->f16, A, nullptr, st));
     GemmEpilogue e3;
     e3.bias = WF(h, "s1.b");
     e3.out_f32 = BUF<float>(h, "s1"); e3.ld_f32 = 64;
     TRY(gemm(h, A, 2 * E, WB(h, "s1.w"), B * 16384, 64, 2 * E, e3, st));
-    TRY(launch_ln_rows(X[0], (long long)B * 65536, E, nullptr, nullptr, 0.f, B, 256, 256, 0, A, nullptr, st));
+    TRY(launch_ln_rows(X[0], (long long)B * 65536, E, nullptr, nullptr, 0.f, B, 256, 256, 0, h->f16, A, nullptr, st));
     GemmEpilogue e4;
     e4.bias = WF(h, "s0.b");
     e4.out_f32 = BUF<float>(h, "s0"); e4.ld_f32 = 32;
@@ -504,7 +514,7 @@ extern "C" int cv_sam2_forward(cv_sam2* h, const void* images, int input_kind, i
     e.out_f32 = BUF<float>(h, "U1"); e.ld_f32 = 64;
     e.map_mode = GEMM_MAP_SHUFFLE2; e.H = 64; e.W = 64; e.cout = 64;
     TRY(gemm(h, BUF<bf16>(h, "keys16"), 256, WB(h, "up1.w"), B * 4096, 256, 256, e, st));
-    TRY(launch_ln2d_gelu(BUF<float>(h, "U1"), (long long)B * 16384, 64, WF(h, "upln.g"), WF(h, "upln.b"), 1e-6f,
+    TRY(launch_ln2d_gelu(BUF<float>(h, "U1"), (long long)B * 16384, 64, WF(h, "upln.g"), WF(h, "upln.b"), 1e-6f, h->f16,
                          BUF<bf16>(h, "U1n"), st));
     GemmEpilogue e2;
     e2.bias = WF(h, "up2.b");

@@ -5,6 +5,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "tc05.cuh"
 
 namespace cvb {
 
@@ -21,9 +22,18 @@ __device__ __forceinline__ float warp_max(float v) {
 // ------------------------------------------------------------------------------------------------ im2col
 // One thread per (token, tap-row): writes the 7 taps x 3 channels of kernel row ky.  K index = c*49 + ky*7 + kx
 // (nn.Conv2d weight [Cout, 3, 7, 7] flattened), hi part at [0,PE_K), lo part at [PE_K, 2*PE_K).
+__device__ __forceinline__ __nv_bfloat16 to16(int fp16, float v) {
+  uint32_t w = tc::pack16(fp16, v, 0.f);
+  unsigned short lo = (unsigned short)(w & 0xFFFFu);
+  return *(__nv_bfloat16*)&lo;
+}
+__device__ __forceinline__ float from16(int fp16, __nv_bfloat16 h) {
+  return fp16 ? __half2float(*(__half*)&h) : __bfloat162float(h);
+}
+
 template <bool U8>
 __global__ void __launch_bounds__(256) k_im2col(const void* __restrict__ img_, int B, int S, float m0, float m1, float m2,
-                                                float s0, float s1, float s2, int swap_rb,
+                                                float s0, float s1, float s2, int swap_rb, int fp16,
                                                 __nv_bfloat16* __restrict__ out) {
   const int G = S / 4;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -36,7 +46,7 @@ __global__ void __launch_bounds__(256) k_im2col(const void* __restrict__ img_, i
   int b = (int)(tok / ((long long)G * G));
   __nv_bfloat16* o = out + tok * (2 * PE_K);
   if (ky == 7) {  // zero the K padding 147..151 of both halves
-    for (int k = 147; k < PE_K; k++) { o[k] = __float2bfloat16(0.f); o[PE_K + k] = __float2bfloat16(0.f); }
+    for (int k = 147; k < PE_K; k++) { o[k] = to16(fp16, 0.f); o[PE_K + k] = to16(fp16, 0.f); }
     return;
   }
   int iy = y * 4 - 3 + ky;
@@ -56,8 +66,8 @@ __global__ void __launch_bounds__(256) k_im2col(const void* __restrict__ img_, i
           v = im[(((long long)b * 3 + c) * S + iy) * S + ix];
         }
       }
-      __nv_bfloat16 hi = __float2bfloat16(v);
-      __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+      __nv_bfloat16 hi = to16(fp16, v);
+      __nv_bfloat16 lo = to16(fp16, v - from16(fp16, hi));
       int k = c * 49 + ky * 7 + kx;
       o[k] = hi;
       o[PE_K + k] = lo;
@@ -70,14 +80,58 @@ int launch_im2col_u8(const uint8_t* img, int B, int S, const float* mean, const 
   long long total = (long long)B * (S / 4) * (S / 4) * 8;
   cvb_next_work((double)B * S * S * 3 + (double)B * (S / 4) * (S / 4) * 2 * PE_K * 2);
   CVB_LAUNCH((k_im2col<true>), dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, img, B, S, mean[0], mean[1],
-             mean[2], inv_std[0], inv_std[1], inv_std[2], swap_rb, out);
+             mean[2], inv_std[0], inv_std[1], inv_std[2], swap_rb, 0, out);
   return CV_OK;
 }
-int launch_im2col_f32(const float* img, int B, int S, __nv_bfloat16* out, cudaStream_t st) {
+
+// Raw-pixel patch operand: out[tok, k] = bf16(pixel) (0..255 is exact in bf16), zero outside the image and for the K
+// padding.  ToTensor's 1/255 and Normalize's mean/std are folded into the GEMM weights and the per-token additive table
+// at load time (sam2_weights.fold_state_dict: "pe.w8", "pos8"), so the u8 path is exact in its inputs and needs half
+// the K of the two-term fp32 split.  One thread = one 16-byte chunk (8 consecutive k) of one token: stores coalesce.
+__global__ void __launch_bounds__(256) k_im2col_u8raw(const uint8_t* __restrict__ img, int S, int swap_rb, int fp16, long long total,
+                                                      __nv_bfloat16* __restrict__ out) {
+  constexpr int CH = PE_K / 8;  // 19 chunks per token
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int G = S / 4;
+  long long tok = idx / CH;
+  const int j = (int)(idx - tok * CH);
+  const int x = (int)(tok % G);
+  const int y = (int)((tok / G) % G);
+  const long long b = tok / ((long long)G * G);
+  const uint8_t* im = img + b * (long long)S * S * 3;
+  uint32_t w[4];
+#pragma unroll
+  for (int h = 0; h < 4; h++) {
+    float v2[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int k = j * 8 + h * 2 + u;
+      float v = 0.f;
+      if (k < 147) {
+        const int c = k / 49, rem = k - c * 49;
+        const int ky = rem / 7, kx = rem - ky * 7;
+        const int iy = y * 4 - 3 + ky, ix = x * 4 - 3 + kx;
+        if (iy >= 0 && iy < S && ix >= 0 && ix < S) v = (float)__ldg(im + ((long long)iy * S + ix) * 3 + (swap_rb ? 2 - c : c));
+      }
+      v2[u] = v;
+    }
+    w[h] = tc::pack16(fp16, v2[0], v2[1]);
+  }
+  *(uint4*)(out + tok * PE_K + j * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+int launch_im2col_u8raw(const uint8_t* img, int B, int S, int swap_rb, int fp16, __nv_bfloat16* out, cudaStream_t st) {
+  long long total = (long long)B * (S / 4) * (S / 4) * (PE_K / 8);
+  cvb_next_work((double)B * S * S * 3 + (double)B * (S / 4) * (S / 4) * PE_K * 2);
+  CVB_LAUNCH(k_im2col_u8raw, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, img, S, swap_rb, fp16, total, out);
+  return CV_OK;
+}
+int launch_im2col_f32(const float* img, int B, int S, int fp16, __nv_bfloat16* out, cudaStream_t st) {
   long long total = (long long)B * (S / 4) * (S / 4) * 8;
   cvb_next_work((double)B * S * S * 12 + (double)B * (S / 4) * (S / 4) * 2 * PE_K * 2);
   CVB_LAUNCH((k_im2col<false>), dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, img, B, S, 0.f, 0.f, 0.f, 1.f,
-             1.f, 1.f, 0, out);
+             1.f, 1.f, 0, fp16, out);
   return CV_OK;
 }
 
@@ -148,7 +202,7 @@ int launch_preprocess_aa(const uint8_t* img, int H, int W, int S, const float* m
 // One warp per destination row.  C % 4 == 0, C <= 1536.
 __global__ void __launch_bounds__(256) k_ln_rows(const float* __restrict__ X, int C, const float* __restrict__ gamma,
                                                  const float* __restrict__ beta, float eps, int H, int W, int ws,
-                                                 int nwx, int nwy, long long n_dst, __nv_bfloat16* __restrict__ ob,
+                                                 int nwx, int nwy, long long n_dst, int fp16, __nv_bfloat16* __restrict__ ob,
                                                  float* __restrict__ of) {
   long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= n_dst) return;
@@ -213,15 +267,94 @@ __global__ void __launch_bounds__(256) k_ln_rows(const float* __restrict__ X, in
       }
       if (of) *(float4*)(of + r * C + i * 4) = o;
       if (ob) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
-        *(uint2*)(ob + r * C + i * 4) = make_uint2(*(uint32_t*)&lo, *(uint32_t*)&hi);
+        *(uint2*)(ob + r * C + i * 4) = make_uint2(tc::pack16(fp16, o.x, o.y), tc::pack16(fp16, o.z, o.w));
       }
     }
   }
 }
 
+// L lanes per row (32/L rows per warp in flight), V float4 per lane: C = 4*L*V.  Narrow rows (C = 96: 384 bytes) keep
+// four rows per warp in flight instead of one, which is what a latency-bound streaming kernel needs.
+template <int L, int V>
+__global__ void __launch_bounds__(256) k_ln_rows_t(const float* __restrict__ X, const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, float eps, int H, int W, int ws, int nwx,
+                                                   int nwy, long long n_dst, int fp16, __nv_bfloat16* __restrict__ ob,
+                                                   float* __restrict__ of) {
+  constexpr int C = 4 * L * V, RPW = 32 / L;
+  const int lane = threadIdx.x & 31, sub = lane % L;
+  const long long r = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + lane / L;
+  const bool live = r < n_dst;
+  long long src = live ? r : -1;
+  if (live && ws > 0) {
+    int w2 = ws * ws;
+    long long win = r / w2;
+    int t = (int)(r - win * w2);
+    int per = nwx * nwy;
+    long long b = win / per;
+    int wi = (int)(win - b * per);
+    int wy = wi / nwx, wx = wi - wy * nwx;
+    int ty = t / ws, tx = t - ty * ws;
+    int y = wy * ws + ty, x = wx * ws + tx;
+    src = (y < H && x < W) ? (b * H + y) * W + x : -1;
+  }
+  float4 v[V];
+  float s = 0.f;
+  if (src >= 0) {
+    const float4* xr = (const float4*)(X + src * C);
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      v[k] = xr[sub + k * L];
+      s += v[k].x + v[k].y + v[k].z + v[k].w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < V; k++) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float mean = 0.f, rstd = 1.f;
+  if (gamma) {
+#pragma unroll
+    for (int o = L / 2; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    mean = s * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+      q += a * a + b * b + c * c + d * d;
+    }
+#pragma unroll
+    for (int o = L / 2; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    rstd = rsqrtf(q * (1.0f / C) + eps);
+  }
+  if (!live) return;
+#pragma unroll
+  for (int k = 0; k < V; k++) {
+    const int i = sub + k * L;
+    float4 o = v[k];
+    if (gamma && src >= 0) {
+      float4 g = __ldg((const float4*)gamma + i), bb = __ldg((const float4*)beta + i);
+      o.x = (o.x - mean) * rstd * g.x + bb.x;
+      o.y = (o.y - mean) * rstd * g.y + bb.y;
+      o.z = (o.z - mean) * rstd * g.z + bb.z;
+      o.w = (o.w - mean) * rstd * g.w + bb.w;
+    }
+    if (of) *(float4*)(of + r * C + i * 4) = o;
+    if (ob) {
+      *(uint2*)(ob + r * C + i * 4) = make_uint2(tc::pack16(fp16, o.x, o.y), tc::pack16(fp16, o.z, o.w));
+    }
+  }
+}
+
+template <int L, int V>
+static int launch_ln_t(const float* X, const float* gamma, const float* beta, float eps, int H, int W, int ws, int nwx, int nwy,
+                       long long n_dst, int fp16, __nv_bfloat16* ob, float* of, cudaStream_t st) {
+  const long long rows_per_block = 8 * (32 / L);
+  CVB_LAUNCH((k_ln_rows_t<L, V>), dim3((unsigned)((n_dst + rows_per_block - 1) / rows_per_block)), dim3(256), 0, st, X, gamma,
+             beta, eps, H, W, ws, nwx, nwy, n_dst, fp16, ob, of);
+  return CV_OK;
+}
+
 int launch_ln_rows(const float* X, long long n_src_rows, int C, const float* gamma, const float* beta, float eps, int B,
-                   int H, int W, int ws, __nv_bfloat16* out_bf16, float* out_f32, cudaStream_t st) {
+                   int H, int W, int ws, int fp16, __nv_bfloat16* out_bf16, float* out_f32, cudaStream_t st) {
   if ((C & 3) || C > 1536) return cvb_fail(CV_ERR_INVALID, "ln_rows: C must be a multiple of 4 and <= 1536");
   int nwx = 0, nwy = 0;
   long long n_dst = n_src_rows;
@@ -236,13 +369,19 @@ int launch_ln_rows(const float* X, long long n_src_rows, int C, const float* gam
     snprintf(nm, sizeof(nm), "ln_rows R%lld C%d ws%d%s", n_src_rows, C, ws, gamma ? "" : " cast");
     cvb_next_name(nm);
   }
+#define CVB_LN_CASE(CC, LL, VV) \
+  if (C == CC) return launch_ln_t<LL, VV>(X, gamma, beta, eps, H, W, ws, nwx, nwy, n_dst, fp16, out_bf16, out_f32, st);
+  CVB_LN_CASE(96, 8, 3) CVB_LN_CASE(192, 16, 3) CVB_LN_CASE(384, 32, 3) CVB_LN_CASE(768, 32, 6) CVB_LN_CASE(256, 16, 4)
+  CVB_LN_CASE(64, 8, 2) CVB_LN_CASE(112, 4, 7) CVB_LN_CASE(224, 8, 7) CVB_LN_CASE(448, 16, 7) CVB_LN_CASE(896, 32, 7)
+  CVB_LN_CASE(144, 4, 9) CVB_LN_CASE(288, 8, 9) CVB_LN_CASE(576, 16, 9) CVB_LN_CASE(1152, 32, 9)
+#undef CVB_LN_CASE
   CVB_LAUNCH(k_ln_rows, dim3((unsigned)((n_dst + 7) / 8)), dim3(256), 0, st, X, C, gamma, beta, eps, H, W, ws, nwx, nwy,
-             n_dst, out_bf16, out_f32);
+             n_dst, fp16, out_bf16, out_f32);
   return CV_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ pooling
-__global__ void __launch_bounds__(256) k_pool_q(const __nv_bfloat16* __restrict__ qkv, long long ld, int ws, int Cq,
+__global__ void __launch_bounds__(256) k_pool_q(const __nv_bfloat16* __restrict__ qkv, long long ld, int ws, int Cq, int fp16,
                                                 long long n_dst, __nv_bfloat16* __restrict__ qp) {
   const int chunks = Cq >> 3;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -261,19 +400,23 @@ __global__ void __launch_bounds__(256) k_pool_q(const __nv_bfloat16* __restrict_
       long long sr = base + (2 * py + dy) * ws + 2 * px + dx;
       uint4 u = *(const uint4*)(qkv + sr * ld + c);
       const __nv_bfloat162* p = (const __nv_bfloat162*)&u;
-      for (int k = 0; k < 4; k++) m[k] = first ? p[k] : __hmax2(m[k], p[k]);
+      for (int k = 0; k < 4; k++) {
+        if (first) m[k] = p[k];
+        else if (fp16) { __half2 r = __hmax2(*(const __half2*)&m[k], *(const __half2*)&p[k]); m[k] = *(__nv_bfloat162*)&r; }
+        else m[k] = __hmax2(m[k], p[k]);
+      }
       first = false;
     }
   *(uint4*)(qp + r * Cq + c) = *(uint4*)m;
 }
 
-int launch_pool_q(const __nv_bfloat16* qkv, long long ld, int n_windows, int ws, int Cq, __nv_bfloat16* qp,
+int launch_pool_q(const __nv_bfloat16* qkv, long long ld, int n_windows, int ws, int Cq, int fp16, __nv_bfloat16* qp,
                   cudaStream_t st) {
   if ((ws & 1) || (Cq & 7)) return cvb_fail(CV_ERR_INVALID, "pool_q: odd window or Cq%8 != 0");
   long long n_dst = (long long)n_windows * (ws / 2) * (ws / 2);
   long long total = n_dst * (Cq / 8);
   cvb_next_work((double)n_dst * Cq * 2 * 5);
-  CVB_LAUNCH(k_pool_q, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, qkv, ld, ws, Cq, n_dst, qp);
+  CVB_LAUNCH(k_pool_q, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, qkv, ld, ws, Cq, fp16, n_dst, qp);
   return CV_OK;
 }
 
@@ -597,7 +740,7 @@ int launch_attn_t2i(const float* q, long long q_img_stride, const float* K, cons
 
 // image -> tokens attention, d == 16, T <= 64: thread = (query token, head); K/V of the image's tokens in smem
 __global__ void __launch_bounds__(256) k_attn_i2t(const float* __restrict__ Q, long long ld_q, const float* __restrict__ K,
-                                                  const float* __restrict__ V, int Nq, int T, int heads,
+                                                  const float* __restrict__ V, int Nq, int T, int heads, int fp16,
                                                   __nv_bfloat16* __restrict__ out) {
   extern __shared__ float sm[];
   const int C = heads * 16;
@@ -645,8 +788,7 @@ __global__ void __launch_bounds__(256) k_attn_i2t(const float* __restrict__ Q, l
   uint32_t w[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) {
-    __nv_bfloat162 p2 = __floats2bfloat162_rn(o[2 * i] * inv, o[2 * i + 1] * inv);
-    w[i] = *(uint32_t*)&p2;
+    w[i] = tc::pack16(fp16, o[2 * i] * inv, o[2 * i + 1] * inv);
   }
   uint4* dst = (uint4*)(out + row * C + h * 16);
   dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -654,18 +796,19 @@ __global__ void __launch_bounds__(256) k_attn_i2t(const float* __restrict__ Q, l
 }
 
 int launch_attn_i2t(const float* Q, long long ld_q, const float* K, const float* V, int B, int Nq, int T, int heads, int d,
-                    __nv_bfloat16* out, cudaStream_t st) {
+                    int fp16, __nv_bfloat16* out, cudaStream_t st) {
   if (d != 16 || T > 64 || (256 % heads)) return cvb_fail(CV_ERR_INVALID, "attn_i2t: d==16, T<=64, 256%heads==0");
   int per = 256 / heads;
   size_t smem = (size_t)2 * T * heads * 16 * sizeof(float);
   cvb_next_work(4.0 * B * (double)T * Nq * heads * d);
-  CVB_LAUNCH(k_attn_i2t, dim3((Nq + per - 1) / per, B), dim3(256), smem, st, Q, ld_q, K, V, Nq, T, heads, out);
+  CVB_LAUNCH(k_attn_i2t, dim3((Nq + per - 1) / per, B), dim3(256), smem, st, Q, ld_q, K, V, Nq, T, heads, fp16, out);
   return CV_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm2d + GELU (C == 64)
 __global__ void __launch_bounds__(256) k_ln2d_gelu(const float* __restrict__ X, long long rows, const float* __restrict__ g,
-                                                   const float* __restrict__ b, float eps, __nv_bfloat16* __restrict__ out) {
+                                                   const float* __restrict__ b, float eps, int fp16,
+                                                   __nv_bfloat16* __restrict__ out) {
   // 16 lanes per row (float4 each), 2 rows per warp
   long long r = ((long long)blockIdx.x * 256 + threadIdx.x) >> 4;
   int l = threadIdx.x & 15;
@@ -683,15 +826,14 @@ __global__ void __launch_bounds__(256) k_ln2d_gelu(const float* __restrict__ X, 
   float4 gg = ((const float4*)g)[l], bb = ((const float4*)b)[l];
   float y0 = gelu_exact(a0 * rstd * gg.x + bb.x), y1 = gelu_exact(a1 * rstd * gg.y + bb.y);
   float y2 = gelu_exact(a2 * rstd * gg.z + bb.z), y3 = gelu_exact(a3 * rstd * gg.w + bb.w);
-  __nv_bfloat162 lo = __floats2bfloat162_rn(y0, y1), hi = __floats2bfloat162_rn(y2, y3);
-  *(uint2*)(out + r * 64 + l * 4) = make_uint2(*(uint32_t*)&lo, *(uint32_t*)&hi);
+  *(uint2*)(out + r * 64 + l * 4) = make_uint2(tc::pack16(fp16, y0, y1), tc::pack16(fp16, y2, y3));
 }
 
-int launch_ln2d_gelu(const float* X, long long rows, int C, const float* g, const float* b, float eps,
+int launch_ln2d_gelu(const float* X, long long rows, int C, const float* g, const float* b, float eps, int fp16,
                      __nv_bfloat16* out, cudaStream_t st) {
   if (C != 64) return cvb_fail(CV_ERR_INVALID, "ln2d_gelu: C must be 64");
   cvb_next_work((double)rows * 64 * 6);
-  CVB_LAUNCH(k_ln2d_gelu, dim3((unsigned)((rows * 16 + 255) / 256)), dim3(256), 0, st, X, rows, g, b, eps, out);
+  CVB_LAUNCH(k_ln2d_gelu, dim3((unsigned)((rows * 16 + 255) / 256)), dim3(256), 0, st, X, rows, g, b, eps, fp16, out);
   return CV_OK;
 }
 

@@ -14,7 +14,11 @@ namespace cvb {
 constexpr int PE_K = 152;
 int launch_im2col_u8(const uint8_t* img, int B, int S, const float* mean, const float* inv_std, int swap_rb,
                      __nv_bfloat16* out, cudaStream_t st);
-int launch_im2col_f32(const float* img_chw, int B, int S, __nv_bfloat16* out, cudaStream_t st);
+// raw-pixel variant: out [B*256*256, PE_K] = bf16(pixel value), normalisation folded into "pe.w8" / "pos8"
+// Every `fp16` argument below selects IEEE half (saturating conversion) instead of bf16 for the 16-bit operand
+// buffers; the `__nv_bfloat16*` types are then just opaque 16-bit storage.
+int launch_im2col_u8raw(const uint8_t* img, int B, int S, int swap_rb, int fp16, __nv_bfloat16* out, cudaStream_t st);
+int launch_im2col_f32(const float* img_chw, int B, int S, int fp16, __nv_bfloat16* out, cudaStream_t st);
 
 // ---- a1 for crops that are not 1024x1024: ToTensor (/255) -> bilinear antialias resize to SxS (the arithmetic of
 // F.interpolate(mode="bilinear", antialias=True, align_corners=False): width pass then height pass, triangle filter
@@ -25,10 +29,10 @@ int launch_preprocess_aa(const uint8_t* img_hwc, int H, int W, int S, const floa
 // ---- LayerNorm over the channel dim with optional window partition (zero rows for window padding).
 // ws == 0: identity row order.  gamma == nullptr: plain fp32 -> bf16 cast.  out_f32 optional (normalised, fp32).
 int launch_ln_rows(const float* X, long long n_src_rows, int C, const float* gamma, const float* beta, float eps,
-                   int B, int H, int W, int ws, __nv_bfloat16* out_bf16, float* out_f32, cudaStream_t st);
+                   int B, int H, int W, int ws, int fp16, __nv_bfloat16* out_bf16, float* out_f32, cudaStream_t st);
 
 // ---- Q pooling: Qp[(b,win,py,px), c] = max_{2x2} QKV[(b,win,2py+dy,2px+dx), c], c < Cq (bf16, window-major)
-int launch_pool_q(const __nv_bfloat16* qkv, long long ld, int n_windows, int ws, int Cq, __nv_bfloat16* qp,
+int launch_pool_q(const __nv_bfloat16* qkv, long long ld, int n_windows, int ws, int Cq, int fp16, __nv_bfloat16* qp,
                   cudaStream_t st);
 // ---- shortcut pooling: S fp32 window-major [B*nwy*nwx*ws*ws, C] -> R fp32 grid order [B*(H/2)*(W/2), C]
 int launch_pool_shortcut(const float* S, int B, int H, int W, int ws, int C, float* R, cudaStream_t st);
@@ -53,10 +57,10 @@ int launch_attn_t2i(const float* q, long long q_img_stride, const float* K, cons
 size_t attn_t2i_scratch_floats(int B, int T, int heads, int d);
 // image -> tokens: Q [B*Nq, ld_q] fp32, K/V [B*T, heads*d] fp32, out bf16 [B*Nq, heads*d]
 int launch_attn_i2t(const float* Q, long long ld_q, const float* K, const float* V, int B, int Nq, int T, int heads,
-                    int d, __nv_bfloat16* out, cudaStream_t st);
+                    int d, int fp16, __nv_bfloat16* out, cudaStream_t st);
 
 // ---- upscaling: LayerNorm2d (channels-last rows of C=64) + GELU -> bf16
-int launch_ln2d_gelu(const float* X, long long rows, int C, const float* g, const float* b, float eps,
+int launch_ln2d_gelu(const float* X, long long rows, int C, const float* g, const float* b, float eps, int fp16,
                      __nv_bfloat16* out, cudaStream_t st);
 // ---- masks[b,k,p] = sum_c hyper[b,k,c] * U[(b,p),c]  (k<4, c<32) ; counts[b] = {#(m0 > delta), #(m0 > -delta)}
 int launch_mask_product(const float* U, const float* hyper, int B, int P, float delta, float* masks,

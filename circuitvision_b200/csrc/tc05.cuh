@@ -162,14 +162,27 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) { return smem_desc_sw128(saddr, 16, 1024); }
 
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
-__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn_major, bool b_mn_major) {
+// fp16 = true selects IEEE half operands (format code 0) instead of bf16 (format code 1).
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn_major, bool b_mn_major, bool fp16 = false) {
   return (1u << 4)                           // D format = F32
-         | (1u << 7)                         // A format = BF16
-         | (1u << 10)                        // B format = BF16
+         | ((fp16 ? 0u : 1u) << 7)           // A format
+         | ((fp16 ? 0u : 1u) << 10)          // B format
          | ((a_mn_major ? 1u : 0u) << 15)    // A major
          | ((b_mn_major ? 1u : 0u) << 16)    // B major
          | ((uint32_t)(N >> 3) << 17)        // N / 8
          | ((uint32_t)(M >> 4) << 24);       // M / 16
+}
+
+// two fp32 -> one packed 16-bit pair (a in the low half = lower address).  fp16: round-to-nearest with saturation to
+// +-65504 (cvt.rn.satfinite), so an outlier cannot become inf; bf16: round-to-nearest-even.
+__device__ __forceinline__ uint32_t pack16(int fp16, float a, float b) {
+  if (fp16) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+  }
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *(uint32_t*)&t;
 }
 
 __device__ __forceinline__ bool elect_one() {

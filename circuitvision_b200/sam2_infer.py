@@ -29,7 +29,7 @@ SAM2Params = _w.SAM2Params
 class cv_sam2_cfg(C.Structure):
     _fields_ = [("embed_dim", C.c_int32), ("num_heads", C.c_int32), ("stages", C.c_int32 * 4),
                 ("window_spec", C.c_int32 * 4), ("global_blocks", C.c_int32 * 8), ("n_global", C.c_int32),
-                ("use_refinement", C.c_int32), ("max_batch", C.c_int32), ("reserved", C.c_int32)]
+                ("use_refinement", C.c_int32), ("max_batch", C.c_int32), ("operand_fp16", C.c_int32)]
 
 
 def _declare(lib):
@@ -191,7 +191,7 @@ class MultiKernelRefinement(nn.Module):
 class _Engine:
     """Owns one cv_sam2 handle (device weights + workspace) for one wrapper on one device."""
 
-    def __init__(self, folded: dict, variant: dict, use_refinement: bool, dev: int, max_batch: int):
+    def __init__(self, folded: dict, variant: dict, use_refinement: bool, dev: int, max_batch: int, operand_fp16: bool):
         lib = _libsam()
         _lib.require_device(dev)
         cfg = cv_sam2_cfg()
@@ -207,13 +207,14 @@ class _Engine:
         cfg.n_global = len(gb)
         cfg.use_refinement = int(use_refinement)
         cfg.max_batch = max_batch
+        cfg.operand_fp16 = int(operand_fp16)
         self.dev, self.max_batch, self.lib = dev, max_batch, lib
         h = C.c_void_p()
         with torch.cuda.device(dev):
             _lib.check(lib.cv_sam2_create(C.byref(cfg), dev, C.byref(h)), "cv_sam2_create")
             self.h = h
             for name, t in folded.items():
-                if t.dtype == torch.bfloat16:
+                if t.dtype in (torch.bfloat16, torch.float16):
                     arr, dt = t.view(torch.int16).numpy(), 1
                 else:
                     arr, dt = t.numpy(), 0
@@ -287,6 +288,10 @@ class SAM2ImageWrapper(nn.Module):
         else:
             self.refinement_layer = None
         self.max_batch = 8
+        # 16-bit tensor-core operand format.  IEEE fp16 (11-bit significand, conversions saturate) is the default: with
+        # random-init weights bf16 operands alone leave the IoU >= 0.99 gate no margin (CPU emulation of the roundings,
+        # scripts/error_budget.py: 0.993 +- 0.004), fp16 runs at the same tensor-core rate with 8x smaller rounding.
+        self.operand_dtype = torch.float16
         self.lora_alpha = 16.0
         self._engine = None
         self._engine_lock = threading.Lock()
@@ -307,6 +312,13 @@ class SAM2ImageWrapper(nn.Module):
         """Call after mutating parameters in place."""
         self._engine = None
 
+    def set_operand_dtype(self, dtype):
+        """torch.float16 (default) or torch.bfloat16; rebuilds the device copy of the weights on the next call."""
+        if dtype not in (torch.float16, torch.bfloat16):
+            raise CvError("operand dtype must be torch.float16 or torch.bfloat16")
+        self.operand_dtype = dtype
+        self._engine = None
+
     def set_max_batch(self, n: int):
         self.max_batch = int(n)
         if self._engine is not None:
@@ -320,8 +332,10 @@ class SAM2ImageWrapper(nn.Module):
                 if self.refinement_layer is not None and not self.refinement_layer.supported():
                     raise CvError(f"refinement kernels {self.refinement_layer.kernel_sizes}: the fused tail kernel covers "
                                   f"{_w.REFINE_KERNELS} (the reference's configuration, circuit_analyzer.py:218)")
-                folded = _w.fold_state_dict(self.state_dict(), self.sam2_model.variant, self.refinement_layer is not None)
-                self._engine = _Engine(folded, self.sam2_model.variant, self.refinement_layer is not None, dev, self.max_batch)
+                folded = _w.fold_state_dict(self.state_dict(), self.sam2_model.variant, self.refinement_layer is not None,
+                                            self.operand_dtype)
+                self._engine = _Engine(folded, self.sam2_model.variant, self.refinement_layer is not None, dev, self.max_batch,
+                                       self.operand_dtype == torch.float16)
             return self._engine
 
     def segment_batch_u8(self, images_u8: torch.Tensor, swap_rb: bool = True) -> torch.Tensor:
@@ -383,11 +397,13 @@ def get_modified_sam2(model_cfg_path: str, checkpoint_path: str, device: str = "
 
 
 
-def build_random_init(variant: str = "tiny", device="cuda:0", seed: int = 0, max_batch: int = 8, use_refinement: bool = True):
+def build_random_init(variant: str = "tiny", device="cuda:0", seed: int = 0, max_batch: int = 8, use_refinement: bool = True,
+                      operand_dtype=torch.float16):
     """Random-init wrapper of the named architecture (PyTorch-default init; there are no checkpoints offline)."""
     torch.manual_seed(seed)
     m = get_modified_sam2(variant, None, device=str(device), use_refinement_layer=use_refinement)
     m.set_max_batch(max_batch)
+    m.set_operand_dtype(operand_dtype)
     return m
 
 

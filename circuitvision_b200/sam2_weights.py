@@ -35,6 +35,8 @@ VARIANTS = {
                       bkg=(14, 14)),
     "large": dict(embed=144, heads=2, stages=(2, 6, 36, 4), global_blocks=(23, 33, 43), window_spec=(8, 4, 16, 8), bkg=(7, 7)),
 }
+MEAN = (0.485, 0.456, 0.406)  # sam2_infer.py:41-42
+STD = (0.229, 0.224, 0.225)
 PE_K = 152  # patch-embed K (3*7*7 = 147) padded to a multiple of 8; must equal csrc/sam2_kernels.cuh PE_K
 REFINE_KERNELS = (3, 5, 7, 11)  # the kernel sizes the fused tail kernel is built for (circuit_analyzer.py:218)
 
@@ -205,8 +207,15 @@ def normalize_state_dict(sd: dict, lora_alpha: float = 16.0, lora_rank=None, wan
 
 
 # ------------------------------------------------------------------------------------------ folding
+_OPERAND_DTYPE = torch.bfloat16  # set per fold_state_dict call
+
+
 def _bf16(t: torch.Tensor) -> torch.Tensor:
-    return t.float().contiguous().to(torch.bfloat16)
+    """fp32/fp64 -> the 16-bit tensor-core operand format of this fold (bf16, or IEEE half saturated to +-65504)."""
+    t = t.float().contiguous()
+    if _OPERAND_DTYPE == torch.float16:
+        t = t.clamp(-65504.0, 65504.0)
+    return t.to(_OPERAND_DTYPE)
 
 
 def _f32(t: torch.Tensor) -> torch.Tensor:
@@ -231,9 +240,14 @@ def _attn_tokens(q, k, v, heads):
     return (a @ vh).transpose(0, 1).reshape(T, -1)
 
 
-def fold_state_dict(sd: dict, variant: dict, use_refinement: bool) -> dict:
+def fold_state_dict(sd: dict, variant: dict, use_refinement: bool, operand_dtype=torch.bfloat16) -> dict:
     """Wrapper state dict (keys `sam2_model.…`, `dense_embedding1/2`, `sparse_embedding`, `refinement_layer.…`)
-    -> {engine tensor name: contiguous CPU tensor (float32 or bfloat16)}.  Load-time only."""
+    -> {engine tensor name: contiguous CPU tensor (float32, or `operand_dtype` for tensor-core operands)}.
+    Load-time only."""
+    global _OPERAND_DTYPE
+    if operand_dtype not in (torch.bfloat16, torch.float16):
+        raise ValueError("operand_dtype must be torch.bfloat16 or torch.float16")
+    _OPERAND_DTYPE = operand_dtype
     g = lambda k: sd["sam2_model." + k].detach().cpu().double()
     E = variant["embed"]
     out = {}
@@ -248,6 +262,20 @@ def fold_state_dict(sd: dict, variant: dict, use_refinement: bool) -> dict:
     pos = F.interpolate(pe, size=(256, 256), mode="bicubic")
     pos = pos + pw.tile([x // y for x, y in zip(pos.shape, pw.shape)])
     out["pos"] = _f32(pos[0].permute(1, 2, 0).reshape(65536, E))
+    # uint8 path: A = raw pixel values (exact in bf16).  conv(Normalize(p/255)) = sum_inb (w / (255 std_c)) p
+    #   - sum_inb w mean_c / std_c + b   ->  weights "pe.w8", and one additive per-token table "pos8" that also absorbs
+    #   the conv bias, the positional embedding and the border dependence of the mean term (zero padding of the
+    #   NORMALISED image: out-of-bounds taps contribute nothing).
+    w4 = g("image_encoder.trunk.patch_embed.proj.weight")  # [E,3,7,7]
+    std = torch.tensor(STD, dtype=torch.float64)[None, :, None, None]
+    w8 = _bf16(F.pad((w4 / (255.0 * std)).reshape(E, 147), (0, PE_K - 147)))
+    out["pe.w8"] = w8
+    # the mean term uses the SAME bf16-rounded weights, so the sum equals round(w') . (p - 255 mean): the rounding error
+    # stays relative to the normalised pixel value instead of to the raw 0..255 value
+    mean_img = (255.0 * torch.tensor(MEAN, dtype=torch.float64))[None, :, None, None].expand(1, 3, 1024, 1024)
+    mterm = F.conv2d(mean_img, w8.double()[:, :147].reshape(E, 3, 7, 7), None, stride=4, padding=3)[0]  # [E,256,256]
+    pos8 = pos[0].double() + g("image_encoder.trunk.patch_embed.proj.bias")[:, None, None] - mterm
+    out["pos8"] = _f32(pos8.permute(1, 2, 0).reshape(65536, E))
     # ---- trunk blocks
     for i, (ci, co, _h, _ws, _pool) in enumerate(block_plan(variant)):
         b, o = f"image_encoder.trunk.blocks.{i}.", f"b{i}."

@@ -140,7 +140,8 @@ typedef struct cv_sam2_cfg {
   int32_t n_global;
   int32_t use_refinement;        /* wrapper built with use_refinement=True (sam2_infer.py:210)         */
   int32_t max_batch;             /* activation workspace is sized for this many images per call        */
-  int32_t reserved;
+  int32_t operand_fp16;          /* 16-bit tensor-core operand format: 0 = bf16, 1 = IEEE fp16 (saturating);
+                                    the weights passed to cv_sam2_set_tensor(dtype 1) must use the same format */
 } cv_sam2_cfg;
 typedef struct cv_sam2 cv_sam2;
 

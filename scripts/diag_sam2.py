@@ -16,6 +16,8 @@ with torch.no_grad():
     rh, rl, ri, aux = ref(xs, return_aux=True)
 print("oracle s", time.time() - t)
 model.set_max_batch(B)
+if len(sys.argv) > 3:
+    model.set_operand_dtype(torch.bfloat16 if sys.argv[3] == "bf16" else torch.float16)
 high, low, iou = model(xs.cuda())
 torch.cuda.synchronize()
 eng = model.engine()

@@ -1,9 +1,11 @@
 """GPU parity of the SAM 2.1 path (through the C ABI, via the sam2_infer drop-in classes) against the fp32 CPU oracle
 with identical random-init weights (oracle/sam2_oracle.py; PARITY UNPINNED by reference tests — see its header).
 
-Tolerances (bf16 MMA operands, fp32 accumulation / residual stream / softmax / LayerNorm):
-  * thresholded mask IoU vs the fp32 oracle >= 0.99 per image (BASELINE.json north_star);
-  * low-res logits: max |err| <= 8 % and mean |err| <= 1.5 % of the logit standard deviation;
+Tolerances (16-bit MMA operands, fp32 accumulation / residual stream / softmax / LayerNorm):
+  * thresholded mask IoU vs the fp32 oracle >= 0.99 per image (BASELINE.json north_star) — the default IEEE-fp16
+    operand format is held to >= 0.997 (measured 0.9987-0.9991); the bf16 operand mode is held to >= 0.985
+    (measured 0.994-0.996; a CPU emulation of the bf16 roundings alone gives 0.993 +- 0.004, scripts/error_budget.py);
+  * low-res logits (fp16 operands): max |err| <= 1.5 % and mean |err| <= 0.3 % of the logit standard deviation;
   * predicted IoU: |err| <= 1e-3; the stability / best-IoU token selection must be identical.
 The fp32 CUDA-core pieces (preprocess, logits resize, refinement head) are held to fp32 round-off."""
 import numpy as np
@@ -52,19 +54,38 @@ def test_forward_parity_tiny(pair, inputs):
     assert torch.equal(sel, want)
     std = rl.std().item()
     d = (low.cpu() - rl).abs()
-    assert d.max().item() <= 0.08 * std and d.mean().item() <= 0.015 * std, (d.max().item() / std, d.mean().item() / std)
+    assert d.max().item() <= 0.015 * std and d.mean().item() <= 0.003 * std, (d.max().item() / std, d.mean().item() / std)
     assert (iou.cpu() - ri).abs().max().item() <= 1e-3
     fg = (rh > 0).float().mean().item()
     assert 0.05 < fg < 0.95, "degenerate oracle mask would make the IoU gate vacuous"
     for i in range(3):
-        assert _iou(high[i].cpu() > 0, rh[i] > 0) >= 0.99
-    # stage outputs of the trunk (fp32 residual stream) stay within 5 % of their spread
+        assert _iou(high[i].cpu() > 0, rh[i] > 0) >= 0.997
+    # stage outputs of the trunk (fp32 residual stream) stay within 1 % of their spread
     E = 96
     for s in range(4):
         hw = 256 >> s
         got = eng.read_buffer(f"X{s}", (3, hw, hw, E << s)).cpu()
         want_s = aux["trunk"][s].permute(0, 2, 3, 1)
-        assert (got - want_s).abs().max().item() <= 0.05 * want_s.std().item(), s
+        assert (got - want_s).abs().max().item() <= 0.01 * want_s.std().item(), s
+
+
+def test_bf16_operand_mode(pair, inputs):
+    """The same path with bf16 tensor-core operands (north_star's nominal format): looser, still above the 0.985 floor."""
+    ref, model = pair
+    with torch.no_grad():
+        rh, rl, ri = ref(inputs)
+    model.set_operand_dtype(torch.bfloat16)
+    try:
+        model.set_max_batch(3)
+        high, low, iou = model(inputs.cuda())
+        torch.cuda.synchronize()
+    finally:
+        model.set_operand_dtype(torch.float16)
+    std = rl.std().item()
+    d = (low.cpu() - rl).abs()
+    assert d.max().item() <= 0.08 * std and d.mean().item() <= 0.015 * std
+    for i in range(3):
+        assert _iou(high[i].cpu() > 0, rh[i] > 0) >= 0.985
 
 
 def test_batched_equals_stack_of_singles(pair, inputs):
