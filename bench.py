@@ -38,6 +38,8 @@ def _args():
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--variant", default="tiny")
+    ap.add_argument("--operands", default="fp16", choices=["fp16", "bf16"],
+                    help="16-bit tensor-core operand format of the SAM 2.1 path (DESIGN.md section 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with events in the timed region")
     return ap.parse_args()
@@ -249,7 +251,9 @@ def main():
     sam = None
     if use_sam2:
         from circuitvision_b200 import sam2_infer
-        sam = sam2_infer.build_random_init(a.variant, device=dev, seed=0, max_batch=B)
+        import torch as _t
+        sam = sam2_infer.build_random_init(a.variant, device=dev, seed=0, max_batch=B,
+                                           operand_dtype=_t.float16 if a.operands == "fp16" else _t.bfloat16)
     d_masks = [torch.from_numpy(m).to(dev) for m in pool_masks]
     h_masks = [torch.from_numpy(m).pin_memory() for m in pool_masks]
     d_boxes = [na.upload_boxes(bx, S, S) for bx in pool_boxes]
@@ -355,7 +359,7 @@ def main():
     kern_rows = []
     if table:
         # the library tags GEMM / attention / LayerNorm launches with their shapes; fold them back per kernel
-        alias = {"gemm ": "k_gemm_tc", "attn ": "k_attn_tc", "ln_rows ": "k_ln_rows"}
+        alias = {"gemm ": "k_gemm_tc", "attn_global ": "k_attn_global", "attn ": "k_attn_tc", "ln_rows ": "k_ln_rows"}
         folded = {}
         for r in table:
             name = next((v for k, v in alias.items() if r["name"].startswith(k)), r["name"])
@@ -372,7 +376,7 @@ def main():
         top = max(table, key=lambda r: r["ms"])
         avg_s = top["ms"] / 1e3 / max(1, top["launches"])
         wpl = top["work"] / max(1, top["launches"])
-        tensor = top["name"] in ("k_gemm_tc", "k_attn_tc")
+        tensor = top["name"] in ("k_gemm_tc", "k_attn_tc", "k_attn_global")
         if tensor:
             ach = wpl / avg_s / 1e12
             roofline = {"kernel": top["name"], "bound": "tensor", "achieved": ach, "peak": tens_peak, "unit": "TFLOP/s",
@@ -405,7 +409,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16 (fp32 accumulate) + u8/int32" if use_sam2 else "u8/int32",
+        "dtype": (("fp16" if a.operands == "fp16" else "bf16") + " tensor-core operands, fp32 accumulate + u8/int32") if use_sam2 else "u8/int32",
         "data": "synthetic",
         "config": {"workload": workload_name(workload, a), "images_per_gpu_per_step": B, "size": S,
                    "l2_policy": f"inputs rotate over a pool of {n_pool} batches ({n_pool * B * S * S * (13 if use_sam2 else 1) >> 20} MiB) larger than L2",

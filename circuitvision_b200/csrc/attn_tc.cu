@@ -530,7 +530,8 @@ int attn_tc_launch(const __nv_bfloat16* q, long long ldq, int qcols, int qcol0, 
   cvb_next_work(4.0 * (double)Mq * (double)Wkv * ATT_D * heads);
   if (cvb_profile_on()) {
     char nm[96];
-    snprintf(nm, sizeof(nm), "attn Mq%d Wq%d Wkv%d h%d", Mq, Wq, Wkv, heads);
+    const bool glob = Wq == Wkv && (Wkv % ATT_BN) == 0 && (Wq % (2 * ATT_BM)) == 0 && (Mq % (2 * ATT_BM)) == 0;
+    snprintf(nm, sizeof(nm), "%s Mq%d Wq%d Wkv%d h%d", glob ? "attn_global" : "attn", Mq, Wq, Wkv, heads);
     cvb_next_name(nm);
   }
   if (Wq == Wkv && (Wkv % ATT_BN) == 0 && (Wq % (2 * ATT_BM)) == 0 && (Mq % (2 * ATT_BM)) == 0) {
