@@ -501,6 +501,299 @@ k_attn_global(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
   }
 }
 
+// ------------------------------------------------------------------------------------------------ windowed attention
+// Persistent kernel for every block-diagonal case that is not global (Hiera's 8x8 / 4x4 / 14x14 / 7x7 windows and their
+// Q-pooled variants).  These are HBM-bound (a few hundred keys per query), so the design goal is streaming efficiency:
+//   * work item = (128-row query tile, head); a CTA walks pairs of items, one item per "slot" (slot = S/O TMEM region +
+//     Q buffer + 4 softmax warps), so the softmax of one item overlaps the loads and MMAs of the other;
+//   * K/V tiles of both slots flow through ONE 4-entry TMA ring in exactly the order the MMA warp consumes them;
+//   * P stays in TMEM (TS MMA), O accumulates in TMEM; per-row window masking; the reference keeps zero-pad tokens as
+//     ordinary keys, so padding is NOT masked — only keys of other windows are.
+// The running maximum is fixed at the first tile that has visible keys and O / l are rescaled only when a later tile
+// exceeds it by more than 2^8 (same exactness argument as the global kernel).
+constexpr int AW_THREADS = 384;
+constexpr int AW_RING = 4;
+constexpr int AW_SMEM = 1024 + ATT_TILE_BYTES * (2 + AW_RING) + 256;
+
+struct WinItem {
+  int q0, kv_lo, n_kt, head, valid;
+};
+__device__ __forceinline__ WinItem win_item(const AttnParams& p, int n_items, int it) {
+  WinItem w;
+  w.valid = it < n_items;
+  int qt = it / p.heads;
+  w.head = it - qt * p.heads;
+  w.q0 = qt * ATT_BM;
+  int r_last = min(w.q0 + ATT_BM - 1, p.Mq - 1);
+  w.kv_lo = (w.q0 / p.Wq) * p.Wkv;
+  int kv_hi = (r_last / p.Wq + 1) * p.Wkv;
+  w.n_kt = w.valid ? (kv_hi - w.kv_lo + ATT_BN - 1) / ATT_BN : 0;
+  return w;
+}
+
+__global__ void __launch_bounds__(AW_THREADS, 1)
+k_attn_win(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+           const __grid_constant__ CUtensorMap tv, AttnParams p, int n_items) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;                       // [2]
+  uint8_t* sR = sQ + 2 * ATT_TILE_BYTES;    // K/V ring [AW_RING]
+  uint64_t* bars = (uint64_t*)(sR + AW_RING * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;                  // [2]
+  uint64_t* q_empty = bars + 2;             // [2]
+  uint64_t* r_full = bars + 4;              // [AW_RING]
+  uint64_t* r_empty = bars + 4 + AW_RING;   // [AW_RING]
+  uint64_t* s_full = bars + 4 + 2 * AW_RING;  // [2]
+  uint64_t* p_full = s_full + 2;            // [2]
+  uint64_t* o_full = s_full + 4;            // [2]
+  uint64_t* o_free = s_full + 6;            // [2]
+  uint32_t* tmem_slot = (uint32_t*)(s_full + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_pairs = (n_items + 1) / 2;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tq);
+    tc::prefetch_tmap(&tk);
+    tc::prefetch_tmap(&tv);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; i++) {
+      tc::mbar_init(&q_full[i], 1);
+      tc::mbar_init(&q_empty[i], 1);
+      tc::mbar_init(&s_full[i], 1);
+      tc::mbar_init(&p_full[i], 4);
+      tc::mbar_init(&o_full[i], 1);
+      tc::mbar_init(&o_free[i], 4);
+    }
+    for (int i = 0; i < AW_RING; i++) {
+      tc::mbar_init(&r_full[i], 1);
+      tc::mbar_init(&r_empty[i], 1);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc<512>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: Q per slot, K/V through the ring in MMA consumption order
+    if (lane == 0) {
+      uint32_t ring = 0, ring_uses = 0;
+      uint32_t q_uses[2] = {0, 0};
+      auto load_kv = [&](const CUtensorMap* tm, int col, int row) {
+        tc::mbar_wait(&r_empty[ring], ((ring_uses / AW_RING) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(&r_full[ring], ATT_TILE_BYTES);
+        uint8_t* dst = sR + ring * ATT_TILE_BYTES;
+        tc::tma_load_2d(dst, tm, &r_full[ring], col, row);
+        tc::tma_load_2d(dst + ATT_BN * 128, tm, &r_full[ring], col + 64, row);
+        ring = (ring + 1) % AW_RING;
+        ring_uses++;
+      };
+      for (int pp = blockIdx.x; pp < n_pairs; pp += gridDim.x) {
+        WinItem it[2] = {win_item(p, n_items, 2 * pp), win_item(p, n_items, 2 * pp + 1)};
+        for (int g = 0; g < 2; g++)
+          if (it[g].valid) {
+            tc::mbar_wait(&q_empty[g], (q_uses[g] & 1) ^ 1);
+            tc::mbar_arrive_expect_tx(&q_full[g], ATT_TILE_BYTES);
+            uint8_t* dst = sQ + g * ATT_TILE_BYTES;
+            tc::tma_load_2d(dst, &tq, &q_full[g], p.qcol0 + it[g].head * ATT_D, it[g].q0);
+            tc::tma_load_2d(dst + ATT_BM * 128, &tq, &q_full[g], p.qcol0 + it[g].head * ATT_D + 64, it[g].q0);
+            q_uses[g]++;
+          }
+        for (int g = 0; g < 2; g++)
+          if (it[g].n_kt > 0) load_kv(&tk, p.kcol0 + it[g].head * ATT_D, it[g].kv_lo);
+        const int nmax = max(it[0].n_kt, it[1].n_kt);
+        for (int j = 0; j < nmax; j++)
+          for (int g = 0; g < 2; g++)
+            if (j < it[g].n_kt) {
+              load_kv(&tv, p.vcol0 + it[g].head * ATT_D, it[g].kv_lo + j * ATT_BN);
+              if (j + 1 < it[g].n_kt) load_kv(&tk, p.kcol0 + it[g].head * ATT_D, it[g].kv_lo + (j + 1) * ATT_BN);
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_qk = tc::idesc_bf16(ATT_BM, ATT_BN, false, false, p.fp16 != 0);
+      const uint32_t idesc_pv = tc::idesc_bf16(ATT_BM, ATT_D, false, true, p.fp16 != 0);
+      uint32_t ring = 0, ring_uses = 0;
+      uint32_t q_uses[2] = {0, 0}, p_uses[2] = {0, 0}, item_uses[2] = {0, 0};
+      auto ring_wait = [&]() -> uint32_t {
+        tc::mbar_wait(&r_full[ring], (ring_uses / AW_RING) & 1);
+        tc::tc_fence_after();
+        return tc::smem_u32(sR + ring * ATT_TILE_BYTES);
+      };
+      auto ring_release = [&]() {
+        tc::mma_commit(&r_empty[ring]);
+        ring = (ring + 1) % AW_RING;
+        ring_uses++;
+      };
+      auto issue_qk = [&](int g, bool last) {
+        const uint32_t k_addr = ring_wait();
+        const uint32_t q_addr = tc::smem_u32(sQ + g * ATT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; k++) {
+          uint32_t off = (k >> 2) * (ATT_BM * 128) + (k & 3) * 32;
+          tc::mma_f16_ss(tmem_base + g * 128, tc::desc_kmajor(q_addr + off), tc::desc_kmajor(k_addr + off), idesc_qk,
+                         k > 0 ? 1u : 0u);
+        }
+        tc::mma_commit(&s_full[g]);
+        ring_release();
+        if (last) tc::mma_commit(&q_empty[g]);
+      };
+      for (int pp = blockIdx.x; pp < n_pairs; pp += gridDim.x) {
+        WinItem it[2] = {win_item(p, n_items, 2 * pp), win_item(p, n_items, 2 * pp + 1)};
+        for (int g = 0; g < 2; g++)
+          if (it[g].n_kt > 0) {
+            tc::mbar_wait(&q_full[g], q_uses[g] & 1);
+            q_uses[g]++;
+            issue_qk(g, it[g].n_kt == 1);
+          }
+        const int nmax = max(it[0].n_kt, it[1].n_kt);
+        for (int j = 0; j < nmax; j++)
+          for (int g = 0; g < 2; g++)
+            if (j < it[g].n_kt) {
+              tc::mbar_wait(&p_full[g], p_uses[g] & 1);
+              p_uses[g]++;
+              if (j == 0) {
+                // the previous item of this slot has been read out of O
+                tc::mbar_wait(&o_free[g], (item_uses[g] & 1) ^ 1);
+                item_uses[g]++;
+              }
+              tc::tc_fence_after();
+              const uint32_t v_addr = ring_wait();
+#pragma unroll
+              for (int k = 0; k < ATT_BN / 16; k++) {
+                uint64_t b = tc::smem_desc_sw128(v_addr + k * 2048, ATT_BN * 128, 1024);
+                tc::mma_f16_ts(tmem_base + 256 + g * ATT_D, tmem_base + g * 128 + k * 8, b, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+              }
+              tc::mma_commit(&o_full[g]);
+              ring_release();
+              if (j + 1 < it[g].n_kt) issue_qk(g, j + 2 == it[g].n_kt);
+            }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax + output: warps 4-7 slot 0, warps 8-11 slot 1
+    const int g = (warp - 4) >> 2;
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
+    const uint32_t tS = tmem_base + lane_sel + g * 128;
+    const uint32_t tO = tmem_base + lane_sel + 256 + g * ATT_D;
+    uint32_t s_uses = 0, pv_done = 0;  // cumulative tiles of this slot
+    for (int pp = blockIdx.x; pp < n_pairs; pp += gridDim.x) {
+      const WinItem it = win_item(p, n_items, 2 * pp + g);
+      if (it.n_kt == 0) continue;
+      const int grow = it.q0 + r;
+      const bool row_ok = grow < p.Mq;
+      const int wq = (row_ok ? grow : it.q0) / p.Wq;
+      const int vis0 = wq * p.Wkv - it.kv_lo;  // first visible key relative to the item's first key tile
+      float m_ref = -INFINITY, l = 0.f;
+      for (int j = 0; j < it.n_kt; j++) {
+        const int c_lo = max(vis0 - j * ATT_BN, 0), c_hi = row_ok ? min(vis0 + p.Wkv - j * ATT_BN, ATT_BN) : 0;
+        tc::mbar_wait(&s_full[g], s_uses & 1);
+        s_uses++;
+        tc::tc_fence_after();
+        float tmx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < ATT_BN / 32; c++) {
+          uint32_t v[32];
+          tc::tmem_ld_32x32(tS + c * 32, v);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            int col = c * 32 + i;
+            if (col >= c_lo && col < c_hi) tmx = fmaxf(tmx, __uint_as_float(v[i]));
+          }
+        }
+        const float tm = tmx * p.scale_log2;  // -inf when the row sees nothing in this tile
+        const bool first = (m_ref == -INFINITY) && (tmx != -INFINITY);
+        const bool need = (m_ref != -INFINITY) && (tm > m_ref + 8.0f);
+        if (first) m_ref = tm;
+        if (__any_sync(0xffffffffu, need)) {
+          // O holds the tiles accumulated so far: wait for the last P V of this item, then rescale
+          tc::mbar_wait(&o_full[g], (pv_done - 1) & 1);
+          tc::tc_fence_after();
+          const float alpha = need ? ex2(m_ref - tm) : 1.0f;
+#pragma unroll
+          for (int c = 0; c < ATT_D / 32; c++) {
+            uint32_t v[32];
+            tc::tmem_ld_32x32(tO + c * 32, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tc::tmem_st_32x32(tO + c * 32, v);
+          }
+          tc::tmem_st_wait();
+          l *= alpha;
+          if (need) m_ref = tm;
+        }
+        float rowsum = 0.f;
+        const float mr = (m_ref == -INFINITY) ? 0.f : m_ref;
+#pragma unroll
+        for (int c = 0; c < ATT_BN / 32; c++) {
+          uint32_t v[32];
+          tc::tmem_ld_32x32(tS + c * 32, v);
+          tc::tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const int col = c * 32 + i;
+            float p0 = ex2(fmaf(__uint_as_float(v[i]), p.scale_log2, -mr));
+            float p1 = ex2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -mr));
+            if (col < c_lo || col >= c_hi) p0 = 0.f;
+            if (col + 1 < c_lo || col + 1 >= c_hi) p1 = 0.f;
+            rowsum += p0 + p1;
+            pk[i >> 1] = tc::pack16(p.fp16, p0, p1);
+          }
+          tc::tmem_st_32x16(tS + c * 16, pk);
+        }
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&p_full[g]);
+        l += rowsum;
+        pv_done++;
+      }
+      tc::mbar_wait(&o_full[g], (pv_done - 1) & 1);
+      tc::tc_fence_after();
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      __nv_bfloat16* o = p.out + (long long)grow * p.ld_out + it.head * ATT_D;
+#pragma unroll
+      for (int c = 0; c < ATT_D / 32; c++) {
+        uint32_t v[32];
+        tc::tmem_ld_32x32(tO + c * 32, v);
+        tc::tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              w[k] = tc::pack16(p.fp16, __uint_as_float(v[i + 2 * k]) * inv, __uint_as_float(v[i + 2 * k + 1]) * inv);
+            *(uint4*)(o + c * 32 + i) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&o_free[g]);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+int device_sm_count();
+
 // q/k/v: bf16 matrices [Mq|Mkv, ld*] whose columns [col0 + h*96, col0 + (h+1)*96) hold head h.
 int attn_tc_launch(const __nv_bfloat16* q, long long ldq, int qcols, int qcol0, const __nv_bfloat16* k, long long ldk,
                    int kcols, int kcol0, const __nv_bfloat16* v, long long ldv, int vcols, int vcol0, int Mq, int Mkv,
@@ -544,7 +837,18 @@ int attn_tc_launch(const __nv_bfloat16* q, long long ldq, int qcols, int qcol0, 
     CVB_LAUNCH(k_attn_global, dim3(Mq / (2 * ATT_BM), heads), dim3(AG_THREADS), AG_SMEM, st, tq, tk, tv, p);
     return CV_OK;
   }
-  CVB_LAUNCH(k_attn_tc, dim3((Mq + ATT_BM - 1) / ATT_BM, heads), dim3(ATT_THREADS), ATT_SMEM, st, tq, tk, tv, p);
+  {
+    static bool attr_set_w = false;
+    if (!attr_set_w) {
+      cudaError_t e = cudaFuncSetAttribute(k_attn_win, cudaFuncAttributeMaxDynamicSharedMemorySize, AW_SMEM);
+      if (e != cudaSuccess) return cvb_fail_cuda(e, "cudaFuncSetAttribute(k_attn_win)");
+      attr_set_w = true;
+    }
+    const int n_items = ((Mq + ATT_BM - 1) / ATT_BM) * heads;
+    const int n_pairs = (n_items + 1) / 2;
+    const int grid = n_pairs < device_sm_count() ? n_pairs : device_sm_count();
+    CVB_LAUNCH(k_attn_win, dim3(grid), dim3(AW_THREADS), AW_SMEM, st, tq, tk, tv, p, n_items);
+  }
   return CV_OK;
 }
 
