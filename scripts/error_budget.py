@@ -75,9 +75,38 @@ def neck_dec_act(m):
         if isinstance(mod, (nn.Conv2d, nn.ConvTranspose2d)):
             hs.append(mod.register_forward_pre_hook(lambda mod, inp: (bf(inp[0]),)))
     return hs
+def dec_tok16(m):
+    """token side of the decoder (two-way transformer linears, hyper / iou MLPs) with fp16 weights and inputs"""
+    hs = []
+    for mod in m.sam2_model.sam_mask_decoder.modules():
+        if isinstance(mod, nn.Linear):
+            mod.weight.data = f16(mod.weight.data)
+            hs.append(mod.register_forward_pre_hook(lambda mod, inp: (f16(inp[0]),)))
+    return hs
+def dec_tok_bf(m):
+    hs = []
+    for mod in m.sam2_model.sam_mask_decoder.modules():
+        if isinstance(mod, nn.Linear):
+            mod.weight.data = bf(mod.weight.data)
+            hs.append(mod.register_forward_pre_hook(lambda mod, inp: (bf(inp[0]),)))
+    return hs
+def _dec_sel(pred, cast):
+    def f(m):
+        hs = []
+        for name, mod in m.sam2_model.sam_mask_decoder.named_modules():
+            if isinstance(mod, nn.Linear) and pred(name):
+                mod.weight.data = cast(mod.weight.data)
+                hs.append(mod.register_forward_pre_hook(lambda mod, inp: (cast(inp[0]),)))
+        return hs
+    return f
+_img_side = lambda n: any(k in n for k in ("token_to_image.k_proj", "token_to_image.v_proj", "image_to_token.q_proj", "image_to_token.out_proj"))
 which = sys.argv[1:] or ["pe_bf16", "pe_fp16", "trunk_w", "trunk_act", "trunk_qkv_out", "neck_dec_w", "all"]
 table = dict(pe_bf16=pe_bf16, pe_fp16=pe_fp16, trunk_w=trunk_w, trunk_act=trunk_act, trunk_qkv_out=trunk_qkv_out, neck_dec_w=neck_dec_w,
              trunk_bf16=all_of(trunk_w, trunk_act, trunk_qkv_out), trunk_fp16=all_of(trunk_w16, trunk_act16), neck_dec_act=neck_dec_act,
              trunk_bf16_dec_act=all_of(trunk_w, trunk_act, trunk_qkv_out, neck_dec_act),
+             dec_img16=_dec_sel(_img_side, f16), dec_img_bf=_dec_sel(_img_side, bf),
+             dec_hyper16=_dec_sel(lambda n: "hypernetworks" in n or "iou_prediction" in n, f16),
+             dec_tokside16=_dec_sel(lambda n: "transformer" in n and not _img_side(n), f16),
+             dec_tok16=dec_tok16, dec_tok_bf=dec_tok_bf,
              all=all_of(pe_bf16, trunk_w, trunk_act, trunk_qkv_out, neck_dec_w), all_fp16pe=all_of(pe_fp16, trunk_w, trunk_act, trunk_qkv_out, neck_dec_w))
 for k in which: run(k, table[k])

@@ -172,3 +172,40 @@ def test_segment_never_raises():
     from circuitvision_b200.circuit_analyzer import CircuitAnalyzer
     A = CircuitAnalyzer(sam2_model=object(), sam2_transforms=object(), use_sam2=True, debug=True, device=0)
     assert A.segment_with_sam2(np.zeros((10, 10), np.uint8)) == (None, None, None)  # :381-386
+
+
+def test_crop_pipeline_matches_per_image_calls(pair):
+    """The batched, stream-pipelined host API returns what the two per-image drop-in calls return."""
+    from oracle import node_oracle
+    from circuitvision_b200 import sam2_infer
+    from circuitvision_b200.circuit_analyzer import CircuitAnalyzer
+    from circuitvision_b200.pipeline import CropPipeline
+    _, model = pair
+    A = CircuitAnalyzer(sam2_model=model, sam2_transforms=sam2_infer.SAM2Transforms(1024, 0.0), debug=True, device=0)
+    data = [synth.make_schematic(40 + i, 1024, render_rgb=True) for i in range(4)]
+    pipe = CropPipeline(model, batch=2, depth=2)
+    batches = []
+    for k in range(2):
+        crops = torch.from_numpy(np.stack([data[2 * k + i][2] for i in range(2)])).pin_memory()
+        batches.append(crops)
+        pipe.submit(crops, [data[2 * k + i][1] for i in range(2)])
+    for k in range(2):
+        res = pipe.collect()
+        for i in range(2):
+            _, boxes, rgb = data[2 * k + i]
+            mask1, _, _ = A.segment_with_sam2(rgb)
+            mask = res.masks[i]
+            # batched == single up to attention-tile rounding (see test_batched_equals_stack_of_singles)
+            assert _iou(torch.from_numpy(mask > 0), torch.from_numpy(mask1 > 0)) >= 0.998
+            e = res.extents[i]
+            ys, xs = np.nonzero(mask)
+            assert (int(xs.min()), int(ys.min()), int(xs.max()), int(ys.max())) == tuple(int(v) for v in e)
+            # node analysis of the pipeline's own mask: identical to the per-image drop-in call on that mask
+            nodes, emptied, enhanced, *_ = A.get_node_connections(rgb, mask, boxes)
+            assert np.array_equal(res.emptied[i], emptied) and np.array_equal(res.enhanced[i], enhanced)
+            a, b = node_oracle.node_signature(res.nodes(i)), node_oracle.node_signature(nodes)
+            assert len(a) == len(b)
+            for x, y in zip(a, b):
+                assert x[0] == y[0] and x[1] == y[1] and np.array_equal(x[2], y[2])
+    with pytest.raises(Exception):
+        pipe.collect()
