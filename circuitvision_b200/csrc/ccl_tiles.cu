@@ -1,0 +1,399 @@
+// Native-resolution connected-component labelling (cv_ccl_label, BASELINE cfg 4) — tiled, bit-parallel union-find.
+//
+// Not a reference code path: the oracle is cv2.connectedComponents up to renaming; labels are
+// canonical: labels[p] = 1 + min linear index of p's component, 0 for background.
+//
+// Traffic plan (the kernel is HBM-bound; algorithmic bytes = 1 B/px mask read + 4 B/px label write):
+//   pass A  k_ccl_tile_label : each CTA loads a 128 x 32 tile of the mask as BITS (one 32-pixel word per thread), labels it
+//                              entirely in shared memory (sub-runs = maximal runs inside a word; unions between words of
+//                              a row and between adjacent rows by bit overlap; atomicMin union-find on a 16 KB parent
+//                              array) and writes the label image once, fully coalesced: 1 + 4 B/px.
+//   pass B  k_ccl_tile_seams : only pixels on tile seams (3.9 % of the image) merge components across tiles with the
+//                              global atomicMin union-find on the label image (roots point at roots).
+//   pass B2 k_ccl_tile_compress: path halving from the same seam pixels so the trees pass C walks are one or two hops deep.
+//   pass C  k_ccl_tile_fixup : one thread per 32-pixel word re-reads the mask bits (1 B/px, no full label read), takes
+//                              the tile-local root named at each sub-run's first pixel, looks up its global root and
+//                              rewrites only the runs whose component changed (sparse row segments); counts roots.
+// Total ≈ 6 B/px + seams instead of the 16+ B/px of a per-pixel init / merge / flatten pipeline.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/cv_b200.h"
+#include "common.cuh"
+
+namespace cvb {
+
+constexpr int CT_W = 128, CT_H = 32, CT_WORDS = CT_W / 32, CT_THREADS = CT_H * CT_WORDS;
+
+// ---- global union-find on the label image (parent of x = L[x] - 1; 0 = background)
+__device__ __forceinline__ int gfind(const int* L, int x) {
+  int y = __ldcg(L + x) - 1;
+  while (y != x) {
+    x = y;
+    y = __ldcg(L + x) - 1;
+  }
+  return x;
+}
+__device__ __forceinline__ void gunion(int* L, int a, int b) {
+  bool done;
+  do {
+    a = gfind(L, a);
+    b = gfind(L, b);
+    if (a < b) {
+      int old = atomicMin(L + b, a + 1) - 1;
+      done = (old == b);
+      b = old;
+    } else if (b < a) {
+      int old = atomicMin(L + a, b + 1) - 1;
+      done = (old == a);
+      a = old;
+    } else {
+      done = true;
+    }
+  } while (!done);
+}
+
+// ---- shared-memory union-find on sub-run start positions (tile-local pixel index)
+__device__ __forceinline__ int sfind(const volatile int* P, int x) {
+  int y = P[x];
+  while (y != x) {
+    x = y;
+    y = P[x];
+  }
+  return x;
+}
+__device__ __forceinline__ void sunion(int* P, int a, int b) {
+  bool done;
+  do {
+    a = sfind(P, a);
+    b = sfind(P, b);
+    if (a < b) {
+      int old = atomicMin(P + b, a);
+      done = (old == b);
+      b = old;
+    } else if (b < a) {
+      int old = atomicMin(P + a, b);
+      done = (old == a);
+      a = old;
+    } else {
+      done = true;
+    }
+  } while (!done);
+}
+
+// start of the sub-run of `word` that contains set bit x
+__device__ __forceinline__ int run_start(uint32_t word, int x) {
+  uint32_t below = ~word & ((x ? (1u << x) : 1u) - 1u);
+  return below ? 32 - __clz(below) : 0;
+}
+// number of consecutive set bits of `word` starting at bit s (bit s is set)
+__device__ __forceinline__ int run_len(uint32_t word, int s) {
+  uint32_t inv = ~(word >> s);
+  int l = __ffs(inv) - 1;  // inv == 0 -> -1
+  return (l < 0 || l > 32 - s) ? 32 - s : l;
+}
+__device__ __forceinline__ uint32_t run_mask(int s, int len) {
+  return (len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u)) << s;
+}
+
+// 32 mask bytes of row y starting at x -> bit i set iff pixel x+i is non-zero (out-of-image pixels are 0)
+__device__ __forceinline__ uint32_t load_word(const uint8_t* __restrict__ im, int H, int W, int y, int x, bool vec_ok) {
+  if (y >= H || x >= W) return 0u;
+  const uint8_t* p = im + (size_t)y * W + x;
+  uint32_t w = 0;
+  if (vec_ok && x + 32 <= W) {
+    const uint4 a = __ldg((const uint4*)p), b = __ldg((const uint4*)p + 1);
+    const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      // MSB of each byte := (byte != 0); the multiply gathers the four MSBs (bits 7,15,23,31) into bits 28..31
+      uint32_t m = (((v[k] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v[k]) & 0x80808080u;
+      w |= ((m * 0x00204081u) >> 28) << (4 * k);
+    }
+  } else {
+    const int n = min(32, W - x);
+    for (int i = 0; i < n; i++) w |= (uint32_t)(p[i] != 0) << i;
+  }
+  return w;
+}
+
+// Element of the union-find = a maximal horizontal run of the tile row (it may span several 32-pixel words), identified
+// by the tile-local index of its first pixel.  fid[r][c] = element of the run that ENTERS word c of row r from the left
+// (valid when the word's bit 0 is set and the previous word's bit 31 is set).
+__device__ __forceinline__ bool carries_in(const uint32_t (*bits)[CT_WORDS], int r, int c) {
+  return c > 0 && (bits[r][c] & 1u) && (bits[r][c - 1] >> 31);
+}
+__device__ __forceinline__ int elem_of(const uint32_t (*bits)[CT_WORDS], const int (*fid)[CT_WORDS], int r, int c, int st) {
+  return (st == 0 && carries_in(bits, r, c)) ? fid[r][c] : r * CT_W + c * 32 + st;
+}
+
+// Labels one tile in shared memory.  On return (after the trailing __syncthreads) P[e] holds the ROOT (tile-local pixel
+// index of the component's first pixel in raster order) for every run element e of the tile.
+template <int CONN>
+__device__ __forceinline__ uint32_t tile_label(const uint8_t* __restrict__ im, int H, int W, int x0, int y0, bool vec_ok,
+                                               uint32_t (*bits)[CT_WORDS], int (*fid)[CT_WORDS], int* P) {
+  const int r = threadIdx.x / CT_WORDS, c = threadIdx.x % CT_WORDS;
+  const uint32_t w = load_word(im, H, W, y0 + r, x0 + c * 32, vec_ok);
+  const int base = r * CT_W + c * 32;
+  // resolve runs across the words of the row with shuffles (the 4 words of a row sit in 4 adjacent lanes)
+  const uint32_t lw = __shfl_up_sync(0xffffffffu, w, 1);
+  const bool cin = c > 0 && (w & 1u) && (lw >> 31);
+  int first = base;  // element of my first sub-run
+#pragma unroll
+  for (int k = 0; k < CT_WORDS - 1; k++) {
+    const int lf = __shfl_up_sync(0xffffffffu, first, 1);
+    if (cin) {
+      const int ls = run_start(lw, 31);
+      first = ls > 0 ? base - 32 + ls : lf;
+    }
+  }
+  bits[r][c] = w;
+  fid[r][c] = first;
+  uint32_t starts = w & ~(w << 1);
+  if (cin) starts &= ~1u;  // a continued run is not an element of its own
+  for (uint32_t s = starts; s; s &= s - 1) {
+    int i = __ffs(s) - 1;
+    P[base + i] = base + i;
+  }
+  __syncthreads();
+  if (w && r > 0) {
+    const uint32_t up = bits[r - 1][c];
+    const uint32_t upl = (c > 0) ? bits[r - 1][c - 1] : 0u, upr = (c + 1 < CT_WORDS) ? bits[r - 1][c + 1] : 0u;
+    const bool up_cin = (c > 0) && (up & 1u) && (upl >> 31);
+    uint32_t cur = w;
+    while (cur) {
+      const int s = __ffs(cur) - 1;
+      const int len = run_len(cur, s);
+      const uint32_t rm = run_mask(s, len);
+      cur &= ~rm;
+      const int me = (s == 0 && cin) ? first : base + s;
+      uint32_t aw = rm;
+      if (CONN == 8) aw |= (rm << 1) | (rm >> 1);
+      uint32_t cand = aw & up;
+      while (cand) {
+        const int us = __ffs(cand) - 1;
+        const int st = run_start(up, us);
+        cand &= ~run_mask(st, run_len(up, st));
+        // both runs continue from the previous word and already touch there: that thread made the union
+        if (s == 0 && cin && st == 0 && up_cin) continue;
+        sunion(P, me, elem_of(bits, fid, r - 1, c, st));
+      }
+      if (CONN == 8) {
+        if (s == 0 && !cin && (upl >> 31)) sunion(P, me, elem_of(bits, fid, r - 1, c - 1, run_start(upl, 31)));
+        if (s + len == 32 && !(up >> 31) && (upr & 1u)) sunion(P, me, elem_of(bits, fid, r - 1, c + 1, 0));
+      }
+    }
+  }
+  __syncthreads();
+  for (uint32_t s = starts; s; s &= s - 1) {
+    int i = __ffs(s) - 1;
+    P[base + i] = sfind(P, base + i);  // roots point at themselves, so concurrent finds stay valid
+  }
+  __syncthreads();
+  return w;
+}
+
+template <int CONN>
+__global__ void __launch_bounds__(CT_THREADS) k_ccl_tile_label(const uint8_t* __restrict__ masks, int* __restrict__ labels,
+                                                                int H, int W, int vec_ok) {
+  __shared__ uint32_t bits[CT_H][CT_WORDS];
+  __shared__ int fid[CT_H][CT_WORDS];
+  __shared__ int P[CT_H * CT_W];
+  const int b = blockIdx.z, x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
+  const uint8_t* im = masks + (size_t)b * H * W;
+  int* L = labels + (size_t)b * H * W;
+  tile_label<CONN>(im, H, W, x0, y0, vec_ok != 0, bits, fid, P);
+  // coalesced label write: each warp takes rows warp, warp+4, ...; lane l owns pixels 4l..4l+3 of the row
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = lane >> 3, sh = (lane & 7) * 4;
+  for (int r = warp; r < CT_H; r += CT_THREADS / 32) {
+    const int y = y0 + r;
+    if (y >= H) break;
+    const uint32_t word = bits[r][c];
+    int out[4] = {0, 0, 0, 0};
+    if ((word >> sh) & 0xFu) {
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if ((word >> (sh + k)) & 1u) {
+          const int root = P[elem_of(bits, fid, r, c, run_start(word, sh + k))];
+          out[k] = (y0 + root / CT_W) * W + x0 + (root % CT_W) + 1;
+        }
+    }
+    const int x = x0 + lane * 4;
+    int* dst = L + (size_t)y * W + x;
+    if (vec_ok && x + 4 <= W) {
+      *(int4*)dst = make_int4(out[0], out[1], out[2], out[3]);
+    } else {
+      for (int k = 0; k < 4; k++)
+        if (x + k < W) dst[k] = out[k];
+    }
+  }
+}
+
+// seams: blockIdx.y selects (0) horizontal seams y = k*CT_H or (1) vertical seams x = k*CT_W
+template <int CONN>
+__global__ void __launch_bounds__(256) k_ccl_tile_seams(const uint8_t* __restrict__ masks, int* __restrict__ labels, int H,
+                                                        int W) {
+  const int b = blockIdx.z;
+  const uint8_t* im = masks + (size_t)b * H * W;
+  int* L = labels + (size_t)b * H * W;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.y == 0) {
+    const int n_seams = (H - 1) / CT_H;  // rows CT_H, 2*CT_H, ... < H
+    if (t >= (long long)n_seams * W) return;
+    const int y = (int)(t / W + 1) * CT_H, x = (int)(t % W);
+    const int p = y * W + x;
+    if (!im[p]) return;
+    const bool left = x > 0 && im[p - 1], up = im[p - W] != 0;
+    const bool ul = x > 0 && im[p - W - 1], ur = x + 1 < W && im[p - W + 1];
+    if (up) {
+      if (!(left && ul)) gunion(L, p, p - W);
+    } else if (CONN == 8) {
+      if (ul && !left) gunion(L, p, p - W - 1);
+      if (ur) gunion(L, p, p - W + 1);
+    }
+  } else {
+    const int n_seams = (W - 1) / CT_W;
+    if (t >= (long long)n_seams * H) return;
+    const int x = (int)(t / H + 1) * CT_W, y = (int)(t % H);
+    const int p = y * W + x;
+    if (!im[p]) return;
+    if (im[p - 1]) {
+      gunion(L, p, p - 1);
+    } else if (CONN == 8) {
+      if (y > 0 && im[p - W - 1]) gunion(L, p, p - W - 1);
+      if (y + 1 < H && im[p + W - 1]) gunion(L, p, p + W - 1);
+    }
+  }
+}
+
+// pass B2: the seam unions link tile roots to tile roots without compression, so a component that crosses many tiles
+// (a wire network) ends up as a deep tree.  Every seam pixel re-walks its root's path with path halving (each step
+// re-points a node at its grandparent with atomicMin), after which pass C finds global roots in one or two hops.
+__global__ void __launch_bounds__(256) k_ccl_tile_compress(const uint8_t* __restrict__ masks, int* __restrict__ labels, int H,
+                                                           int W) {
+  const int b = blockIdx.z;
+  const uint8_t* im = masks + (size_t)b * H * W;
+  int* L = labels + (size_t)b * H * W;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int p;
+  if (blockIdx.y == 0) {
+    const int n_seams = (H - 1) / CT_H;
+    if (t >= (long long)n_seams * W) return;
+    p = (int)(t / W + 1) * CT_H * W + (int)(t % W);
+  } else {
+    const int n_seams = (W - 1) / CT_W;
+    if (t >= (long long)n_seams * H) return;
+    p = (int)(t % H) * W + (int)(t / H + 1) * CT_W;
+  }
+  if (!im[p]) return;
+  int x = __ldcg(L + p) - 1;
+  while (true) {
+    const int y = __ldcg(L + x) - 1;
+    if (y == x) break;
+    const int z = __ldcg(L + y) - 1;
+    if (z != y) atomicMin(L + x, z + 1);  // ancestors only ever get smaller indices
+    x = z;
+  }
+}
+
+// pass C: one thread per 32-pixel word.  The label pass A wrote at the LAST pixel of a sub-run names the run's
+// tile-local root (only root pixels — always the first pixel of a run — are modified by the seam unions); if that root
+// was merged into another component, the whole run is rewritten with the global root.
+__global__ void __launch_bounds__(256) k_ccl_tile_fixup(const uint8_t* __restrict__ masks, int* __restrict__ labels, int H, int W,
+                                                        int vec_ok, int* __restrict__ ncomp, int* __restrict__ partial) {
+  __shared__ int block_roots;
+  if (threadIdx.x == 0) block_roots = 0;
+  __syncthreads();
+  const int b = blockIdx.z;
+  const uint8_t* im = masks + (size_t)b * H * W;
+  int* L = labels + (size_t)b * H * W;
+  const int words_per_row = (W + 31) / 32;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;  // < 2^31 / 32 words
+  int n_roots = 0;
+  if (t < words_per_row * H) {
+    const int y = t / words_per_row, x = (t - y * words_per_row) * 32;
+    const uint32_t w = load_word(im, H, W, y, x, vec_ok != 0);
+    for (uint32_t s = w & ~(w << 1); s; s &= s - 1) {
+      const int i = __ffs(s) - 1;
+      const int len = run_len(w, i);
+      const int px = y * W + x + i;
+      const int ref = __ldcg(L + px + len - 1);  // tile-local root + 1 (a run's last pixel is never a root unless len == 1)
+      const int f = gfind(L, ref - 1);
+      if (ref != f + 1) {
+        for (int k = 0; k < len; k++) L[px + k] = f + 1;
+      }
+      n_roots += (f == px);  // this run starts at the first pixel of its component
+    }
+  }
+  if (ncomp) {
+    for (int o = 16; o; o >>= 1) n_roots += __shfl_xor_sync(0xffffffffu, n_roots, o);
+    if ((threadIdx.x & 31) == 0 && n_roots) atomicAdd(&block_roots, n_roots);
+    __syncthreads();
+    if (threadIdx.x == 0 && block_roots) {
+      // spread the per-image counter over 32 slots so that the adds do not serialise on one L2 line
+      if (partial) atomicAdd(partial + ((size_t)b * 32 + (blockIdx.x & 31)) * 32, block_roots);
+      else atomicAdd(ncomp + b, block_roots);
+    }
+  }
+}
+
+__global__ void k_ccl_count_finish(const int* __restrict__ partial, int* __restrict__ ncomp, int B) {
+  int b = blockIdx.x, l = threadIdx.x;
+  int v = partial[((size_t)b * 32 + l) * 32];
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (l == 0 && b < B) ncomp[b] = v;
+}
+
+}  // namespace cvb
+
+using namespace cvb;
+
+template <int CONN>
+static int ccl_run(const uint8_t* masks, int B, int H, int W, int32_t* labels, int32_t* n_components, int* partial,
+                   cudaStream_t st) {
+  const int vec_ok = (W % 16 == 0) && (((uintptr_t)masks & 15) == 0) && (((uintptr_t)labels & 15) == 0);
+  dim3 tg((W + CT_W - 1) / CT_W, (H + CT_H - 1) / CT_H, B);
+  const double px = (double)B * H * W;
+  cvb_next_work(5.0 * px);
+  CVB_LAUNCH((k_ccl_tile_label<CONN>), tg, dim3(CT_THREADS), 0, st, masks, labels, H, W, vec_ok);
+  const long long seam_px = max((long long)((H - 1) / CT_H) * W, (long long)((W - 1) / CT_W) * H);
+  if (seam_px > 0) {
+    cvb_next_work(0.0);
+    CVB_LAUNCH((k_ccl_tile_seams<CONN>), dim3((unsigned)((seam_px + 255) / 256), 2, B), dim3(256), 0, st, masks, labels, H, W);
+    CVB_LAUNCH(k_ccl_tile_compress, dim3((unsigned)((seam_px + 255) / 256), 2, B), dim3(256), 0, st, masks, labels, H, W);
+  }
+  cvb_next_work(1.0 * px);
+  const long long n_words = (long long)((W + 31) / 32) * H;
+  CVB_LAUNCH(k_ccl_tile_fixup, dim3((unsigned)((n_words + 255) / 256), 1, B), dim3(256), 0, st, masks, labels, H, W, vec_ok,
+             n_components, partial);
+  if (n_components && partial) CVB_LAUNCH(k_ccl_count_finish, dim3(B), dim3(32), 0, st, partial, n_components, B);
+  return CV_OK;
+}
+
+extern "C" size_t cv_ccl_workspace_bytes(int B, int H, int W) {
+  (void)H; (void)W;
+  // labels are resolved in place in the caller's label image; the workspace only spreads the component counters
+  return (size_t)(B > 0 ? B : 1) * 32 * 32 * sizeof(int);
+}
+
+extern "C" int cv_ccl_label(const uint8_t* masks, int B, int H, int W, int connectivity, int32_t* labels,
+                            int32_t* n_components, void* workspace, size_t workspace_bytes, void* stream_) {
+  cvb_reset_launches();
+  if (!masks || !labels || B <= 0 || H <= 0 || W <= 0)
+    return cvb_fail(CV_ERR_INVALID, "cv_ccl_label: null pointer or non-positive size");
+  if (connectivity != 4 && connectivity != 8) return cvb_fail(CV_ERR_INVALID, "cv_ccl_label: connectivity must be 4 or 8");
+  if ((long long)H * W >= (1ll << 31) - 2) return cvb_fail(CV_ERR_INVALID, "cv_ccl_label: image too large for int32 labels");
+  if (B > 65535) return cvb_fail(CV_ERR_INVALID, "cv_ccl_label: batch too large");
+  cudaStream_t st = (cudaStream_t)stream_;
+  int* partial = nullptr;
+  if (n_components) {
+    CVB_CHECK(cudaMemsetAsync(n_components, 0, (size_t)B * 4, st));
+    if (workspace && workspace_bytes >= cv_ccl_workspace_bytes(B, H, W)) {
+      partial = (int*)workspace;
+      CVB_CHECK(cudaMemsetAsync(partial, 0, cv_ccl_workspace_bytes(B, H, W), st));
+    }
+  }
+  return connectivity == 8 ? ccl_run<8>(masks, B, H, W, labels, n_components, partial, st)
+                           : ccl_run<4>(masks, B, H, W, labels, n_components, partial, st);
+}

@@ -49,6 +49,48 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
+// The same GELU on a PAIR of values with Blackwell's packed fp32x2 arithmetic (FFMA2 / FMUL2): the polynomial, the
+// exponent argument and the final blend each issue once for two elements, which is what the epilogue-bound fc1 GEMMs
+// need (the epilogue, not the tensor pipe, limits them: ~100 M GELUs per image).
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void up2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
+  const uint64_t z = pk2(fabsf(x0) * 0.70710678118654752440f, fabsf(x1) * 0.70710678118654752440f);
+  float d0, d1, t0, t1;
+  up2(fma2(z, pk2(0.3275911f, 0.3275911f), pk2(1.0f, 1.0f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const uint64_t t = pk2(t0, t1);
+  // negated A&S coefficients: p = -(a1 t + ... + a5 t^5)
+  uint64_t p = fma2(t, pk2(-1.061405429f, -1.061405429f), pk2(1.453152027f, 1.453152027f));
+  p = fma2(p, t, pk2(-1.421413741f, -1.421413741f));
+  p = fma2(p, t, pk2(0.284496736f, 0.284496736f));
+  p = fma2(p, t, pk2(-0.254829592f, -0.254829592f));
+  p = mul2(p, t);
+  float e0, e1, ex0, ex1;
+  up2(mul2(mul2(z, z), pk2(-1.4426950408889634f, -1.4426950408889634f)), e0, e1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex0) : "f"(e0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex1) : "f"(e1));
+  float r0, r1;
+  up2(fma2(p, pk2(ex0, ex1), pk2(1.0f, 1.0f)), r0, r1);  // |erf| = 1 - poly * exp(-z^2)
+  const uint64_t hx = mul2(pk2(x0, x1), pk2(0.5f, 0.5f));
+  up2(fma2(hx, pk2(copysignf(r0, x0), copysignf(r1, x1)), hx), x0, x1);
+}
+
 __device__ __forceinline__ long long gemm_dest_row(const GemmEpilogue& e, int map, long long r) {
   if (map == GEMM_MAP_UNWINDOW) {
     int w2 = e.ws * e.ws;
@@ -73,6 +115,14 @@ __device__ __forceinline__ float apply_act(int act, float x) {
   if (act == GEMM_ACT_GELU) return gelu_fast(x);
   if (act == GEMM_ACT_RELU) return fmaxf(x, 0.f);
   return x;
+}
+__device__ __forceinline__ void apply_act2(int act, float& a, float& b) {
+  if (act == GEMM_ACT_GELU) {
+    gelu_fast2(a, b);
+  } else if (act == GEMM_ACT_RELU) {
+    a = fmaxf(a, 0.f);
+    b = fmaxf(b, 0.f);
+  }
 }
 
 // ACT / RES / OUT / MAP / RBA: compile-time epilogue configuration, -1 = read from GemmEpilogue at run time.
@@ -268,7 +318,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
             for (int j = 0; j < 8; j++) { f[4 * j] += rv[j].x; f[4 * j + 1] += rv[j].y; f[4 * j + 2] += rv[j].z; f[4 * j + 3] += rv[j].w; }
           }
 #pragma unroll
-          for (int i = 0; i < 32; i++) f[i] = apply_act(act, f[i]);
+          for (int i = 0; i < 32; i += 2) apply_act2(act, f[i], f[i + 1]);
           if (has_res && !rba) {
 #pragma unroll
             for (int j = 0; j < 8; j++) { f[4 * j] += rv[j].x; f[4 * j + 1] += rv[j].y; f[4 * j + 2] += rv[j].z; f[4 * j + 3] += rv[j].w; }
@@ -297,7 +347,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
         } else {
           if (!rba) {
 #pragma unroll
-            for (int i = 0; i < 32; i++) f[i] = apply_act(act, f[i]);
+            for (int i = 0; i < 32; i += 2) apply_act2(act, f[i], f[i + 1]);
           }
 #pragma unroll
           for (int j = 0; j < 8; j++)
@@ -312,7 +362,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
               float4 x = *(const float4*)(buf + r * 128 + ((sub_c ^ (r & 7)) << 4));
               const int oc = ocol0 + sub_c * 4;
               if (has_res) { x.x += rres[it].x; x.y += rres[it].y; x.z += rres[it].z; x.w += rres[it].w; }
-              if (rba) { x.x = apply_act(act, x.x); x.y = apply_act(act, x.y); x.z = apply_act(act, x.z); x.w = apply_act(act, x.w); }
+              if (rba) { apply_act2(act, x.x, x.y); apply_act2(act, x.z, x.w); }
               if (out_f32) *(float4*)(e.out_f32 + d * e.ld_f32 + oc) = x;
               if (out_b16) {
                 uint2 pk;

@@ -730,34 +730,4 @@ extern "C" int cv_nodes_analyze(const uint8_t* masks, int B, int H, int W, const
   return CV_OK;
 }
 
-// ------------------------------------------------------------------------------------------------
-// native-resolution CCL (BASELINE cfg 4)
-// ------------------------------------------------------------------------------------------------
-extern "C" size_t cv_ccl_workspace_bytes(int B, int H, int W) {
-  (void)B; (void)H; (void)W;
-  return 256;  // labels are resolved in place in the caller's label image
-}
-
-extern "C" int cv_ccl_label(const uint8_t* masks, int B, int H, int W, int connectivity, int32_t* labels,
-                            int32_t* n_components, void* workspace, size_t workspace_bytes, void* stream_) {
-  cvb_reset_launches();
-  (void)workspace; (void)workspace_bytes;
-  if (!masks || !labels || B <= 0 || H <= 0 || W <= 0)
-    return cvb_fail(CV_ERR_INVALID, "cv_ccl_label: null pointer or non-positive size");
-  if (connectivity != 4 && connectivity != 8) return cvb_fail(CV_ERR_INVALID, "cv_ccl_label: connectivity must be 4 or 8");
-  if ((long long)H * W >= (1ll << 31) - 2) return cvb_fail(CV_ERR_INVALID, "cv_ccl_label: image too large for int32 labels");
-  if (B > 65535) return cvb_fail(CV_ERR_INVALID, "cv_ccl_label: batch too large");
-  cudaStream_t st = (cudaStream_t)stream_;
-  int n = H * W;
-  if (n_components) CVB_CHECK(cudaMemsetAsync(n_components, 0, (size_t)B * 4, st));
-  dim3 cg((W + 31) / 32, (H + 7) / 8, B), cb(32, 8);
-  const double px = (double)B * n;
-  cvb_next_work(5.0 * px);
-  CVB_LAUNCH((k_ccl_init<1, false>), cg, cb, 0, st, masks, labels, H, W);
-  cvb_next_work(5.0 * px);
-  if (connectivity == 8) CVB_LAUNCH((k_ccl_merge<1, false, 8>), cg, cb, 0, st, masks, labels, H, W);
-  else CVB_LAUNCH((k_ccl_merge<1, false, 4>), cg, cb, 0, st, masks, labels, H, W);
-  cvb_next_work(9.0 * px);
-  CVB_LAUNCH((k_ccl_flatten<1, false>), dim3((n + 255) / 256, B), dim3(256), 0, st, masks, labels, n, n_components);
-  return CV_OK;
-}
+// native-resolution CCL (cv_ccl_label, BASELINE cfg 4) lives in ccl_tiles.cu

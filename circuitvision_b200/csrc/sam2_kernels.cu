@@ -738,70 +738,83 @@ int launch_attn_t2i(const float* q, long long q_img_stride, const float* K, cons
   return CV_OK;
 }
 
-// image -> tokens attention, d == 16, T <= 64: thread = (query token, head); K/V of the image's tokens in smem
+// image -> tokens attention, d == 16: thread = one image token (query row), looping over the heads; the image's T
+// decoder tokens (K/V, fp32) sit in shared memory and every lane of a warp reads the same K/V address (broadcast, no
+// bank conflicts); T is a template parameter so the score array lives in registers.
+template <int T>
 __global__ void __launch_bounds__(256) k_attn_i2t(const float* __restrict__ Q, long long ld_q, const float* __restrict__ K,
-                                                  const float* __restrict__ V, int Nq, int T, int heads, int fp16,
+                                                  const float* __restrict__ V, int Nq, int heads, int fp16,
                                                   __nv_bfloat16* __restrict__ out) {
   extern __shared__ float sm[];
   const int C = heads * 16;
   float* sk = sm;
   float* sv = sm + T * C;
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < T * C; i += 256) {
-    sk[i] = K[(long long)b * T * C + i];
-    sv[i] = V[(long long)b * T * C + i];
+  for (int i = threadIdx.x; i < T * C / 4; i += 256) {
+    ((float4*)sk)[i] = ((const float4*)(K + (long long)b * T * C))[i];
+    ((float4*)sv)[i] = ((const float4*)(V + (long long)b * T * C))[i];
   }
   __syncthreads();
-  const int per = 256 / heads;
-  const int h = threadIdx.x % heads;
-  const int tq = blockIdx.x * per + threadIdx.x / heads;
+  const int tq = blockIdx.x * 256 + threadIdx.x;
   if (tq >= Nq) return;
-  long long row = (long long)b * Nq + tq;
-  float qv[16];
-  const float4* qp = (const float4*)(Q + row * ld_q + h * 16);
+  const long long row = (long long)b * Nq + tq;
+  for (int h = 0; h < heads; h++) {
+    float qv[16];
+    const float4* qp = (const float4*)(Q + row * ld_q + h * 16);
 #pragma unroll
-  for (int c = 0; c < 4; c++) {
-    float4 x = qp[c];
-    qv[c * 4] = x.x * 0.25f; qv[c * 4 + 1] = x.y * 0.25f; qv[c * 4 + 2] = x.z * 0.25f; qv[c * 4 + 3] = x.w * 0.25f;
+    for (int c = 0; c < 4; c++) {
+      float4 x = qp[c];
+      // 1/sqrt(16) and log2(e) folded into q so the softmax is a bare ex2
+      qv[c * 4] = x.x * 0.36067376f; qv[c * 4 + 1] = x.y * 0.36067376f;
+      qv[c * 4 + 2] = x.z * 0.36067376f; qv[c * 4 + 3] = x.w * 0.36067376f;
+    }
+    float sc[T];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < T; j++) {
+      const float4* kr = (const float4*)(sk + j * C + h * 16);
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        float4 kk = kr[c];
+        s = fmaf(qv[c * 4], kk.x, s); s = fmaf(qv[c * 4 + 1], kk.y, s);
+        s = fmaf(qv[c * 4 + 2], kk.z, s); s = fmaf(qv[c * 4 + 3], kk.w, s);
+      }
+      sc[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    float l = 0.f, o[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) o[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < T; j++) {
+      float pe;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe) : "f"(sc[j] - mx));
+      l += pe;
+      const float4* vr = (const float4*)(sv + j * C + h * 16);
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        float4 vv = vr[c];
+        o[c * 4] = fmaf(pe, vv.x, o[c * 4]); o[c * 4 + 1] = fmaf(pe, vv.y, o[c * 4 + 1]);
+        o[c * 4 + 2] = fmaf(pe, vv.z, o[c * 4 + 2]); o[c * 4 + 3] = fmaf(pe, vv.w, o[c * 4 + 3]);
+      }
+    }
+    const float inv = 1.f / l;
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = tc::pack16(fp16, o[2 * i] * inv, o[2 * i + 1] * inv);
+    uint4* dst = (uint4*)(out + row * C + h * 16);
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
   }
-  float sc[64];
-  float mx = -INFINITY;
-  for (int j = 0; j < T; j++) {
-    const float* kr = sk + j * C + h * 16;
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 16; i++) s = fmaf(qv[i], kr[i], s);
-    sc[j] = s;
-    mx = fmaxf(mx, s);
-  }
-  float l = 0.f, o[16];
-#pragma unroll
-  for (int i = 0; i < 16; i++) o[i] = 0.f;
-  for (int j = 0; j < T; j++) {
-    float pexp = expf(sc[j] - mx);
-    l += pexp;
-    const float* vr = sv + j * C + h * 16;
-#pragma unroll
-    for (int i = 0; i < 16; i++) o[i] = fmaf(pexp, vr[i], o[i]);
-  }
-  float inv = 1.f / l;
-  uint32_t w[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    w[i] = tc::pack16(fp16, o[2 * i] * inv, o[2 * i + 1] * inv);
-  }
-  uint4* dst = (uint4*)(out + row * C + h * 16);
-  dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-  dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
 int launch_attn_i2t(const float* Q, long long ld_q, const float* K, const float* V, int B, int Nq, int T, int heads, int d,
                     int fp16, __nv_bfloat16* out, cudaStream_t st) {
-  if (d != 16 || T > 64 || (256 % heads)) return cvb_fail(CV_ERR_INVALID, "attn_i2t: d==16, T<=64, 256%heads==0");
-  int per = 256 / heads;
+  if (d != 16 || T != 38 || heads > 16) return cvb_fail(CV_ERR_INVALID, "attn_i2t: built for d == 16, T == 38 decoder tokens");
   size_t smem = (size_t)2 * T * heads * 16 * sizeof(float);
   cvb_next_work(4.0 * B * (double)T * Nq * heads * d);
-  CVB_LAUNCH(k_attn_i2t, dim3((Nq + per - 1) / per, B), dim3(256), smem, st, Q, ld_q, K, V, Nq, T, heads, fp16, out);
+  CVB_LAUNCH((k_attn_i2t<38>), dim3((Nq + 255) / 256, B), dim3(256), smem, st, Q, ld_q, K, V, Nq, heads, fp16, out);
   return CV_OK;
 }
 

@@ -260,7 +260,9 @@ def ccl_label(d_masks: torch.Tensor, connectivity: int = 8, want_counts: bool = 
     counts = torch.empty((B,), dtype=torch.int32, device=d_masks.device) if want_counts else None
     with torch.cuda.device(d_masks.device):
         st = torch.cuda.current_stream(d_masks.device).cuda_stream
+        ws_bytes = lib.cv_ccl_workspace_bytes(B, H, W)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=d_masks.device)
         rc = lib.cv_ccl_label(d_masks.data_ptr(), B, H, W, connectivity, labels.data_ptr(),
-                              counts.data_ptr() if want_counts else None, None, 0, st)
+                              counts.data_ptr() if want_counts else None, ws.data_ptr(), ws_bytes, st)
     _lib.check(rc, "cv_ccl_label")
     return labels, counts
