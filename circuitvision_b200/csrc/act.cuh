@@ -1,0 +1,71 @@
+// Activation helpers shared by the GEMM epilogue and the CUDA-core kernels: exact-erf GELU evaluated with the
+// Abramowitz & Stegun 7.1.26 erf (|error| <= 1.5e-7) on scalar and on packed fp32x2 (FFMA2) arithmetic.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cvb {
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// exact-erf GELU with erf from Abramowitz & Stegun 7.1.26 (|erf error| <= 1.5e-7, far below the bf16 / fp32-sum noise
+// of the value it is applied to): 2 MUFU + ~14 FMA-pipe instructions instead of erff's ~40.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  float ex;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(z * z * -1.4426950408889634f));
+  const float erf_abs = fmaf(-p, ex, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+
+// The same GELU on a PAIR of values with Blackwell's packed fp32x2 arithmetic (FFMA2 / FMUL2): the polynomial, the
+// exponent argument and the final blend each issue once for two elements, which is what the epilogue-bound fc1 GEMMs
+// need (the epilogue, not the tensor pipe, limits them: ~100 M GELUs per image).
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void up2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
+  const uint64_t z = pk2(fabsf(x0) * 0.70710678118654752440f, fabsf(x1) * 0.70710678118654752440f);
+  float d0, d1, t0, t1;
+  up2(fma2(z, pk2(0.3275911f, 0.3275911f), pk2(1.0f, 1.0f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const uint64_t t = pk2(t0, t1);
+  // negated A&S coefficients: p = -(a1 t + ... + a5 t^5)
+  uint64_t p = fma2(t, pk2(-1.061405429f, -1.061405429f), pk2(1.453152027f, 1.453152027f));
+  p = fma2(p, t, pk2(-1.421413741f, -1.421413741f));
+  p = fma2(p, t, pk2(0.284496736f, 0.284496736f));
+  p = fma2(p, t, pk2(-0.254829592f, -0.254829592f));
+  p = mul2(p, t);
+  float e0, e1, ex0, ex1;
+  up2(mul2(mul2(z, z), pk2(-1.4426950408889634f, -1.4426950408889634f)), e0, e1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex0) : "f"(e0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex1) : "f"(e1));
+  float r0, r1;
+  up2(fma2(p, pk2(ex0, ex1), pk2(1.0f, 1.0f)), r0, r1);  // |erf| = 1 - poly * exp(-z^2)
+  const uint64_t hx = mul2(pk2(x0, x1), pk2(0.5f, 0.5f));
+  up2(fma2(hx, pk2(copysignf(r0, x0), copysignf(r1, x1)), hx), x0, x1);
+}
+
+
+}  // namespace cvb

@@ -5,9 +5,11 @@
 //
 // Traffic plan (the kernel is HBM-bound; algorithmic bytes = 1 B/px mask read + 4 B/px label write):
 //   pass A  k_ccl_tile_label : each CTA loads a 128 x 32 tile of the mask as BITS (one 32-pixel word per thread), labels it
-//                              entirely in shared memory (sub-runs = maximal runs inside a word; unions between words of
-//                              a row and between adjacent rows by bit overlap; atomicMin union-find on a 16 KB parent
-//                              array) and writes the label image once, fully coalesced: 1 + 4 B/px.
+//                              entirely in shared memory (elements = maximal horizontal runs; unions between adjacent
+//                              rows by bit overlap; atomicMin union-find on a 16 KB parent array) and writes the label
+//                              image once, fully coalesced: 1 + 4 B/px.  It also emits a per-word "dirty" bitmap
+//                              (word holds a run of a component that touches the tile border) and counts the
+//                              components that stay inside their tile.
 //   pass B  k_ccl_tile_seams : only pixels on tile seams (3.9 % of the image) merge components across tiles with the
 //                              global atomicMin union-find on the label image (roots point at roots).
 //   pass B2 k_ccl_tile_compress: path halving from the same seam pixels so the trees pass C walks are one or two hops deep.
@@ -127,27 +129,31 @@ __device__ __forceinline__ int elem_of(const uint32_t (*bits)[CT_WORDS], const i
   return (st == 0 && carries_in(bits, r, c)) ? fid[r][c] : r * CT_W + c * 32 + st;
 }
 
-// Labels one tile in shared memory.  On return (after the trailing __syncthreads) P[e] holds the ROOT (tile-local pixel
-// index of the component's first pixel in raster order) for every run element e of the tile.
+// Thread <-> word mapping: lane = row, warp = word column (r = t % 32, c = t / 32).  A vertical wire then keeps whole
+// warps busy instead of one lane in every warp, which matters because the union-find code is divergent.
+//
+// Builds the tile's union-find in shared memory.  On return (after the trailing __syncthreads) the forest is complete:
+// sfind(P, e) gives the ROOT (tile-local pixel index of the component's first pixel in raster order) of run element e.
 template <int CONN>
 __device__ __forceinline__ uint32_t tile_label(const uint8_t* __restrict__ im, int H, int W, int x0, int y0, bool vec_ok,
                                                uint32_t (*bits)[CT_WORDS], int (*fid)[CT_WORDS], int* P) {
-  const int r = threadIdx.x / CT_WORDS, c = threadIdx.x % CT_WORDS;
+  const int r = threadIdx.x % CT_H, c = threadIdx.x / CT_H;
   const uint32_t w = load_word(im, H, W, y0 + r, x0 + c * 32, vec_ok);
   const int base = r * CT_W + c * 32;
-  // resolve runs across the words of the row with shuffles (the 4 words of a row sit in 4 adjacent lanes)
-  const uint32_t lw = __shfl_up_sync(0xffffffffu, w, 1);
-  const bool cin = c > 0 && (w & 1u) && (lw >> 31);
-  int first = base;  // element of my first sub-run
-#pragma unroll
-  for (int k = 0; k < CT_WORDS - 1; k++) {
-    const int lf = __shfl_up_sync(0xffffffffu, first, 1);
-    if (cin) {
+  bits[r][c] = w;
+  __syncthreads();
+  // the run that enters my word from the left starts in the nearest word to the left that is not completely set
+  bool cin = false;
+  int first = base;
+  if (c > 0 && (w & 1u) && (bits[r][c - 1] >> 31)) {
+    cin = true;
+    for (int k = c - 1; k >= 0; k--) {
+      const uint32_t lw = bits[r][k];
       const int ls = run_start(lw, 31);
-      first = ls > 0 ? base - 32 + ls : lf;
+      first = r * CT_W + k * 32 + ls;
+      if (ls > 0 || k == 0 || !(bits[r][k - 1] >> 31)) break;
     }
   }
-  bits[r][c] = w;
   fid[r][c] = first;
   uint32_t starts = w & ~(w << 1);
   if (cin) starts &= ~1u;  // a continued run is not an element of its own
@@ -185,39 +191,83 @@ __device__ __forceinline__ uint32_t tile_label(const uint8_t* __restrict__ im, i
     }
   }
   __syncthreads();
-  for (uint32_t s = starts; s; s &= s - 1) {
-    int i = __ffs(s) - 1;
-    P[base + i] = sfind(P, base + i);  // roots point at themselves, so concurrent finds stay valid
-  }
-  __syncthreads();
   return w;
 }
 
+// dirty[(b*n_tiles + tile)*4 + warp] bit l: the word owned by thread 32*warp + l holds a sub-run of a component that
+// touches the tile border — only such components can be merged by the seam pass, so only those words are revisited by
+// pass C.  Components that stay inside their tile are final after pass A and are counted here.
 template <int CONN>
 __global__ void __launch_bounds__(CT_THREADS) k_ccl_tile_label(const uint8_t* __restrict__ masks, int* __restrict__ labels,
-                                                                int H, int W, int vec_ok) {
+                                                                int H, int W, int vec_ok, uint32_t* __restrict__ dirty,
+                                                                int* __restrict__ ncomp, int* __restrict__ partial) {
   __shared__ uint32_t bits[CT_H][CT_WORDS];
   __shared__ int fid[CT_H][CT_WORDS];
   __shared__ int P[CT_H * CT_W];
+  __shared__ uint32_t touch[CT_H * CT_W / 32];  // bit per tile-local pixel: root of a border-touching component
+  __shared__ int closed_roots;
   const int b = blockIdx.z, x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
   const uint8_t* im = masks + (size_t)b * H * W;
   int* L = labels + (size_t)b * H * W;
-  tile_label<CONN>(im, H, W, x0, y0, vec_ok != 0, bits, fid, P);
+  if (threadIdx.x < CT_H * CT_W / 32) touch[threadIdx.x] = 0u;
+  if (threadIdx.x == 0) closed_roots = 0;
+  const uint32_t w = tile_label<CONN>(im, H, W, x0, y0, vec_ok != 0, bits, fid, P);
+  int* G = P;  // after the second sync below the slots hold the GLOBAL label of the sub-run starting there
+  const int r = threadIdx.x % CT_H, c = threadIdx.x / CT_H;
+  const int base = r * CT_W + c * 32;
+  const bool cin = carries_in(bits, r, c);
+  const uint32_t sub = w & ~(w << 1);  // every sub-run of my word, continued or not
+  // root and global label of every sub-run; roots of components that touch the tile border are marked.  The root is
+  // parked in P[base + i]: for a run element that is path compression, for a continued sub-run the slot is unused.
+  for (uint32_t s = sub; s; s &= s - 1) {
+    const int i = __ffs(s) - 1;
+    const int root = sfind(P, (i == 0 && cin) ? fid[r][c] : base + i);
+    const bool edge = r == 0 || r == CT_H - 1 || (c == 0 && i == 0) || (c == CT_WORDS - 1 && i + run_len(w, i) == 32);
+    if (edge) atomicOr(&touch[root >> 5], 1u << (root & 31));
+    if (root != base + i) P[base + i] = root;
+  }
+  __syncthreads();
+  bool my_dirty = false;
+  int n_closed = 0;
+  for (uint32_t s = sub; s; s &= s - 1) {
+    const int i = __ffs(s) - 1;
+    const int root = P[base + i];
+    const bool t = (touch[root >> 5] >> (root & 31)) & 1u;
+    my_dirty |= t;
+    n_closed += (!t && root == base + i);  // first pixel of a component that cannot change any more
+    G[base + i] = (y0 + root / CT_W) * W + x0 + (root % CT_W) + 1;  // nobody else reads my slots any more
+  }
+  if (my_dirty) n_closed = 0;  // pass C revisits this word and counts every root in it
+  const uint32_t dmask = __ballot_sync(0xffffffffu, my_dirty);
+  if (dirty && (threadIdx.x & 31) == 0)
+    dirty[(((size_t)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (CT_THREADS / 32) + (threadIdx.x >> 5)] = dmask;
+  if (ncomp) {
+    for (int o = 16; o; o >>= 1) n_closed += __shfl_xor_sync(0xffffffffu, n_closed, o);
+    if ((threadIdx.x & 31) == 0 && n_closed) atomicAdd(&closed_roots, n_closed);
+  }
+  __syncthreads();
+  if (ncomp && dirty && threadIdx.x == 0 && closed_roots) {
+    if (partial) atomicAdd(partial + ((size_t)b * 32 + ((blockIdx.x + blockIdx.y) & 31)) * 32, closed_roots);
+    else atomicAdd(ncomp + b, closed_roots);
+  }
   // coalesced label write: each warp takes rows warp, warp+4, ...; lane l owns pixels 4l..4l+3 of the row
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = lane >> 3, sh = (lane & 7) * 4;
-  for (int r = warp; r < CT_H; r += CT_THREADS / 32) {
-    const int y = y0 + r;
+  const int wc = lane >> 3, sh = (lane & 7) * 4;
+  for (int rr = warp; rr < CT_H; rr += CT_THREADS / 32) {
+    const int y = y0 + rr;
     if (y >= H) break;
-    const uint32_t word = bits[r][c];
+    const uint32_t word = bits[rr][wc];
+    const uint32_t nib = (word >> sh) & 0xFu;
     int out[4] = {0, 0, 0, 0};
-    if ((word >> sh) & 0xFu) {
+    if (nib) {
+      const int gb = rr * CT_W + wc * 32;
+      if (nib == 0xFu) {
+        out[0] = out[1] = out[2] = out[3] = G[gb + run_start(word, sh)];
+      } else {
 #pragma unroll
-      for (int k = 0; k < 4; k++)
-        if ((word >> (sh + k)) & 1u) {
-          const int root = P[elem_of(bits, fid, r, c, run_start(word, sh + k))];
-          out[k] = (y0 + root / CT_W) * W + x0 + (root % CT_W) + 1;
-        }
+        for (int k = 0; k < 4; k++)
+          if ((nib >> k) & 1u) out[k] = G[gb + run_start(word, sh + k)];
+      }
     }
     const int x = x0 + lane * 4;
     int* dst = L + (size_t)y * W + x;
@@ -297,22 +347,25 @@ __global__ void __launch_bounds__(256) k_ccl_tile_compress(const uint8_t* __rest
   }
 }
 
-// pass C: one thread per 32-pixel word.  The label pass A wrote at the LAST pixel of a sub-run names the run's
-// tile-local root (only root pixels — always the first pixel of a run — are modified by the seam unions); if that root
-// was merged into another component, the whole run is rewritten with the global root.
-__global__ void __launch_bounds__(256) k_ccl_tile_fixup(const uint8_t* __restrict__ masks, int* __restrict__ labels, int H, int W,
-                                                        int vec_ok, int* __restrict__ ncomp, int* __restrict__ partial) {
-  __shared__ int block_roots;
-  if (threadIdx.x == 0) block_roots = 0;
-  __syncthreads();
-  const int b = blockIdx.z;
+// pass C: same thread <-> word mapping as pass A.  Only words flagged dirty are revisited.  The label pass A wrote at
+// the LAST pixel of a sub-run names the run's tile-local root (only root pixels — always the first pixel of a run — are
+// modified by the seam unions); if that root was merged into another component, the whole run is rewritten.
+// With dirty == nullptr every word is visited (and every root is counted here).
+__global__ void __launch_bounds__(CT_THREADS) k_ccl_tile_fixup(const uint8_t* __restrict__ masks, int* __restrict__ labels, int H,
+                                                                int W, int vec_ok, const uint32_t* __restrict__ dirty,
+                                                                int* __restrict__ ncomp, int* __restrict__ partial) {
+  const int b = blockIdx.z, x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
+  const int lane = threadIdx.x & 31;
+  uint32_t dmask = 0xffffffffu;
+  if (dirty)
+    dmask = __ldg(dirty + (((size_t)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (CT_THREADS / 32) + (threadIdx.x >> 5));
+  if (dmask == 0u) return;  // whole warp: nothing in its 8 rows can have changed
   const uint8_t* im = masks + (size_t)b * H * W;
   int* L = labels + (size_t)b * H * W;
-  const int words_per_row = (W + 31) / 32;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;  // < 2^31 / 32 words
+  const int r = threadIdx.x % CT_H, c = threadIdx.x / CT_H;
+  const int y = y0 + r, x = x0 + c * 32;
   int n_roots = 0;
-  if (t < words_per_row * H) {
-    const int y = t / words_per_row, x = (t - y * words_per_row) * 32;
+  if ((dmask >> lane) & 1u) {
     const uint32_t w = load_word(im, H, W, y, x, vec_ok != 0);
     for (uint32_t s = w & ~(w << 1); s; s &= s - 1) {
       const int i = __ffs(s) - 1;
@@ -323,17 +376,15 @@ __global__ void __launch_bounds__(256) k_ccl_tile_fixup(const uint8_t* __restric
       if (ref != f + 1) {
         for (int k = 0; k < len; k++) L[px + k] = f + 1;
       }
-      n_roots += (f == px);  // this run starts at the first pixel of its component
+      // this run starts at the first pixel of its component (pass A counted the roots of the words it left clean)
+      n_roots += (f == px);
     }
   }
   if (ncomp) {
     for (int o = 16; o; o >>= 1) n_roots += __shfl_xor_sync(0xffffffffu, n_roots, o);
-    if ((threadIdx.x & 31) == 0 && n_roots) atomicAdd(&block_roots, n_roots);
-    __syncthreads();
-    if (threadIdx.x == 0 && block_roots) {
-      // spread the per-image counter over 32 slots so that the adds do not serialise on one L2 line
-      if (partial) atomicAdd(partial + ((size_t)b * 32 + (blockIdx.x & 31)) * 32, block_roots);
-      else atomicAdd(ncomp + b, block_roots);
+    if (lane == 0 && n_roots) {
+      if (partial) atomicAdd(partial + ((size_t)b * 32 + ((blockIdx.x + blockIdx.y + 7) & 31)) * 32, n_roots);
+      else atomicAdd(ncomp + b, n_roots);
     }
   }
 }
@@ -351,30 +402,31 @@ using namespace cvb;
 
 template <int CONN>
 static int ccl_run(const uint8_t* masks, int B, int H, int W, int32_t* labels, int32_t* n_components, int* partial,
-                   cudaStream_t st) {
+                   uint32_t* dirty, cudaStream_t st) {
   const int vec_ok = (W % 16 == 0) && (((uintptr_t)masks & 15) == 0) && (((uintptr_t)labels & 15) == 0);
   dim3 tg((W + CT_W - 1) / CT_W, (H + CT_H - 1) / CT_H, B);
   const double px = (double)B * H * W;
   cvb_next_work(5.0 * px);
-  CVB_LAUNCH((k_ccl_tile_label<CONN>), tg, dim3(CT_THREADS), 0, st, masks, labels, H, W, vec_ok);
+  CVB_LAUNCH((k_ccl_tile_label<CONN>), tg, dim3(CT_THREADS), 0, st, masks, labels, H, W, vec_ok, dirty, n_components, partial);
   const long long seam_px = max((long long)((H - 1) / CT_H) * W, (long long)((W - 1) / CT_W) * H);
   if (seam_px > 0) {
-    cvb_next_work(0.0);
     CVB_LAUNCH((k_ccl_tile_seams<CONN>), dim3((unsigned)((seam_px + 255) / 256), 2, B), dim3(256), 0, st, masks, labels, H, W);
     CVB_LAUNCH(k_ccl_tile_compress, dim3((unsigned)((seam_px + 255) / 256), 2, B), dim3(256), 0, st, masks, labels, H, W);
   }
-  cvb_next_work(1.0 * px);
-  const long long n_words = (long long)((W + 31) / 32) * H;
-  CVB_LAUNCH(k_ccl_tile_fixup, dim3((unsigned)((n_words + 255) / 256), 1, B), dim3(256), 0, st, masks, labels, H, W, vec_ok,
-             n_components, partial);
+  CVB_LAUNCH(k_ccl_tile_fixup, tg, dim3(CT_THREADS), 0, st, masks, labels, H, W, vec_ok, dirty, n_components, partial);
   if (n_components && partial) CVB_LAUNCH(k_ccl_count_finish, dim3(B), dim3(32), 0, st, partial, n_components, B);
   return CV_OK;
 }
 
+static size_t ccl_dirty_bytes(int B, int H, int W) {
+  return (size_t)B * ((W + CT_W - 1) / CT_W) * ((H + CT_H - 1) / CT_H) * (CT_THREADS / 32) * sizeof(uint32_t);
+}
+static size_t ccl_partial_bytes(int B) { return (size_t)(B > 0 ? B : 1) * 32 * 32 * sizeof(int); }
+
 extern "C" size_t cv_ccl_workspace_bytes(int B, int H, int W) {
-  (void)H; (void)W;
-  // labels are resolved in place in the caller's label image; the workspace only spreads the component counters
-  return (size_t)(B > 0 ? B : 1) * 32 * 32 * sizeof(int);
+  // labels are resolved in place in the caller's label image; the workspace holds the spread component counters and
+  // the per-tile dirty bitmap
+  return ccl_partial_bytes(B) + ccl_dirty_bytes(B, H, W);
 }
 
 extern "C" int cv_ccl_label(const uint8_t* masks, int B, int H, int W, int connectivity, int32_t* labels,
@@ -387,13 +439,13 @@ extern "C" int cv_ccl_label(const uint8_t* masks, int B, int H, int W, int conne
   if (B > 65535) return cvb_fail(CV_ERR_INVALID, "cv_ccl_label: batch too large");
   cudaStream_t st = (cudaStream_t)stream_;
   int* partial = nullptr;
-  if (n_components) {
-    CVB_CHECK(cudaMemsetAsync(n_components, 0, (size_t)B * 4, st));
-    if (workspace && workspace_bytes >= cv_ccl_workspace_bytes(B, H, W)) {
-      partial = (int*)workspace;
-      CVB_CHECK(cudaMemsetAsync(partial, 0, cv_ccl_workspace_bytes(B, H, W), st));
-    }
+  uint32_t* dirty = nullptr;
+  if (workspace && workspace_bytes >= cv_ccl_workspace_bytes(B, H, W)) {
+    partial = (int*)workspace;
+    dirty = (uint32_t*)((uint8_t*)workspace + ccl_partial_bytes(B));
+    if (n_components) CVB_CHECK(cudaMemsetAsync(partial, 0, ccl_partial_bytes(B), st));
   }
-  return connectivity == 8 ? ccl_run<8>(masks, B, H, W, labels, n_components, partial, st)
-                           : ccl_run<4>(masks, B, H, W, labels, n_components, partial, st);
+  if (n_components) CVB_CHECK(cudaMemsetAsync(n_components, 0, (size_t)B * 4, st));
+  return connectivity == 8 ? ccl_run<8>(masks, B, H, W, labels, n_components, partial, dirty, st)
+                           : ccl_run<4>(masks, B, H, W, labels, n_components, partial, dirty, st);
 }

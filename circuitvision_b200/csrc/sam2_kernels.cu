@@ -6,10 +6,11 @@
 
 #include "common.cuh"
 #include "tc05.cuh"
+#include "act.cuh"
 
 namespace cvb {
 
-__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_exact(float x) { return gelu_fast(x); }
 __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
@@ -921,24 +922,27 @@ int launch_select_mask(const float* masks, const float* iou, const unsigned int*
 // CTA = 32 x 32 output pixels.  up[42][44]: bilinearly upsampled logits of the tile + halo 5 (zero outside the
 // 1024^2 image: Conv2d padding='same' pads the upsampled map with zeros).  Thread = 4 consecutive pixels of a row.
 constexpr int TL = 32, THALO = 5, TUP = TL + 2 * THALO;
-struct TailConst {
-  float w3[4 * 9], w5[4 * 25], w7[4 * 49], w11[4 * 121];
+// weights tap-major with the 4 channels of a tap contiguous, so one broadcast LDS.128 feeds 16 FMAs (4 channels x 4
+// pixels); with scalar weight loads the kernel was LSU-bound (one shared-memory wavefront per 4 FMAs)
+struct __align__(16) TailConst {
+  float4 w3[9], w5[25], w7[49], w11[121];
   float b[16], cw[16], cb;
 };
 
 __global__ void __launch_bounds__(256) k_tail(const float* __restrict__ low, int src_full, RefineWeights rw, float* __restrict__ high,
                                               uint8_t* __restrict__ mask, int* __restrict__ extents) {
-  __shared__ float up[TUP][TUP + 2];
+  __shared__ __align__(16) float up[TUP][TUP + 2];
   __shared__ TailConst tc_;
   const int S = 1024, LS = 256;
   const int b = blockIdx.z;
   const int X0 = blockIdx.x * TL, Y0 = blockIdx.y * TL;
   const float* lo = low + (long long)b * (src_full ? S * S : LS * LS);
   if (rw.use_refine) {
-    for (int i = threadIdx.x; i < 4 * 9; i += 256) tc_.w3[i] = rw.w[0][i];
-    for (int i = threadIdx.x; i < 4 * 25; i += 256) tc_.w5[i] = rw.w[1][i];
-    for (int i = threadIdx.x; i < 4 * 49; i += 256) tc_.w7[i] = rw.w[2][i];
-    for (int i = threadIdx.x; i < 4 * 121; i += 256) tc_.w11[i] = rw.w[3][i];
+    // global layout [channel][k*k] -> shared [tap][channel]
+    for (int i = threadIdx.x; i < 4 * 9; i += 256) ((float*)tc_.w3)[(i % 9) * 4 + i / 9] = rw.w[0][i];
+    for (int i = threadIdx.x; i < 4 * 25; i += 256) ((float*)tc_.w5)[(i % 25) * 4 + i / 25] = rw.w[1][i];
+    for (int i = threadIdx.x; i < 4 * 49; i += 256) ((float*)tc_.w7)[(i % 49) * 4 + i / 49] = rw.w[2][i];
+    for (int i = threadIdx.x; i < 4 * 121; i += 256) ((float*)tc_.w11)[(i % 121) * 4 + i / 121] = rw.w[3][i];
     if (threadIdx.x < 16) {
       tc_.b[threadIdx.x] = rw.b[threadIdx.x >> 2][threadIdx.x & 3];
       tc_.cw[threadIdx.x] = rw.cw[threadIdx.x];
@@ -975,48 +979,42 @@ __global__ void __launch_bounds__(256) k_tail(const float* __restrict__ low, int
         for (int p = 0; p < 4; p++) acc[a][c][p] = 0.f;
 #pragma unroll 1
     for (int dy = -5; dy <= 5; dy++) {
-      float row[14];
+      float row[16];
+      {
+        // tx is a multiple of 4 and the row pitch is 44 floats: four aligned 16-byte loads cover row[0..15] (14 used)
+        const float4* rp = (const float4*)&up[ty + THALO + dy][tx];
 #pragma unroll
-      for (int i = 0; i < 14; i++) row[i] = up[ty + THALO + dy][tx + i];
+        for (int i = 0; i < 4; i++) {
+          float4 v = rp[i];
+          row[4 * i] = v.x; row[4 * i + 1] = v.y; row[4 * i + 2] = v.z; row[4 * i + 3] = v.w;
+        }
+      }
+#define CVB_TAP(ACC, WV, OFF)                                   \
+  {                                                             \
+    const float4 wv = (WV);                                     \
+    _Pragma("unroll") for (int p = 0; p < 4; p++) {             \
+      ACC[0][p] = fmaf(wv.x, row[(OFF) + p], ACC[0][p]);        \
+      ACC[1][p] = fmaf(wv.y, row[(OFF) + p], ACC[1][p]);        \
+      ACC[2][p] = fmaf(wv.z, row[(OFF) + p], ACC[2][p]);        \
+      ACC[3][p] = fmaf(wv.w, row[(OFF) + p], ACC[3][p]);        \
+    }                                                           \
+  }
       // branch 3: k = 11
 #pragma unroll
-      for (int dx = 0; dx < 11; dx++)
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-          float w = tc_.w11[c * 121 + (dy + 5) * 11 + dx];
-#pragma unroll
-          for (int p = 0; p < 4; p++) acc[3][c][p] = fmaf(w, row[dx + p], acc[3][c][p]);
-        }
+      for (int dx = 0; dx < 11; dx++) CVB_TAP(acc[3], tc_.w11[(dy + 5) * 11 + dx], dx)
       if (dy >= -3 && dy <= 3) {
 #pragma unroll
-        for (int dx = 0; dx < 7; dx++)
-#pragma unroll
-          for (int c = 0; c < 4; c++) {
-            float w = tc_.w7[c * 49 + (dy + 3) * 7 + dx];
-#pragma unroll
-            for (int p = 0; p < 4; p++) acc[2][c][p] = fmaf(w, row[dx + 2 + p], acc[2][c][p]);
-          }
+        for (int dx = 0; dx < 7; dx++) CVB_TAP(acc[2], tc_.w7[(dy + 3) * 7 + dx], dx + 2)
       }
       if (dy >= -2 && dy <= 2) {
 #pragma unroll
-        for (int dx = 0; dx < 5; dx++)
-#pragma unroll
-          for (int c = 0; c < 4; c++) {
-            float w = tc_.w5[c * 25 + (dy + 2) * 5 + dx];
-#pragma unroll
-            for (int p = 0; p < 4; p++) acc[1][c][p] = fmaf(w, row[dx + 3 + p], acc[1][c][p]);
-          }
+        for (int dx = 0; dx < 5; dx++) CVB_TAP(acc[1], tc_.w5[(dy + 2) * 5 + dx], dx + 3)
       }
       if (dy >= -1 && dy <= 1) {
 #pragma unroll
-        for (int dx = 0; dx < 3; dx++)
-#pragma unroll
-          for (int c = 0; c < 4; c++) {
-            float w = tc_.w3[c * 9 + (dy + 1) * 3 + dx];
-#pragma unroll
-            for (int p = 0; p < 4; p++) acc[0][c][p] = fmaf(w, row[dx + 4 + p], acc[0][c][p]);
-          }
+        for (int dx = 0; dx < 3; dx++) CVB_TAP(acc[0], tc_.w3[(dy + 1) * 3 + dx], dx + 4)
       }
+#undef CVB_TAP
     }
 #pragma unroll
     for (int p = 0; p < 4; p++) {
@@ -1024,7 +1022,12 @@ __global__ void __launch_bounds__(256) k_tail(const float* __restrict__ low, int
 #pragma unroll
       for (int a = 0; a < 4; a++)
 #pragma unroll
-        for (int c = 0; c < 4; c++) o = fmaf(tc_.cw[a * 4 + c], gelu_exact(acc[a][c][p] + tc_.b[a * 4 + c]), o);
+        for (int c = 0; c < 4; c += 2) {
+          float g0 = acc[a][c][p] + tc_.b[a * 4 + c], g1 = acc[a][c + 1][p] + tc_.b[a * 4 + c + 1];
+          gelu_fast2(g0, g1);
+          o = fmaf(tc_.cw[a * 4 + c], g0, o);
+          o = fmaf(tc_.cw[a * 4 + c + 1], g1, o);
+        }
       res[p] = o;
     }
   } else {
