@@ -14,6 +14,8 @@
 // keeps that flag a runtime value for the general C-ABI entry point.
 #include "gemm_tc.cuh"
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc05.cuh"
 #include "act.cuh"
@@ -22,13 +24,26 @@ namespace cvb {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_BUF = 4096;  // one 32 x 32 fp32 box
+constexpr int GEMM_SMEM_MAX = 232448;
 
-template <int BN>
+// CG = CTAs cooperating on one accumulator tile (cta_group): 1 = 128 x BN per CTA; 2 = a CTA pair computes 256 x BN,
+// each CTA holding its own 128 rows of A and HALF of the B tile, so the operand bytes per CTA and k-block drop from
+// 16 + BN/8 KB to 16 + BN/16 KB — more k-blocks in flight for the same shared memory and less L2->SM traffic per flop,
+// which is what bounds the K >= 384 shapes (ncu: the MMA thread spins on the full barriers, not on the epilogue).
+template <int BN, int CG>
+constexpr int gemm_stage_bytes() { return GEMM_BM * 128 + (BN / CG) * 128; }
+template <int CG>
+constexpr int gemm_epi_bufs() { return CG == 2 ? 1 : 2; }
+template <int BN, int CG>
+constexpr int gemm_stages() {
+  int s = (GEMM_SMEM_MAX - 1024 - 256 - 8 * gemm_epi_bufs<CG>() * GEMM_EPI_BUF) / gemm_stage_bytes<BN, CG>();
+  return s > 8 ? 8 : (CG == 1 && s > 4 ? 4 : s);
+}
+template <int BN, int CG>
 constexpr int gemm_smem_bytes() {
-  return 1024 /*align slack*/ + GEMM_STAGES * (GEMM_BM * 128 + BN * 128) + 8 * 2 * GEMM_EPI_BUF + 256;
+  return 1024 /*align slack*/ + gemm_stages<BN, CG>() * gemm_stage_bytes<BN, CG>() + 8 * gemm_epi_bufs<CG>() * GEMM_EPI_BUF + 256;
 }
 
 __device__ __forceinline__ long long gemm_dest_row(const GemmEpilogue& e, int map, long long r) {
@@ -67,20 +82,23 @@ __device__ __forceinline__ void apply_act2(int act, float& a, float& b) {
 
 // ACT / RES / OUT / MAP / RBA: compile-time epilogue configuration, -1 = read from GemmEpilogue at run time.
 // OUT: 0 = fp32, 1 = bf16, 2 = both (runtime-only).
-template <int BN, int ACT, int RES, int OUT, int MAP, int RBA>
+template <int BN, int ACT, int RES, int OUT, int MAP, int RBA, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
           const __grid_constant__ CUtensorMap tmap_out, GemmProblem p, GemmEpilogue e) {
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
-  constexpr int A_BYTES = GEMM_BM * 128, B_BYTES = BN * 128;
+  static_assert(CG == 1 || CG == 2, "CG");
+  constexpr int GEMM_STAGES = gemm_stages<BN, CG>();
+  constexpr int EPI_BUFS = gemm_epi_bufs<CG>();
+  constexpr int A_BYTES = GEMM_BM * 128, B_BYTES = (BN / CG) * 128;
   constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   constexpr bool TMA_OUT = (MAP == GEMM_MAP_IDENTITY) && (OUT == 0 || OUT == 1);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + GEMM_STAGES * A_BYTES;
-  uint8_t* epi = smem + GEMM_STAGES * (A_BYTES + B_BYTES);  // [8 warps][2][4096], 1024-byte aligned
-  uint64_t* bars = (uint64_t*)(epi + 8 * 2 * GEMM_EPI_BUF);
+  uint8_t* epi = smem + GEMM_STAGES * (A_BYTES + B_BYTES);  // [8 warps][EPI_BUFS][4096], 1024-byte aligned
+  uint64_t* bars = (uint64_t*)(epi + 8 * EPI_BUFS * GEMM_EPI_BUF);
   uint64_t* full = bars;                     // [STAGES]
   uint64_t* empty = bars + GEMM_STAGES;      // [STAGES]
   uint64_t* tfull = bars + 2 * GEMM_STAGES;  // [2]
@@ -88,7 +106,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = p.n_tiles_m * p.n_tiles_n;
+  // CG == 2: a tile is 256 rows; CTA `rank` of the pair owns rows [tile_m*256 + rank*128, +128)
+  const int rank = CG == 2 ? (int)tc::cluster_ctarank() : 0;
+  const int n_tiles = ((p.n_tiles_m + CG - 1) / CG) * p.n_tiles_n;
+  const int tile0 = blockIdx.x / CG, tile_stride = gridDim.x / CG;
   const int n_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
 
   if (warp == 0 && lane == 0) {
@@ -103,13 +124,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
     }
     for (int i = 0; i < 2; i++) {
       tc::mbar_init(&tfull[i], 1);
-      tc::mbar_init(&tempty[i], 8);
+      tc::mbar_init(&tempty[i], 8 * CG);  // the leader collects the epilogue warps of both CTAs
     }
     tc::fence_barrier_init();
   }
-  if (warp == 2) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 2) {
+    if (CG == 2) tc::tmem_alloc2<TMEM_COLS>(tmem_slot);
+    else tc::tmem_alloc<TMEM_COLS>(tmem_slot);
+  }
   tc::tc_fence_before();
   __syncthreads();
+  if (CG == 2) tc::cluster_sync();  // the peer's barriers are initialised before anything arrives on them
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -118,26 +143,34 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        int mb = t / p.n_tiles_n, nb = t - mb * p.n_tiles_n;
+      for (int t = tile0; t < n_tiles; t += tile_stride) {
+        int tm = t / p.n_tiles_n, nb = t - tm * p.n_tiles_n;
+        const int mb = tm * CG + rank;
         for (int kb = 0; kb < n_kb; kb++) {
           tc::mbar_wait(&empty[stage], phase ^ 1);
-          tc::mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
-          tc::tma_load_2d(sA + stage * A_BYTES, &tmap_a, &full[stage], kb * GEMM_BK, mb * GEMM_BM);
-          tc::tma_load_2d(sB + stage * B_BYTES, &tmap_w, &full[stage], kb * GEMM_BK, nb * BN);
+          if (CG == 2) {
+            // both CTAs load their half; the bytes of both are counted on the leader's full barrier
+            if (rank == 0) tc::mbar_arrive_expect_tx(&full[stage], 2 * (A_BYTES + B_BYTES));
+            tc::tma_load_2d_2sm(sA + stage * A_BYTES, &tmap_a, &full[stage], kb * GEMM_BK, mb * GEMM_BM);
+            tc::tma_load_2d_2sm(sB + stage * B_BYTES, &tmap_w, &full[stage], kb * GEMM_BK, nb * BN + rank * (BN / 2));
+          } else {
+            tc::mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
+            tc::tma_load_2d(sA + stage * A_BYTES, &tmap_a, &full[stage], kb * GEMM_BK, mb * GEMM_BM);
+            tc::tma_load_2d(sB + stage * B_BYTES, &tmap_w, &full[stage], kb * GEMM_BK, nb * BN);
+          }
           if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread)
-    if (lane == 0) {
-      const uint32_t idesc = tc::idesc_bf16(GEMM_BM, BN, false, false, e.fp16 != 0);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = tc::idesc_bf16(GEMM_BM * CG, BN, false, false, e.fp16 != 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int t = tile0; t < n_tiles; t += tile_stride) {
         tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc::tc_fence_after();
         uint32_t d_tmem = tmem_base + acc * BN;
@@ -146,13 +179,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
           tc::tc_fence_after();
           uint32_t a0 = tc::smem_u32(sA + stage * A_BYTES), b0 = tc::smem_u32(sB + stage * B_BYTES);
           int ksteps = min(GEMM_BK / 16, (p.K - kb * GEMM_BK + 15) / 16);
-          for (int k = 0; k < ksteps; k++)
-            tc::mma_f16_ss(d_tmem, tc::desc_kmajor(a0 + k * 32), tc::desc_kmajor(b0 + k * 32), idesc,
-                           (kb > 0 || k > 0) ? 1u : 0u);
-          tc::mma_commit(&empty[stage]);
+          for (int k = 0; k < ksteps; k++) {
+            if (CG == 2)
+              tc::mma_f16_ss2(d_tmem, tc::desc_kmajor(a0 + k * 32), tc::desc_kmajor(b0 + k * 32), idesc,
+                              (kb > 0 || k > 0) ? 1u : 0u);
+            else
+              tc::mma_f16_ss(d_tmem, tc::desc_kmajor(a0 + k * 32), tc::desc_kmajor(b0 + k * 32), idesc,
+                             (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          if (CG == 2) tc::mma_commit2(&empty[stage]);
+          else tc::mma_commit(&empty[stage]);
           if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
         }
-        tc::mma_commit(&tfull[acc]);
+        if (CG == 2) tc::mma_commit2(&tfull[acc]);
+        else tc::mma_commit(&tfull[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -167,13 +207,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
     const int ew = warp - 4;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access (= warp id mod 4)
     const int cgroup = ew >> 2;
-    uint8_t* bufs = epi + ew * 2 * GEMM_EPI_BUF;
+    uint8_t* bufs = epi + ew * EPI_BUFS * GEMM_EPI_BUF;
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t nbuf = 0;
     const int sub_row = lane >> 3, sub_c = lane & 7;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      int mb = t / p.n_tiles_n, nb = t - mb * p.n_tiles_n;
+    for (int t = tile0; t < n_tiles; t += tile_stride) {
+      int tm = t / p.n_tiles_n, nb = t - tm * p.n_tiles_n;
+      const int mb = tm * CG + rank;
       const long long row0 = (long long)mb * GEMM_BM + quad * 32;
       const long long myrow = row0 + lane;
       long long dest[8];
@@ -189,7 +230,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
 #pragma unroll 1
       for (int c = cgroup; c < BN / 32; c += 2) {
         const int col0 = nb * BN + c * 32;
-        uint8_t* buf = bufs + (nbuf & 1) * GEMM_EPI_BUF;
+        uint8_t* buf = bufs + (nbuf % EPI_BUFS) * GEMM_EPI_BUF;
         nbuf++;
         // residual for the TMA path: this thread's own row, 32 consecutive floats (issued before the TMEM wait)
         float4 rv[8];
@@ -240,7 +281,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
           for (int j = 0; j < 8; j++) bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (TMA_OUT) {
-          if (lane == 0) tc::tma_store_wait_read<1>();  // the store that last read `buf` has drained it
+          if (lane == 0) tc::tma_store_wait_read<EPI_BUFS - 1>();  // the store that last read `buf` has drained it
           __syncwarp();
         }
         tc::tmem_ld_wait();
@@ -318,25 +359,31 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
       // all TMEM reads of this accumulator stage are complete (tmem_ld_wait above): hand it back to the MMA warp
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (CG == 2) tc::mbar_arrive_leader(&tempty[acc]);
+        else tc::mbar_arrive(&tempty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (TMA_OUT && lane == 0) tc::tma_store_wait<0>();  // global writes complete before the CTA retires
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (CG == 2) tc::cluster_sync();  // no CTA of the pair retires while the other may still signal it
   if (warp == 2) {
     tc::tc_fence_after();
-    tc::tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (CG == 2) tc::tmem_dealloc2<TMEM_COLS>(tmem_base);
+    else tc::tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
-template <int BN, int ACT, int RES, int OUT, int MAP, int RBA>
+template <int BN, int ACT, int RES, int OUT, int MAP, int RBA, int CG = 1>
 static int launch_cfg(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M, int N, int K,
                       const GemmEpilogue& epi, int num_sms, cudaStream_t st) {
   static bool attr_set = false;
-  constexpr int smem = gemm_smem_bytes<BN>();
-  auto kern = k_gemm_tc<BN, ACT, RES, OUT, MAP, RBA>;
+  constexpr int smem = gemm_smem_bytes<BN, CG>();
+  static_assert(smem <= GEMM_SMEM_MAX, "shared memory budget");
+  auto kern = k_gemm_tc<BN, ACT, RES, OUT, MAP, RBA, CG>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cvb_fail_cuda(e, "cudaFuncSetAttribute(k_gemm_tc)");
@@ -344,7 +391,7 @@ static int launch_cfg(const __nv_bfloat16* A, long long lda, const __nv_bfloat16
   }
   CUtensorMap ta, tw, to;
   if (!tc_host::make_tmap_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM) ||
-      !tc_host::make_tmap_bf16(&tw, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, BN))
+      !tc_host::make_tmap_bf16(&tw, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, BN / CG))
     return cvb_fail(CV_ERR_CUDA, "cuTensorMapEncodeTiled failed (GEMM operands)");
   constexpr bool TMA_OUT = (MAP == GEMM_MAP_IDENTITY) && (OUT == 0 || OUT == 1);
   if (TMA_OUT) {
@@ -360,14 +407,36 @@ static int launch_cfg(const __nv_bfloat16* A, long long lda, const __nv_bfloat16
   p.M = M; p.N = N; p.K = K;
   p.n_tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
   p.n_tiles_n = (N + BN - 1) / BN;
-  long long tiles = (long long)p.n_tiles_m * p.n_tiles_n;
-  int grid = (int)(tiles < num_sms ? tiles : num_sms);
+  long long tiles = (long long)((p.n_tiles_m + CG - 1) / CG) * p.n_tiles_n;
+  const int max_groups = num_sms / CG;
+  int grid = (int)(tiles < max_groups ? tiles : max_groups) * CG;
   cvb_next_work(2.0 * (double)M * (double)N * (double)K);
   if (cvb_profile_on()) {
     char nm[96];
-    snprintf(nm, sizeof(nm), "gemm M%d N%d K%d bn%d%s%s%s%s", M, N, K, BN, epi.out_bf16 ? " ->bf16" : "", epi.out_f32 ? " ->f32" : "",
-             epi.res ? " +res" : "", ACT < 0 ? " generic" : "");
+    snprintf(nm, sizeof(nm), "gemm M%d N%d K%d bn%d%s%s%s%s%s", M, N, K, BN, epi.out_bf16 ? " ->bf16" : "", epi.out_f32 ? " ->f32" : "",
+             epi.res ? " +res" : "", ACT < 0 ? " generic" : "", CG == 2 ? " 2cta" : "");
     cvb_next_name(nm);
+  }
+  if (CG == 2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    bool prof = cvb_profile_on();
+    if (prof) cvb_profile_begin("k_gemm_tc", st, cvb_take_work());
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tw, to, p, epi);
+    if (prof) cvb_profile_end(st);
+    if (le != cudaSuccess) return cvb_fail_cuda(le, "launch k_gemm_tc (CTA pair)");
+    cvb_count_launch();
+    return CV_OK;
   }
   CVB_LAUNCH(kern, dim3(grid), dim3(GEMM_THREADS), smem, st, ta, tw, to, p, epi);
   return CV_OK;
@@ -382,6 +451,14 @@ static int launch_bn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16*
   const bool tma_ok = f32 ? (((uintptr_t)e.out_f32 & 15) == 0 && (e.ld_f32 % 4) == 0)
                           : (((uintptr_t)e.out_bf16 & 15) == 0 && (e.ld_bf16 % 8) == 0);
   if (e.map_mode == GEMM_MAP_IDENTITY && tma_ok && !(f32 && b16)) {
+    // CTA pairs for the K >= 256 shapes that are bound by operand delivery, not by HBM
+    static const bool pairs_on = getenv("CVB_GEMM_PAIRS") ? atoi(getenv("CVB_GEMM_PAIRS")) != 0 : true;
+    if (pairs_on && BN == 256 && K >= 256 && M >= 1024) {  // measured: BN = 192 pairs are no faster than single CTAs
+      if (b16 && !res && e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 0, 1, 0, 0, 2>(CVB_GEMM_ARGS);
+      if (b16 && !res && e.act == GEMM_ACT_GELU) return launch_cfg<BN, 1, 0, 1, 0, 0, 2>(CVB_GEMM_ARGS);
+      if (f32 && res && e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 1, 0, 0, 0, 2>(CVB_GEMM_ARGS);
+      if (f32 && !res && e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 0, 0, 0, 0, 2>(CVB_GEMM_ARGS);
+    }
     if (b16 && !res && e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 0, 1, 0, 0>(CVB_GEMM_ARGS);  // qkv
     if (b16 && !res && e.act == GEMM_ACT_GELU) return launch_cfg<BN, 1, 0, 1, 0, 0>(CVB_GEMM_ARGS);  // mlp fc1
     if (f32 && res && e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 1, 0, 0, 0>(CVB_GEMM_ARGS);   // fc2, global proj, tables
@@ -406,6 +483,7 @@ int gemm_tc_launch(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W
   if (epi.map_mode == GEMM_MAP_SHUFFLE2 && (epi.cout % 32)) return cvb_fail(CV_ERR_INVALID, "gemm: shuffle needs cout%32==0");
   if (epi.bias && ((uintptr_t)epi.bias & 15)) return cvb_fail(CV_ERR_INVALID, "gemm: bias must be 16-byte aligned");
   if (epi.res && (((uintptr_t)epi.res & 15) || (epi.ld_res % 4))) return cvb_fail(CV_ERR_INVALID, "gemm: residual alignment");
+  if (N % 256 == 0 && K >= 256 && M >= 1024) return launch_bn<256>(A, lda, W, ldw, M, N, K, epi, num_sms, st);
   if (N % 192 == 0) return launch_bn<192>(A, lda, W, ldw, M, N, K, epi, num_sms, st);
   if (N % 128 == 0) return launch_bn<128>(A, lda, W, ldw, M, N, K, epi, num_sms, st);
   if (N % 96 == 0) return launch_bn<96>(A, lda, W, ldw, M, N, K, epi, num_sms, st);

@@ -477,30 +477,55 @@ int launch_add_nearest2(float* Y, const float* L, int B, int H, int W, int C, cu
 }
 
 // ------------------------------------------------------------------------------------------------ token-side linear (fp32)
-// 64 x 64 output tile per CTA, 16 x 16 threads, 4 x 4 micro-tile, K tiles of 16.
+// C[R,N] = act(A[R,K] * W[N,K]^T + bias) (+ res).  64 x 64 output tile per CTA, 16 x 16 threads, 4 x 4 micro-tile, K
+// tiles of 32 double-buffered with cp.async: the K loop of these small GEMMs (R = 38 tokens per image) is
+// latency-bound, so the next tile's global loads are in flight while the current one is multiplied.
+constexpr int TL_BK = 32, TL_LD = 64 + 4;
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, bool ok) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  int sz = ok ? 4 : 0;  // src-size 0 -> zero fill
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
 __global__ void __launch_bounds__(256) k_tok_linear(const float* __restrict__ A, long long lda, const float* __restrict__ Wt,
                                                     const float* __restrict__ bias, int R, int N, int K, int act,
                                                     const float* __restrict__ res, long long ld_res, float* __restrict__ Cm,
                                                     long long ldc) {
-  __shared__ float sA[16][64 + 1];
-  __shared__ float sW[16][64 + 1];
-  int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  int r0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  __shared__ __align__(16) float sA[2][TL_BK][TL_LD];
+  __shared__ __align__(16) float sW[2][TL_BK][TL_LD];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int r0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int n_kt = (K + TL_BK - 1) / TL_BK;
+  auto stage = [&](int kt, int buf) {
+    const int k0 = kt * TL_BK;
+    // 64 rows x 32 k per operand; consecutive threads take consecutive k of one row (coalesced 128-byte rows)
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int e = threadIdx.x + i * 256;
+      const int rr = e >> 5, kk = e & 31;
+      const int gk = k0 + kk;
+      const int gr = r0 + rr, gn = n0 + rr;
+      const bool oka = gr < R && gk < K, okw = gn < N && gk < K;
+      cp_async4(&sA[buf][kk][rr], A + (oka ? (long long)gr * lda + gk : 0), oka);
+      cp_async4(&sW[buf][kk][rr], Wt + (okw ? (long long)gn * K + gk : 0), okw);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
-      int rr = i >> 4, kk = i & 15;
-      int gr = r0 + rr, gk = k0 + kk;
-      sA[kk][rr] = (gr < R && gk < K) ? A[(long long)gr * lda + gk] : 0.f;
-      int gn = n0 + rr;
-      sW[kk][rr] = (gn < N && gk < K) ? Wt[(long long)gn * K + gk] : 0.f;
+  stage(0, 0);
+  for (int kt = 0; kt < n_kt; kt++) {
+    const int buf = kt & 1;
+    if (kt + 1 < n_kt) {
+      stage(kt + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < 16; kk++) {
-      float a[4], w[4];
-#pragma unroll
-      for (int i = 0; i < 4; i++) { a[i] = sA[kk][ty * 4 + i]; w[i] = sW[kk][tx * 4 + i]; }
+    for (int kk = 0; kk < TL_BK; kk++) {
+      const float4 a4 = *(const float4*)&sA[buf][kk][ty * 4];
+      const float4 w4 = *(const float4*)&sW[buf][kk][tx * 4];
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
       for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -622,82 +647,84 @@ int launch_tok_self_attn(const float* q, const float* k, const float* v, int B, 
   return CV_OK;
 }
 
-// tokens -> image attention, d == 16.  CTA = (key split, head, image): stages its 256 keys/values in shared memory;
-// each warp walks a subset of the T queries and emits a partial (max, sum, O[16]) per (query, split).
-constexpr int T2I_SPLIT_KEYS = 256;
-constexpr int T2I_LD = 20;  // padded row (floats): conflict-free float4 reads
-__global__ void __launch_bounds__(128) k_attn_t2i_part(const float* __restrict__ q, long long q_img_stride,
-                                                       const float* __restrict__ K, const float* __restrict__ V,
-                                                       long long ld_kv, int T, int Nk, int heads, float* __restrict__ part) {
-  __shared__ float sk[T2I_SPLIT_KEYS * T2I_LD];
-  __shared__ float sv[T2I_SPLIT_KEYS * T2I_LD];
+// tokens -> image attention, d == 16.  CTA = (key split, head, image): stages its 128 keys/values of one head in shared
+// memory; thread = one decoder token (query) running an online softmax over the split's keys.  Every lane reads the
+// same K/V address (broadcast LDS.128, no bank conflicts) and keeps its (max, sum, O[16]) in registers, so there are no
+// cross-lane reductions at all; the partials per (query, split) are merged by k_attn_t2i_combine.
+constexpr int T2I_SPLIT_KEYS = 128;  // 16 KB of shared memory per CTA -> 14 CTAs per SM
+__global__ void __launch_bounds__(64) k_attn_t2i_part(const float* __restrict__ q, long long q_img_stride,
+                                                      const float* __restrict__ K, const float* __restrict__ V,
+                                                      long long ld_kv, int T, int Nk, int heads, float* __restrict__ part) {
+  __shared__ __align__(16) float sk[T2I_SPLIT_KEYS * 16];
+  __shared__ __align__(16) float sv[T2I_SPLIT_KEYS * 16];
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int nsplit = gridDim.x;
   const int k0 = split * T2I_SPLIT_KEYS;
   const int nk = min(T2I_SPLIT_KEYS, Nk - k0);
-  for (int i = threadIdx.x; i < nk * 4; i += 128) {
+  for (int i = threadIdx.x; i < nk * 4; i += 64) {
     int j = i >> 2, c = (i & 3) * 4;
     long long row = (long long)b * Nk + k0 + j;
-    *(float4*)(sk + j * T2I_LD + c) = *(const float4*)(K + row * ld_kv + h * 16 + c);
-    *(float4*)(sv + j * T2I_LD + c) = *(const float4*)(V + row * ld_kv + h * 16 + c);
+    *(float4*)(sk + j * 16 + c) = *(const float4*)(K + row * ld_kv + h * 16 + c);
+    *(float4*)(sv + j * 16 + c) = *(const float4*)(V + row * ld_kv + h * 16 + c);
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = threadIdx.x;
+  if (t >= T) return;
   const int C = heads * 16;
-  for (int t = warp; t < T; t += 4) {
-    const float* qp = q + (long long)b * q_img_stride + (long long)t * C + h * 16;
-    float qv[16];
+  const float* qp = q + (long long)b * q_img_stride + (long long)t * C + h * 16;
+  float qv[16];
 #pragma unroll
-    for (int i = 0; i < 16; i++) qv[i] = __ldg(qp + i) * 0.25f;  // 1/sqrt(16)
-    float sc[T2I_SPLIT_KEYS / 32];
-    float mx = -INFINITY;
+  for (int i = 0; i < 16; i++) qv[i] = __ldg(qp + i) * 0.36067376f;  // 1/sqrt(16) * log2(e)
+  float m = -INFINITY, l = 0.f, o[16];
 #pragma unroll
-    for (int u = 0; u < T2I_SPLIT_KEYS / 32; u++) {
-      int j = lane + u * 32;
-      float s = -INFINITY;
-      if (j < nk) {
-        s = 0.f;
-        const float4* kr = (const float4*)(sk + j * T2I_LD);
+  for (int i = 0; i < 16; i++) o[i] = 0.f;
+  for (int j0 = 0; j0 < nk; j0 += 8) {
+    // 8 keys per step: one rescale per step instead of per key
+    float sc[8], mx = m;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      float sdot = -INFINITY;
+      if (j0 + u < nk) {
+        const float4* kr = (const float4*)(sk + (j0 + u) * 16);
+        sdot = 0.f;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
           float4 kk = kr[c];
-          s = fmaf(qv[c * 4], kk.x, s); s = fmaf(qv[c * 4 + 1], kk.y, s);
-          s = fmaf(qv[c * 4 + 2], kk.z, s); s = fmaf(qv[c * 4 + 3], kk.w, s);
+          sdot = fmaf(qv[c * 4], kk.x, sdot); sdot = fmaf(qv[c * 4 + 1], kk.y, sdot);
+          sdot = fmaf(qv[c * 4 + 2], kk.z, sdot); sdot = fmaf(qv[c * 4 + 3], kk.w, sdot);
         }
       }
-      sc[u] = s;
-      mx = fmaxf(mx, s);
+      sc[u] = sdot;
+      mx = fmaxf(mx, sdot);
     }
-    mx = warp_max(mx);
-    float l = 0.f, o[16];
+    float alpha;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(alpha) : "f"(m - mx));  // m = -inf -> 0
+    l *= alpha;
 #pragma unroll
-    for (int i = 0; i < 16; i++) o[i] = 0.f;
+    for (int i = 0; i < 16; i++) o[i] *= alpha;
+    m = mx;
 #pragma unroll
-    for (int u = 0; u < T2I_SPLIT_KEYS / 32; u++) {
-      int j = lane + u * 32;
-      if (j < nk) {
-        float pexp = expf(sc[u] - mx);
-        l += pexp;
-        const float4* vr = (const float4*)(sv + j * T2I_LD);
+    for (int u = 0; u < 8; u++) {
+      float pe;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe) : "f"(sc[u] - mx));  // masked keys: ex2(-inf) = 0
+      l += pe;
+      if (j0 + u < nk) {
+        const float4* vr = (const float4*)(sv + (j0 + u) * 16);
 #pragma unroll
         for (int c = 0; c < 4; c++) {
           float4 vv = vr[c];
-          o[c * 4] = fmaf(pexp, vv.x, o[c * 4]); o[c * 4 + 1] = fmaf(pexp, vv.y, o[c * 4 + 1]);
-          o[c * 4 + 2] = fmaf(pexp, vv.z, o[c * 4 + 2]); o[c * 4 + 3] = fmaf(pexp, vv.w, o[c * 4 + 3]);
+          o[c * 4] = fmaf(pe, vv.x, o[c * 4]); o[c * 4 + 1] = fmaf(pe, vv.y, o[c * 4 + 1]);
+          o[c * 4 + 2] = fmaf(pe, vv.z, o[c * 4 + 2]); o[c * 4 + 3] = fmaf(pe, vv.w, o[c * 4 + 3]);
         }
       }
     }
-    l = warp_sum(l);
-#pragma unroll
-    for (int i = 0; i < 16; i++) o[i] = warp_sum(o[i]);
-    if (lane == 0) {
-      float* p = part + ((((long long)b * heads + h) * T + t) * nsplit + split) * 18;
-      p[0] = mx;
-      p[1] = l;
-#pragma unroll
-      for (int i = 0; i < 16; i++) p[2 + i] = o[i];
-    }
   }
+  // partial in natural-log convention of the combine kernel: stored max is in log2 units -> convert
+  float* pp = part + ((((long long)b * heads + h) * T + t) * nsplit + split) * 18;
+  pp[0] = m * 0.69314718056f;
+  pp[1] = l;
+#pragma unroll
+  for (int i = 0; i < 16; i++) pp[2 + i] = o[i];
 }
 
 __global__ void k_attn_t2i_combine(const float* __restrict__ part, int T, int heads, int nsplit, long long total,
@@ -723,16 +750,17 @@ __global__ void k_attn_t2i_combine(const float* __restrict__ part, int T, int he
 
 size_t attn_t2i_scratch_floats(int B, int T, int heads, int d) {
   (void)d;
-  return (size_t)B * heads * T * 16 * 18 + 64;
+  return (size_t)B * heads * T * 32 * 18 + 64;
 }
 
 int launch_attn_t2i(const float* q, long long q_img_stride, const float* K, const float* V, long long ld_kv, int B, int T,
                     int Nk, int heads, int d, float* out, float* scratch, cudaStream_t st) {
   if (d != 16) return cvb_fail(CV_ERR_INVALID, "attn_t2i: head dim must be 16");
   int nsplit = (Nk + T2I_SPLIT_KEYS - 1) / T2I_SPLIT_KEYS;
-  if (nsplit > 16) return cvb_fail(CV_ERR_INVALID, "attn_t2i: at most 4096 keys");
+  if (nsplit > 32) return cvb_fail(CV_ERR_INVALID, "attn_t2i: at most 4096 keys");
   cvb_next_work(4.0 * B * (double)T * Nk * heads * d);
-  CVB_LAUNCH(k_attn_t2i_part, dim3(nsplit, heads, B), dim3(128), 0, st, q, q_img_stride, K, V, ld_kv, T, Nk, heads, scratch);
+  if (T > 64) return cvb_fail(CV_ERR_INVALID, "attn_t2i: at most 64 query tokens");
+  CVB_LAUNCH(k_attn_t2i_part, dim3(nsplit, heads, B), dim3(64), 0, st, q, q_img_stride, K, V, ld_kv, T, Nk, heads, scratch);
   long long total = (long long)B * heads * T * 16;
   CVB_LAUNCH(k_attn_t2i_combine, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, scratch, T, heads, nsplit, total,
              out);
