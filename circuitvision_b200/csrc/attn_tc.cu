@@ -14,12 +14,12 @@
 
 namespace cvb {
 
-constexpr int ATT_D = 96;
 constexpr int ATT_BM = 128;
 constexpr int ATT_BN = 128;
-constexpr int ATT_THREADS = 256;
-constexpr int ATT_TILE_BYTES = 2 * ATT_BM * 128;  // two 64-column atoms of 128 rows x 128 B
-constexpr int ATT_SMEM = 1024 + ATT_TILE_BYTES * (1 /*Q*/ + 2 /*K*/ + 2 /*V*/ + 1 /*P*/) + 256;
+// head dim D = 64 or 96 (Hiera's 56 and 72 are zero-padded to these by the weight folding); a 128-row operand tile is
+// ceil(D / 64) swizzle atoms of 128 rows x 128 bytes
+template <int D>
+constexpr int att_tile_bytes() { return ((D + 63) / 64) * ATT_BM * 128; }
 
 struct AttnParams {
   int Mq, Mkv, Wq, Wkv, heads;
@@ -36,226 +36,6 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
-k_attn_tc(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
-          const __grid_constant__ CUtensorMap tv, AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + ATT_TILE_BYTES;      // [2]
-  uint8_t* sV = sK + 2 * ATT_TILE_BYTES;  // [2]
-  uint8_t* sP = sV + 2 * ATT_TILE_BYTES;
-  uint64_t* bars = (uint64_t*)(sP + ATT_TILE_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * ATT_BM;
-  const int head = blockIdx.y;
-  const int r_last = min(q0 + ATT_BM - 1, p.Mq - 1);
-  const int kv_start = (q0 / p.Wq) * p.Wkv;
-  const int kv_end = (r_last / p.Wq + 1) * p.Wkv;
-  const int n_tiles = (kv_end - kv_start + ATT_BN - 1) / ATT_BN;
-
-  if (warp == 0 && lane == 0) {
-    tc::prefetch_tmap(&tq);
-    tc::prefetch_tmap(&tk);
-    tc::prefetch_tmap(&tv);
-  }
-  if (warp == 1 && lane == 0) {
-    tc::mbar_init(q_full, 1);
-    for (int i = 0; i < 2; i++) {
-      tc::mbar_init(&kv_full[i], 1);
-      tc::mbar_init(&kv_empty[i], 1);
-    }
-    tc::mbar_init(s_full, 1);
-    tc::mbar_init(p_full, 4);  // one arrival per softmax warp
-    tc::mbar_init(o_full, 1);
-    tc::fence_barrier_init();
-  }
-  if (warp == 2) tc::tmem_alloc<256>(tmem_slot);
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      tc::mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
-      tc::tma_load_2d(sQ, &tq, q_full, p.qcol0 + head * ATT_D, q0);
-      tc::tma_load_2d(sQ + ATT_BM * 128, &tq, q_full, p.qcol0 + head * ATT_D + 64, q0);
-      for (int j = 0; j < n_tiles; j++) {
-        int s = j & 1;
-        tc::mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-        tc::mbar_arrive_expect_tx(&kv_full[s], 2 * ATT_TILE_BYTES);
-        int row = kv_start + j * ATT_BN;
-        uint8_t* k = sK + s * ATT_TILE_BYTES;
-        uint8_t* v = sV + s * ATT_TILE_BYTES;
-        tc::tma_load_2d(k, &tk, &kv_full[s], p.kcol0 + head * ATT_D, row);
-        tc::tma_load_2d(k + ATT_BN * 128, &tk, &kv_full[s], p.kcol0 + head * ATT_D + 64, row);
-        tc::tma_load_2d(v, &tv, &kv_full[s], p.vcol0 + head * ATT_D, row);
-        tc::tma_load_2d(v + ATT_BN * 128, &tv, &kv_full[s], p.vcol0 + head * ATT_D + 64, row);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_qk = tc::idesc_bf16(ATT_BM, ATT_BN, false, false, p.fp16 != 0);
-      const uint32_t idesc_pv = tc::idesc_bf16(ATT_BM, ATT_D, false, true, p.fp16 != 0);  // B = V, MN-major
-      const uint32_t q_addr = tc::smem_u32(sQ), p_addr = tc::smem_u32(sP);
-      auto issue_qk = [&](int j) {
-        uint32_t k_addr = tc::smem_u32(sK + (j & 1) * ATT_TILE_BYTES);
-#pragma unroll
-        for (int k = 0; k < ATT_D / 16; k++) {
-          uint32_t off = (k >> 2) * (ATT_BM * 128) + (k & 3) * 32;
-          tc::mma_f16_ss(tmem_S, tc::desc_kmajor(q_addr + off), tc::desc_kmajor(k_addr + off), idesc_qk, k > 0 ? 1u : 0u);
-        }
-        tc::mma_commit(s_full);
-      };
-      tc::mbar_wait(q_full, 0);
-      tc::mbar_wait(&kv_full[0], 0);
-      tc::tc_fence_after();
-      issue_qk(0);
-      for (int j = 0; j < n_tiles; j++) {
-        tc::mbar_wait(p_full, j & 1);
-        tc::tc_fence_after();
-        uint32_t v_addr = tc::smem_u32(sV + (j & 1) * ATT_TILE_BYTES);
-#pragma unroll
-        for (int k = 0; k < ATT_BN / 16; k++) {
-          // A = P: K-major, 64 keys per atom.  B = V: MN-major, 16 key rows (2048 B) per k-step,
-          // LBO = distance between the two 64-wide d atoms, SBO = 8 key rows.
-          uint64_t a = tc::desc_kmajor(p_addr + (k >> 2) * (ATT_BM * 128) + (k & 3) * 32);
-          uint64_t b = tc::smem_desc_sw128(v_addr + k * 2048, ATT_BN * 128, 1024);
-          tc::mma_f16_ss(tmem_O, a, b, idesc_pv, k > 0 ? 1u : 0u);
-        }
-        tc::mma_commit(o_full);
-        tc::mma_commit(&kv_empty[j & 1]);
-        if (j + 1 < n_tiles) {
-          tc::mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-          tc::tc_fence_after();
-          issue_qk(j + 1);
-        }
-      }
-    }
-  } else if (warp >= 4) {
-    const int quad = warp & 3;
-    const int r = quad * 32 + lane;  // row inside the tile == TMEM lane
-    const int grow = q0 + r;
-    const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
-    // keys visible to this row: [w*Wkv, (w+1)*Wkv)
-    const long long wq = (long long)(grow / p.Wq);
-    const int vis_lo = (int)(wq * p.Wkv) - kv_start;
-    const int vis_hi = vis_lo + p.Wkv;
-    float m = -INFINITY, l = 0.f, alpha_pending = 0.f;
-    float O[ATT_D];
-#pragma unroll
-    for (int i = 0; i < ATT_D; i++) O[i] = 0.f;
-    uint8_t* prow = sP + r * 128;
-    auto fold_o = [&](float alpha) {
-#pragma unroll
-      for (int c = 0; c < ATT_D / 32; c++) {
-        uint32_t v[32];
-        tc::tmem_ld_32x32(tmem_O + lane_sel + c * 32, v);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i++) O[c * 32 + i] = O[c * 32 + i] * alpha + __uint_as_float(v[i]);
-      }
-    };
-    for (int j = 0; j < n_tiles; j++) {
-      const int c_lo = vis_lo - j * ATT_BN, c_hi = vis_hi - j * ATT_BN;  // visible columns of this tile
-      const bool full = (c_lo <= 0) && (c_hi >= ATT_BN);
-      tc::mbar_wait(s_full, j & 1);
-      tc::tc_fence_after();
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < ATT_BN / 32; c++) {
-        uint32_t v[32];
-        tc::tmem_ld_32x32(tmem_S + lane_sel + c * 32, v);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i++) {
-          int col = c * 32 + i;
-          float x = __uint_as_float(v[i]) * p.scale_log2;
-          if (!full && (col < c_lo || col >= c_hi)) x = -INFINITY;
-          mx = fmaxf(mx, x);
-        }
-      }
-      const float m_new = fmaxf(m, mx);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = ex2(m - m_use);  // m = -inf -> 0
-      if (j > 0) {
-        tc::mbar_wait(o_full, (j - 1) & 1);  // PV(j-1) finished: O tile valid, P buffer free
-        tc::tc_fence_after();
-        fold_o(alpha_pending);
-      }
-      float rowsum = 0.f;
-#pragma unroll
-      for (int c = 0; c < ATT_BN / 32; c++) {
-        uint32_t v[32];
-        tc::tmem_ld_32x32(tmem_S + lane_sel + c * 32, v);
-        tc::tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          int col = c * 32 + i;
-          float x0 = __uint_as_float(v[i]) * p.scale_log2 - m_use;
-          float x1 = __uint_as_float(v[i + 1]) * p.scale_log2 - m_use;
-          float p0 = ex2(x0), p1 = ex2(x1);
-          if (!full) {
-            if (col < c_lo || col >= c_hi) p0 = 0.f;
-            if (col + 1 < c_lo || col + 1 >= c_hi) p1 = 0.f;
-          }
-          rowsum += p0 + p1;
-          pk[i >> 1] = tc::pack16(p.fp16, p0, p1);
-        }
-        // 32 columns = 4 chunks of 16 bytes; K-major SW128: atom = col/64, chunk' = chunk ^ (row % 8)
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          int col = c * 32 + q * 8;
-          int atom = col >> 6, chunk = (col & 63) >> 3;
-          uint8_t* dst = prow + atom * (ATT_BM * 128) + ((chunk ^ (r & 7)) << 4);
-          *(uint4*)dst = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-        }
-      }
-      l = l * alpha + rowsum;
-      m = m_new;
-      alpha_pending = alpha;
-      tc::fence_proxy_async_smem();
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(p_full);
-    }
-    tc::mbar_wait(o_full, (n_tiles - 1) & 1);
-    tc::tc_fence_after();
-    fold_o(alpha_pending);
-    if (grow < p.Mq) {
-      const float inv = 1.f / l;
-      __nv_bfloat16* o = p.out + (long long)grow * p.ld_out + head * ATT_D;
-#pragma unroll
-      for (int i = 0; i < ATT_D; i += 8) {
-        uint32_t w[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          w[k] = tc::pack16(p.fp16, O[i + 2 * k] * inv, O[i + 2 * k + 1] * inv);
-        }
-        *(uint4*)(o + i) = make_uint4(w[0], w[1], w[2], w[3]);
-      }
-    }
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc::tc_fence_after();
-    tc::tmem_dealloc<256>(tmem_base);
-  }
-}
-
-
 // ------------------------------------------------------------------------------------------------ global attention
 // Wq == Wkv (one window = all tokens of an image), Wkv % 128 == 0, Wq % 256 == 0: the three global blocks of stage 3
 // (4096 x 4096 per head) — 85 of the trunk's 86 attention GFLOP per image.
@@ -269,11 +49,14 @@ k_attn_tc(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtens
 // rescaled (tcgen05.ld -> mul -> tcgen05.st) only when a tile's maximum exceeds it by more than 2^8 — rare after the
 // first tile, and exact either way because the same reference scales numerator and denominator.
 constexpr int AG_THREADS = 384;
-constexpr int AG_SMEM = 1024 + ATT_TILE_BYTES * (2 /*Q0,Q1*/ + 2 /*K*/ + 2 /*V*/) + 256;
+template <int D>
+constexpr int ag_smem() { return 1024 + att_tile_bytes<D>() * (2 /*Q0,Q1*/ + 2 /*K*/ + 2 /*V*/) + 256; }
 
+template <int D>
 __global__ void __launch_bounds__(AG_THREADS, 1)
 k_attn_global(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
               const __grid_constant__ CUtensorMap tv, AttnParams p) {
+  constexpr int ATT_D = D, ATT_TILE_BYTES = att_tile_bytes<D>();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;                      // [2]
@@ -325,7 +108,7 @@ k_attn_global(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
       tc::mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
       for (int g = 0; g < 2; g++) {
         tc::tma_load_2d(sQ + g * ATT_TILE_BYTES, &tq, q_full, p.qcol0 + head * ATT_D, q0 + g * ATT_BM);
-        tc::tma_load_2d(sQ + g * ATT_TILE_BYTES + ATT_BM * 128, &tq, q_full, p.qcol0 + head * ATT_D + 64, q0 + g * ATT_BM);
+        if (D > 64) tc::tma_load_2d(sQ + g * ATT_TILE_BYTES + ATT_BM * 128, &tq, q_full, p.qcol0 + head * ATT_D + 64, q0 + g * ATT_BM);
       }
       for (int j = 0; j < n_tiles; j++) {
         const int s = j & 1;
@@ -335,12 +118,12 @@ k_attn_global(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
         tc::mbar_arrive_expect_tx(&k_full[s], ATT_TILE_BYTES);
         uint8_t* k = sK + s * ATT_TILE_BYTES;
         tc::tma_load_2d(k, &tk, &k_full[s], p.kcol0 + head * ATT_D, row);
-        tc::tma_load_2d(k + ATT_BN * 128, &tk, &k_full[s], p.kcol0 + head * ATT_D + 64, row);
+        if (D > 64) tc::tma_load_2d(k + ATT_BN * 128, &tk, &k_full[s], p.kcol0 + head * ATT_D + 64, row);
         tc::mbar_wait(&v_empty[s], par);
         tc::mbar_arrive_expect_tx(&v_full[s], ATT_TILE_BYTES);
         uint8_t* v = sV + s * ATT_TILE_BYTES;
         tc::tma_load_2d(v, &tv, &v_full[s], p.vcol0 + head * ATT_D, row);
-        tc::tma_load_2d(v + ATT_BN * 128, &tv, &v_full[s], p.vcol0 + head * ATT_D + 64, row);
+        if (D > 64) tc::tma_load_2d(v + ATT_BN * 128, &tv, &v_full[s], p.vcol0 + head * ATT_D + 64, row);
       }
     }
   } else if (warp == 1) {
@@ -513,7 +296,8 @@ k_attn_global(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
 // exceeds it by more than 2^8 (same exactness argument as the global kernel).
 constexpr int AW_THREADS = 384;
 constexpr int AW_RING = 4;
-constexpr int AW_SMEM = 1024 + ATT_TILE_BYTES * (2 + AW_RING) + 256;
+template <int D>
+constexpr int aw_smem() { return 1024 + att_tile_bytes<D>() * (2 + AW_RING) + 256; }
 
 struct WinItem {
   int q0, kv_lo, n_kt, head, valid;
@@ -531,9 +315,11 @@ __device__ __forceinline__ WinItem win_item(const AttnParams& p, int n_items, in
   return w;
 }
 
+template <int D>
 __global__ void __launch_bounds__(AW_THREADS, 1)
 k_attn_win(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
            const __grid_constant__ CUtensorMap tv, AttnParams p, int n_items) {
+  constexpr int ATT_D = D, ATT_TILE_BYTES = att_tile_bytes<D>();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;                       // [2]
@@ -588,7 +374,7 @@ k_attn_win(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUten
         tc::mbar_arrive_expect_tx(&r_full[ring], ATT_TILE_BYTES);
         uint8_t* dst = sR + ring * ATT_TILE_BYTES;
         tc::tma_load_2d(dst, tm, &r_full[ring], col, row);
-        tc::tma_load_2d(dst + ATT_BN * 128, tm, &r_full[ring], col + 64, row);
+        if (D > 64) tc::tma_load_2d(dst + ATT_BN * 128, tm, &r_full[ring], col + 64, row);
         ring = (ring + 1) % AW_RING;
         ring_uses++;
       };
@@ -600,7 +386,7 @@ k_attn_win(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUten
             tc::mbar_arrive_expect_tx(&q_full[g], ATT_TILE_BYTES);
             uint8_t* dst = sQ + g * ATT_TILE_BYTES;
             tc::tma_load_2d(dst, &tq, &q_full[g], p.qcol0 + it[g].head * ATT_D, it[g].q0);
-            tc::tma_load_2d(dst + ATT_BM * 128, &tq, &q_full[g], p.qcol0 + it[g].head * ATT_D + 64, it[g].q0);
+            if (D > 64) tc::tma_load_2d(dst + ATT_BM * 128, &tq, &q_full[g], p.qcol0 + it[g].head * ATT_D + 64, it[g].q0);
             q_uses[g]++;
           }
         for (int g = 0; g < 2; g++)
@@ -794,16 +580,39 @@ k_attn_win(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUten
 
 int device_sm_count();
 
-// q/k/v: bf16 matrices [Mq|Mkv, ld*] whose columns [col0 + h*96, col0 + (h+1)*96) hold head h.
+template <int D>
+static int attn_launch_d(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, bool glob,
+                         cudaStream_t st) {
+  if (glob) {
+    static bool attr_set_g = false;
+    if (!attr_set_g) {
+      cudaError_t e = cudaFuncSetAttribute(k_attn_global<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, ag_smem<D>());
+      if (e != cudaSuccess) return cvb_fail_cuda(e, "cudaFuncSetAttribute(k_attn_global)");
+      attr_set_g = true;
+    }
+    CVB_LAUNCH((k_attn_global<D>), dim3(p.Mq / (2 * ATT_BM), p.heads), dim3(AG_THREADS), ag_smem<D>(), st, tq, tk, tv, p);
+    return CV_OK;
+  }
+  static bool attr_set_w = false;
+  if (!attr_set_w) {
+    cudaError_t e = cudaFuncSetAttribute(k_attn_win<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, aw_smem<D>());
+    if (e != cudaSuccess) return cvb_fail_cuda(e, "cudaFuncSetAttribute(k_attn_win)");
+    attr_set_w = true;
+  }
+  const int n_items = ((p.Mq + ATT_BM - 1) / ATT_BM) * p.heads;
+  const int n_pairs = (n_items + 1) / 2;
+  const int grid = n_pairs < device_sm_count() ? n_pairs : device_sm_count();
+  CVB_LAUNCH((k_attn_win<D>), dim3(grid), dim3(AW_THREADS), aw_smem<D>(), st, tq, tk, tv, p, n_items);
+  return CV_OK;
+}
+
+// q/k/v: 16-bit matrices [Mq|Mkv, ld*] whose columns [col0 + h*D, col0 + (h+1)*D) hold head h; D = 64 or 96 is the
+// (zero-padded) head dim of the buffers, `scale` the softmax scale of the real head dim.
 int attn_tc_launch(const __nv_bfloat16* q, long long ldq, int qcols, int qcol0, const __nv_bfloat16* k, long long ldk,
                    int kcols, int kcol0, const __nv_bfloat16* v, long long ldv, int vcols, int vcol0, int Mq, int Mkv,
-                   int Wq, int Wkv, int heads, float scale, __nv_bfloat16* out, long long ld_out, int fp16, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_attn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
-    if (e != cudaSuccess) return cvb_fail_cuda(e, "cudaFuncSetAttribute(k_attn_tc)");
-    attr_set = true;
-  }
+                   int Wq, int Wkv, int heads, int D, float scale, __nv_bfloat16* out, long long ld_out, int fp16,
+                   cudaStream_t st) {
+  if (D != 64 && D != 96) return cvb_fail(CV_ERR_INVALID, "attention: padded head dim must be 64 or 96");
   if (Mq <= 0 || Mkv <= 0 || Wq <= 0 || Wkv <= 0 || heads <= 0) return cvb_fail(CV_ERR_INVALID, "attention: bad sizes");
   if ((long long)(Mq / Wq) * Wkv > Mkv || (Mq % Wq)) return cvb_fail(CV_ERR_INVALID, "attention: window counts of Q and K/V differ");
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ld_out % 8) || (qcol0 % 8) || (kcol0 % 8) || (vcol0 % 8))
@@ -819,37 +628,15 @@ int attn_tc_launch(const __nv_bfloat16* q, long long ldq, int qcols, int qcol0, 
   p.scale_log2 = scale * 1.4426950408889634f;
   p.fp16 = fp16;
   p.out = out; p.ld_out = ld_out;
-  // algorithmic flops: every query row against the keys of its own window, QK^T and PV
-  cvb_next_work(4.0 * (double)Mq * (double)Wkv * ATT_D * heads);
+  const bool glob = Wq == Wkv && (Wkv % ATT_BN) == 0 && (Wq % (2 * ATT_BM)) == 0 && (Mq % (2 * ATT_BM)) == 0;
+  // algorithmic flops: every query row against the keys of its own window, QK^T and PV (padded head dim as executed)
+  cvb_next_work(4.0 * (double)Mq * (double)Wkv * D * heads);
   if (cvb_profile_on()) {
     char nm[96];
-    const bool glob = Wq == Wkv && (Wkv % ATT_BN) == 0 && (Wq % (2 * ATT_BM)) == 0 && (Mq % (2 * ATT_BM)) == 0;
-    snprintf(nm, sizeof(nm), "%s Mq%d Wq%d Wkv%d h%d", glob ? "attn_global" : "attn", Mq, Wq, Wkv, heads);
+    snprintf(nm, sizeof(nm), "%s Mq%d Wq%d Wkv%d h%d d%d", glob ? "attn_global" : "attn", Mq, Wq, Wkv, heads, D);
     cvb_next_name(nm);
   }
-  if (Wq == Wkv && (Wkv % ATT_BN) == 0 && (Wq % (2 * ATT_BM)) == 0 && (Mq % (2 * ATT_BM)) == 0) {
-    static bool attr_set_g = false;
-    if (!attr_set_g) {
-      cudaError_t e = cudaFuncSetAttribute(k_attn_global, cudaFuncAttributeMaxDynamicSharedMemorySize, AG_SMEM);
-      if (e != cudaSuccess) return cvb_fail_cuda(e, "cudaFuncSetAttribute(k_attn_global)");
-      attr_set_g = true;
-    }
-    CVB_LAUNCH(k_attn_global, dim3(Mq / (2 * ATT_BM), heads), dim3(AG_THREADS), AG_SMEM, st, tq, tk, tv, p);
-    return CV_OK;
-  }
-  {
-    static bool attr_set_w = false;
-    if (!attr_set_w) {
-      cudaError_t e = cudaFuncSetAttribute(k_attn_win, cudaFuncAttributeMaxDynamicSharedMemorySize, AW_SMEM);
-      if (e != cudaSuccess) return cvb_fail_cuda(e, "cudaFuncSetAttribute(k_attn_win)");
-      attr_set_w = true;
-    }
-    const int n_items = ((Mq + ATT_BM - 1) / ATT_BM) * heads;
-    const int n_pairs = (n_items + 1) / 2;
-    const int grid = n_pairs < device_sm_count() ? n_pairs : device_sm_count();
-    CVB_LAUNCH(k_attn_win, dim3(grid), dim3(AW_THREADS), AW_SMEM, st, tq, tk, tv, p, n_items);
-  }
-  return CV_OK;
+  return D == 64 ? attn_launch_d<64>(tq, tk, tv, p, glob, st) : attn_launch_d<96>(tq, tk, tv, p, glob, st);
 }
 
 }  // namespace cvb
@@ -862,8 +649,8 @@ extern "C" int cv_attention_bf16(const void* qkv_q, long long ldq, int qcols, in
                                  void* out, long long ld_out, void* stream) {
   cvb_reset_launches();
   if (!qkv_q || !qkv_k || !qkv_v || !out) return cvb_fail(CV_ERR_INVALID, "cv_attention_bf16: null pointer");
-  if (head_dim != ATT_D) return cvb_fail(CV_ERR_INVALID, "cv_attention_bf16: only head_dim 96 (SAM 2.1 tiny/small) is built");
+  if (head_dim != 64 && head_dim != 96) return cvb_fail(CV_ERR_INVALID, "cv_attention_bf16: head_dim must be 64 or 96 (pad 56 / 72 with zeros)");
   return attn_tc_launch((const __nv_bfloat16*)qkv_q, ldq, qcols, qcol0, (const __nv_bfloat16*)qkv_k, ldk, kcols, kcol0,
-                        (const __nv_bfloat16*)qkv_v, ldv, vcols, vcol0, Mq, Mkv, Wq, Wkv, heads, scale,
+                        (const __nv_bfloat16*)qkv_v, ldv, vcols, vcol0, Mq, Mkv, Wq, Wkv, heads, head_dim, scale,
                         (__nv_bfloat16*)out, ld_out, 0, (cudaStream_t)stream);
 }

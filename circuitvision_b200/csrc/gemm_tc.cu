@@ -230,6 +230,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
 #pragma unroll 1
       for (int c = cgroup; c < BN / 32; c += 2) {
         const int col0 = nb * BN + c * 32;
+        const int ncols = p.N - col0;  // valid columns of this chunk: >= 32, 16 (N % 32 == 16) or <= 0
         uint8_t* buf = bufs + (nbuf % EPI_BUFS) * GEMM_EPI_BUF;
         nbuf++;
         // residual for the TMA path: this thread's own row, 32 consecutive floats (issued before the TMEM wait)
@@ -239,7 +240,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
             long long rr = e.res_row_mod > 0 ? myrow % e.res_row_mod : myrow;
             const float4* rp = (const float4*)(e.res + rr * e.ld_res + col0);
 #pragma unroll
-            for (int j = 0; j < 8; j++) rv[j] = rp[j];
+            for (int j = 0; j < 8; j++) rv[j] = 4 * j < ncols ? rp[j] : make_float4(0.f, 0.f, 0.f, 0.f);
           } else {
 #pragma unroll
             for (int j = 0; j < 8; j++) rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -266,7 +267,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
             }
             dfin[it] = d;
             rres[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_res && d >= 0 && col0 < p.N) {
+            if (has_res && d >= 0 && sub_c * 4 < ncols) {
               long long rr = e.res_row_mod > 0 ? d % e.res_row_mod : d;
               rres[it] = *(const float4*)(e.res + rr * e.ld_res + ocol0 + sub_c * 4);
             }
@@ -275,7 +276,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
         float4 bv[8];
         if (e.bias) {
 #pragma unroll
-          for (int j = 0; j < 8; j++) bv[j] = __ldg((const float4*)(e.bias + ocol0) + j);
+          for (int j = 0; j < 8; j++) bv[j] = 4 * j < ncols ? __ldg((const float4*)(e.bias + ocol0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
 #pragma unroll
           for (int j = 0; j < 8; j++) bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -338,7 +339,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
 #pragma unroll
             for (int it = 0; it < 8; it++) {
               const long long d = dfin[it];
-              if (d < 0) continue;
+              if (d < 0 || sub_c * 4 >= ncols) continue;
               const int r = it * 4 + sub_row;
               float4 x = *(const float4*)(buf + r * 128 + ((sub_c ^ (r & 7)) << 4));
               const int oc = ocol0 + sub_c * 4;
@@ -477,12 +478,20 @@ static int launch_bn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16*
 int gemm_tc_launch(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M, int N, int K,
                    const GemmEpilogue& epi, int num_sms, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return cvb_fail(CV_ERR_INVALID, "gemm: non-positive size");
-  if ((N % 32) || (K % 8) || (lda % 8) || (ldw % 8)) return cvb_fail(CV_ERR_INVALID, "gemm: N%32, K%8, lda%8, ldw%8 must be 0");
+  if ((N % 16) || (K % 8) || (lda % 8) || (ldw % 8)) return cvb_fail(CV_ERR_INVALID, "gemm: N%16, K%8, lda%8, ldw%8 must be 0");
   if (((uintptr_t)A | (uintptr_t)W) & 15) return cvb_fail(CV_ERR_INVALID, "gemm: operands must be 16-byte aligned");
   if (!epi.out_f32 && !epi.out_bf16) return cvb_fail(CV_ERR_INVALID, "gemm: no output");
   if (epi.map_mode == GEMM_MAP_SHUFFLE2 && (epi.cout % 32)) return cvb_fail(CV_ERR_INVALID, "gemm: shuffle needs cout%32==0");
   if (epi.bias && ((uintptr_t)epi.bias & 15)) return cvb_fail(CV_ERR_INVALID, "gemm: bias must be 16-byte aligned");
   if (epi.res && (((uintptr_t)epi.res & 15) || (epi.ld_res % 4))) return cvb_fail(CV_ERR_INVALID, "gemm: residual alignment");
+  if (N % 32) {
+    // N = 112 / 144 (Hiera base+ / large stage-1 width): one n-tile wider than N, the last chunk is half valid
+    if (epi.map_mode == GEMM_MAP_SHUFFLE2) return cvb_fail(CV_ERR_INVALID, "gemm: shuffle needs N%32==0");
+    if (N <= 128) return launch_bn<128>(A, lda, W, ldw, M, N, K, epi, num_sms, st);
+    if (N <= 192) return launch_bn<192>(A, lda, W, ldw, M, N, K, epi, num_sms, st);
+    if (N <= 256) return launch_bn<256>(A, lda, W, ldw, M, N, K, epi, num_sms, st);
+    return cvb_fail(CV_ERR_INVALID, "gemm: N % 32 == 16 is supported up to N = 256");
+  }
   if (N % 256 == 0 && K >= 256 && M >= 1024) return launch_bn<256>(A, lda, W, ldw, M, N, K, epi, num_sms, st);
   if (N % 192 == 0) return launch_bn<192>(A, lda, W, ldw, M, N, K, epi, num_sms, st);
   if (N % 128 == 0) return launch_bn<128>(A, lda, W, ldw, M, N, K, epi, num_sms, st);

@@ -20,7 +20,8 @@
 namespace cvb {
 int attn_tc_launch(const __nv_bfloat16* q, long long ldq, int qcols, int qcol0, const __nv_bfloat16* k, long long ldk,
                    int kcols, int kcol0, const __nv_bfloat16* v, long long ldv, int vcols, int vcol0, int Mq, int Mkv,
-                   int Wq, int Wkv, int heads, float scale, __nv_bfloat16* out, long long ld_out, int fp16, cudaStream_t st);
+                   int Wq, int Wkv, int heads, int D, float scale, __nv_bfloat16* out, long long ld_out, int fp16,
+                   cudaStream_t st);
 int device_sm_count();
 }  // namespace cvb
 
@@ -47,6 +48,8 @@ struct cv_sam2 {
   int stage_end[4];
   bool finalized = false;
   int f16 = 0;  // 16-bit operand format: 0 bf16, 1 IEEE half
+  int hd = 96;  // real head dim (embed_dim / num_heads: 96 tiny/small, 56 base+, 72 large)
+  int D = 96;   // head dim of the attention buffers: hd zero-padded to 64 or 96 by the weight folding
   int launches = 0;
   float refc_b = 0.f;
 };
@@ -79,9 +82,13 @@ static T* BUF(cv_sam2* h, const char* n) { return (T*)h->buf[n].p; }
 
 extern "C" int cv_sam2_create(const cv_sam2_cfg* cfg, int device, cv_sam2** out) {
   if (!cfg || !out) return cvb_fail(CV_ERR_INVALID, "cv_sam2_create: null");
-  if (cfg->embed_dim * 1 / cfg->num_heads != 96)
-    return cvb_fail(CV_ERR_INVALID, "cv_sam2_create: only head_dim 96 variants (SAM 2.1 tiny / small) are built so far");
+  if (cfg->num_heads <= 0 || cfg->embed_dim % cfg->num_heads || cfg->embed_dim % 16)
+    return cvb_fail(CV_ERR_INVALID, "cv_sam2_create: embed_dim must be a multiple of 16 and of num_heads");
+  const int hd = cfg->embed_dim / cfg->num_heads;
+  if (hd > 96 || hd % 8) return cvb_fail(CV_ERR_INVALID, "cv_sam2_create: head dim must be a multiple of 8 and <= 96");
   cv_sam2* h = new cv_sam2();
+  h->hd = hd;
+  h->D = hd <= 64 ? 64 : 96;
   h->cfg = *cfg;
   h->device = device;
   h->f16 = cfg->operand_fp16 ? 1 : 0;
@@ -188,12 +195,13 @@ extern "C" int cv_sam2_finalize(cv_sam2* h) {
     size_t M = window_rows(p, B);
     maxA = std::max(maxA, M * p.dim_in);
     maxA = std::max(maxA, (size_t)B * p.H * p.W * p.dim_out);  // LN2 output / casts
-    maxQKV = std::max(maxQKV, M * 3 * p.dim_out);
+    const size_t Cp = (size_t)p.heads * h->D;  // attention width with the padded head dim
+    maxQKV = std::max(maxQKV, M * 3 * Cp);
     size_t Mq = p.pool ? M / 4 : M;
-    maxAO = std::max(maxAO, Mq * p.dim_out);
+    maxAO = std::max(maxAO, Mq * Cp);
     size_t T = (size_t)B * (p.pool ? (p.H / 2) * (p.W / 2) : p.H * p.W);
     maxHd = std::max(maxHd, T * 4 * p.dim_out);
-    if (p.pool) { maxS = std::max(maxS, M * p.dim_out); maxQp = std::max(maxQp, Mq * p.dim_out); }
+    if (p.pool) { maxS = std::max(maxS, M * p.dim_out); maxQp = std::max(maxQp, Mq * Cp); }
   }
   TRY(alloc_buf(h, "A", maxA * 2, 1));
   TRY(alloc_buf(h, "QKV", maxQKV * 2, 1));
@@ -272,12 +280,13 @@ static int run_block(cv_sam2* h, int i, int B, float* X, float* Xn, cudaStream_t
   GemmEpilogue e;
   e.bias = WF(h, pre + ".qkv.b");
   e.out_bf16 = QKV;
-  e.ld_bf16 = 3 * C;
-  TRY(gemm(h, A, Cin, WB(h, pre + ".qkv.w"), (int)M, 3 * C, Cin, e, st));
+  const int Cp = p.heads * h->D, D = h->D;  // q | k | v each Cp wide, head i at columns [i*D, i*D + hd) (+ zero padding)
+  e.ld_bf16 = 3 * Cp;
+  TRY(gemm(h, A, Cin, WB(h, pre + ".qkv.w"), (int)M, 3 * Cp, Cin, e, st));
   float* Xo = X;
   long long To = T;
   int Ho = H, Wo = W, wso = ws;
-  const float scale = 1.0f / sqrtf((float)(C / p.heads));
+  const float scale = 1.0f / sqrtf((float)h->hd);
   if (p.pool) {
     // shortcut = maxpool2x2(proj(norm1(x))), computed window-major then gathered into the new grid
     float* S = BUF<float>(h, "S");
@@ -288,14 +297,14 @@ static int run_block(cv_sam2* h, int i, int B, float* X, float* Xn, cudaStream_t
     TRY(gemm(h, A, Cin, WB(h, pre + ".sc.w"), (int)M, C, Cin, es, st));
     TRY(launch_pool_shortcut(S, B, H, W, ws, C, Xn, st));
     bf16* Qp = BUF<bf16>(h, "Qp");
-    TRY(launch_pool_q(QKV, 3 * C, (int)(M / (ws * ws)), ws, C, h->f16, Qp, st));
+    TRY(launch_pool_q(QKV, 3 * Cp, (int)(M / (ws * ws)), ws, Cp, h->f16, Qp, st));
     h->launches += 2;
-    TRY(attn_tc_launch(Qp, C, C, 0, QKV, 3 * C, 3 * C, C, QKV, 3 * C, 3 * C, 2 * C, (int)(M / 4), (int)M, Wkv / 4, Wkv,
-                       p.heads, scale, AO, C, h->f16, st));
+    TRY(attn_tc_launch(Qp, Cp, Cp, 0, QKV, 3 * Cp, 3 * Cp, Cp, QKV, 3 * Cp, 3 * Cp, 2 * Cp, (int)(M / 4), (int)M, Wkv / 4, Wkv,
+                       p.heads, D, scale, AO, Cp, h->f16, st));
     Xo = Xn; Ho = H / 2; Wo = W / 2; wso = ws / 2; To = T / 4;
   } else {
-    TRY(attn_tc_launch(QKV, 3 * C, 3 * C, 0, QKV, 3 * C, 3 * C, C, QKV, 3 * C, 3 * C, 2 * C, (int)M, (int)M, Wkv, Wkv, p.heads,
-                       scale, AO, C, h->f16, st));
+    TRY(attn_tc_launch(QKV, 3 * Cp, 3 * Cp, 0, QKV, 3 * Cp, 3 * Cp, Cp, QKV, 3 * Cp, 3 * Cp, 2 * Cp, (int)M, (int)M, Wkv, Wkv,
+                       p.heads, D, scale, AO, Cp, h->f16, st));
   }
   h->launches++;
   // proj + window un-partition + residual (in place on the residual stream)
@@ -307,7 +316,7 @@ static int run_block(cv_sam2* h, int i, int B, float* X, float* Xn, cudaStream_t
     ep.map_mode = GEMM_MAP_UNWINDOW;
     ep.ws = wso; ep.nwx = nwx; ep.nwy = nwy; ep.H = Ho; ep.W = Wo;
   }
-  TRY(gemm(h, AO, C, WB(h, pre + ".proj.w"), (int)(p.pool ? M / 4 : M), C, C, ep, st));
+  TRY(gemm(h, AO, Cp, WB(h, pre + ".proj.w"), (int)(p.pool ? M / 4 : M), C, Cp, ep, st));
   // norm2 -> MLP (GELU) -> residual
   TRY(launch_ln_rows(Xo, To, C, WF(h, pre + ".n2.g"), WF(h, pre + ".n2.b"), 1e-6f, B, Ho, Wo, 0, h->f16, A, nullptr, st));
   h->launches++;

@@ -54,6 +54,14 @@ def variant_from_yaml(path: str) -> dict:
                 bkg=tuple(t.get("window_pos_embed_bkg_spatial_size", (14, 14))))
 
 
+def padded_head_dim(v: dict) -> int:
+    """Head dim of the attention kernels' buffers: the real head dim zero-padded to 64 or 96 (csrc/attn_tc.cu)."""
+    hd = v["embed"] // v["heads"]
+    if hd > 96 or hd % 8:
+        raise ValueError(f"head dim {hd} is not supported (multiple of 8, <= 96)")
+    return 64 if hd <= 64 else 96
+
+
 def block_plan(v: dict):
     """[(dim_in, dim_out, heads, window, q_pool)] per trunk block: the first block of stage s>0 widens
     the channels, pools Q and still uses the previous stage's window."""
@@ -277,11 +285,19 @@ def fold_state_dict(sd: dict, variant: dict, use_refinement: bool, operand_dtype
     pos8 = pos[0].double() + g("image_encoder.trunk.patch_embed.proj.bias")[:, None, None] - mterm
     out["pos8"] = _f32(pos8.permute(1, 2, 0).reshape(65536, E))
     # ---- trunk blocks
-    for i, (ci, co, _h, _ws, _pool) in enumerate(block_plan(variant)):
+    hd = E // variant["heads"]          # real head dim (96 / 56 / 72)
+    D = padded_head_dim(variant)        # head dim of the attention buffers (64 or 96): extra columns are exact zeros
+    for i, (ci, co, nh, _ws, _pool) in enumerate(block_plan(variant)):
         b, o = f"image_encoder.trunk.blocks.{i}.", f"b{i}."
         out[o + "n1.g"], out[o + "n1.b"] = _f32(g(b + "norm1.weight")), _f32(g(b + "norm1.bias"))
-        out[o + "qkv.w"], out[o + "qkv.b"] = _bf16(g(b + "attn.qkv.weight")), _f32(g(b + "attn.qkv.bias"))
-        out[o + "proj.w"], out[o + "proj.b"] = _bf16(g(b + "attn.proj.weight")), _f32(g(b + "attn.proj.bias"))
+        wq, bq, wp = g(b + "attn.qkv.weight"), g(b + "attn.qkv.bias"), g(b + "attn.proj.weight")
+        if D != hd:
+            # rows (part, head, hd) -> (part, head, D) with zero rows / bias; proj columns (head, hd) -> (head, D)
+            wq = F.pad(wq.reshape(3, nh, hd, ci), (0, 0, 0, D - hd)).reshape(3 * nh * D, ci)
+            bq = F.pad(bq.reshape(3, nh, hd), (0, D - hd)).reshape(3 * nh * D)
+            wp = F.pad(wp.reshape(co, nh, hd), (0, D - hd)).reshape(co, nh * D)
+        out[o + "qkv.w"], out[o + "qkv.b"] = _bf16(wq), _f32(bq)
+        out[o + "proj.w"], out[o + "proj.b"] = _bf16(wp), _f32(g(b + "attn.proj.bias"))
         out[o + "n2.g"], out[o + "n2.b"] = _f32(g(b + "norm2.weight")), _f32(g(b + "norm2.bias"))
         out[o + "fc1.w"], out[o + "fc1.b"] = _bf16(g(b + "mlp.layers.0.weight")), _f32(g(b + "mlp.layers.0.bias"))
         out[o + "fc2.w"], out[o + "fc2.b"] = _bf16(g(b + "mlp.layers.1.weight")), _f32(g(b + "mlp.layers.1.bias"))

@@ -209,3 +209,34 @@ def test_crop_pipeline_matches_per_image_calls(pair):
                 assert x[0] == y[0] and x[1] == y[1] and np.array_equal(x[2], y[2])
     with pytest.raises(Exception):
         pipe.collect()
+
+
+@pytest.mark.parametrize("variant", ["small", "base_plus", "large"])
+def test_forward_parity_other_variants(variant):
+    """SAM 2.1 small / base+ / large (head dims 96 / 56 / 72, the latter two zero-padded to 64 / 96; stage-1 widths 112 and
+    144 exercise the N % 32 == 16 GEMM path; large uses 16x16 / 8x8 windows) against the fp32 oracle, one image."""
+    from oracle import sam2_oracle
+    from circuitvision_b200 import sam2_infer
+    ref = sam2_oracle.build_oracle(variant, seed=0)
+    model = sam2_infer.get_modified_sam2(variant, None, device="cuda:0", use_refinement_layer=True)
+    res = model.load_state_dict(ref.state_dict())
+    assert not res.missing_keys and not res.unexpected_keys
+    x = sam2_oracle.preprocess_rgb(synth.make_schematic(5, 1024, render_rgb=True)[2])[None]
+    with torch.no_grad():
+        rh, rl, ri, aux = ref(x, return_aux=True)
+    model.set_max_batch(1)
+    high, low, iou = model(x.cuda())
+    torch.cuda.synchronize()
+    eng = model.engine()
+    sel = eng.read_buffer("sel", (1,), torch.int32).cpu()
+    want = torch.where(aux["stable"], torch.zeros_like(aux["best"]), aux["best"] + 1).int()
+    assert torch.equal(sel, want)
+    std = rl.std().item()
+    d = (low.cpu() - rl).abs()
+    assert d.max().item() <= 0.02 * std and d.mean().item() <= 0.004 * std, (d.max().item() / std, d.mean().item() / std)
+    assert (iou.cpu() - ri).abs().max().item() <= 1e-3
+    hstd = rh.std().item()
+    assert (high.cpu() - rh).abs().max().item() <= 0.03 * hstd
+    assert _iou(low.cpu() > 0, rl > 0) >= 0.99 and _iou(high.cpu() > 0, rh > 0) >= 0.99
+    del model, eng
+    torch.cuda.empty_cache()
