@@ -34,16 +34,16 @@ constexpr int GEMM_SMEM_MAX = 232448;
 // which is what bounds the K >= 384 shapes (ncu: the MMA thread spins on the full barriers, not on the epilogue).
 template <int BN, int CG>
 constexpr int gemm_stage_bytes() { return GEMM_BM * 128 + (BN / CG) * 128; }
-template <int CG>
-constexpr int gemm_epi_bufs() { return CG == 2 ? 1 : 2; }
+template <int BN, int CG>
+constexpr int gemm_epi_bufs() { return (CG == 2 && BN == 256) ? 1 : 2; }
 template <int BN, int CG>
 constexpr int gemm_stages() {
-  int s = (GEMM_SMEM_MAX - 1024 - 256 - 8 * gemm_epi_bufs<CG>() * GEMM_EPI_BUF) / gemm_stage_bytes<BN, CG>();
+  int s = (GEMM_SMEM_MAX - 1024 - 256 - 8 * gemm_epi_bufs<BN, CG>() * GEMM_EPI_BUF) / gemm_stage_bytes<BN, CG>();
   return s > 8 ? 8 : (CG == 1 && s > 4 ? 4 : s);
 }
 template <int BN, int CG>
 constexpr int gemm_smem_bytes() {
-  return 1024 /*align slack*/ + gemm_stages<BN, CG>() * gemm_stage_bytes<BN, CG>() + 8 * gemm_epi_bufs<CG>() * GEMM_EPI_BUF + 256;
+  return 1024 /*align slack*/ + gemm_stages<BN, CG>() * gemm_stage_bytes<BN, CG>() + 8 * gemm_epi_bufs<BN, CG>() * GEMM_EPI_BUF + 256;
 }
 
 __device__ __forceinline__ long long gemm_dest_row(const GemmEpilogue& e, int map, long long r) {
@@ -89,7 +89,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
   static_assert(CG == 1 || CG == 2, "CG");
   constexpr int GEMM_STAGES = gemm_stages<BN, CG>();
-  constexpr int EPI_BUFS = gemm_epi_bufs<CG>();
+  constexpr int EPI_BUFS = gemm_epi_bufs<BN, CG>();
   constexpr int A_BYTES = GEMM_BM * 128, B_BYTES = (BN / CG) * 128;
   constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   constexpr bool TMA_OUT = (MAP == GEMM_MAP_IDENTITY) && (OUT == 0 || OUT == 1);
@@ -454,7 +454,8 @@ static int launch_bn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16*
   if (e.map_mode == GEMM_MAP_IDENTITY && tma_ok && !(f32 && b16)) {
     // CTA pairs for the K >= 256 shapes that are bound by operand delivery, not by HBM
     static const bool pairs_on = getenv("CVB_GEMM_PAIRS") ? atoi(getenv("CVB_GEMM_PAIRS")) != 0 : true;
-    if (pairs_on && BN == 256 && K >= 256 && M >= 1024) {  // measured: BN = 192 pairs are no faster than single CTAs
+    static const int pair_min_bn = getenv("CVB_PAIR_MINBN") ? atoi(getenv("CVB_PAIR_MINBN")) : 256;
+    if (pairs_on && BN >= 128 && BN >= pair_min_bn && K >= 256 && M >= 1024) {
       if (b16 && !res && e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 0, 1, 0, 0, 2>(CVB_GEMM_ARGS);
       if (b16 && !res && e.act == GEMM_ACT_GELU) return launch_cfg<BN, 1, 0, 1, 0, 0, 2>(CVB_GEMM_ARGS);
       if (f32 && res && e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 1, 0, 0, 0, 2>(CVB_GEMM_ARGS);
