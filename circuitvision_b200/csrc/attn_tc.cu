@@ -11,6 +11,7 @@
 //   from its row-major tile)  ->  softmax warps fold O_tile into fp32 registers with the online-softmax rescale.
 #include "common.cuh"
 #include "tc05.cuh"
+#include "act.cuh"
 
 namespace cvb {
 
@@ -202,26 +203,35 @@ k_attn_global(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
         }
         m_ref = mx * p.scale_log2;
       }
-      float tmax = -INFINITY, rowsum = 0.f;
+      // per PAIR of scores: one FMNMX3 (running max), one packed FFMA2 (scale and shift), two ex2, one packed FADD2
+      // (row sum) and one pack — the softmax warps are issue-bound, so every instruction per element counts
+      float tmax = -INFINITY;
+      uint64_t rs2 = pk2(0.f, 0.f);
+      const uint64_t sc2 = pk2(p.scale_log2, p.scale_log2), mr2 = pk2(-m_ref, -m_ref);
+      // the TMEM load of chunk c + 1 is in flight while chunk c is exponentiated
+      uint32_t v[2][32];
+      tc::tmem_ld_32x32(tS, v[0]);
 #pragma unroll
       for (int c = 0; c < ATT_BN / 32; c++) {
-        uint32_t v[32];
-        tc::tmem_ld_32x32(tS + c * 32, v);
         tc::tmem_ld_wait();
+        if (c + 1 < ATT_BN / 32) tc::tmem_ld_32x32(tS + (c + 1) * 32, v[(c + 1) & 1]);
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-          tmax = fmaxf(tmax, fmaxf(s0, s1));
-          const float x0 = fmaf(s0, p.scale_log2, -m_ref), x1 = fmaf(s1, p.scale_log2, -m_ref);
-          // (moving part of the exponentials to an FMA-pipe polynomial was measured: 25 / 50 / 75 % offload made the
-          // kernel 5 / 12 / 23 % slower — it is issue-bound, not MUFU-bound, despite the 58 % XU-pipe reading in ncu)
+          const float s0 = __uint_as_float(v[c & 1][i]), s1 = __uint_as_float(v[c & 1][i + 1]);
+          asm("max.f32 %0, %0, %1, %2;" : "+f"(tmax) : "f"(s0), "f"(s1));
+          float x0, x1;
+          up2(fma2(pk2(s0, s1), sc2, mr2), x0, x1);
           const float p0 = ex2(x0), p1 = ex2(x1);
-          rowsum += p0 + p1;
+          const uint64_t pp = pk2(p0, p1);
+          asm("add.rn.f32x2 %0, %0, %1;" : "+l"(rs2) : "l"(pp));
           pk[i >> 1] = tc::pack16(p.fp16, p0, p1);
         }
         tc::tmem_st_32x16(tS + c * 16, pk);  // P over the already-consumed head of S
       }
+      float rs_lo, rs_hi;
+      up2(rs2, rs_lo, rs_hi);
+      const float rowsum = rs_lo + rs_hi;
       tc::tmem_st_wait();
       tc::tc_fence_before();
       __syncwarp();
