@@ -85,49 +85,58 @@ int launch_im2col_u8(const uint8_t* img, int B, int S, const float* mean, const 
   return CV_OK;
 }
 
-// Raw-pixel patch operand: out[tok, k] = bf16(pixel) (0..255 is exact in bf16), zero outside the image and for the K
-// padding.  ToTensor's 1/255 and Normalize's mean/std are folded into the GEMM weights and the per-token additive table
-// at load time (sam2_weights.fold_state_dict: "pe.w8", "pos8"), so the u8 path is exact in its inputs and needs half
-// the K of the two-term fp32 split.  One thread = one 16-byte chunk (8 consecutive k) of one token: stores coalesce.
-__global__ void __launch_bounds__(256) k_im2col_u8raw(const uint8_t* __restrict__ img, int S, int swap_rb, int fp16, long long total,
+// Raw-pixel patch operand: out[tok, k] = fp16/bf16(pixel value) (0..255 is exact in both), zero outside the image and in
+// the K padding.  ToTensor's 1/255 and Normalize's mean/std are folded into the GEMM weights and the per-token additive
+// table at load time (sam2_weights.fold_state_dict: "pe.w8", "pos8").
+// K order of the u8 path: k = ky*21 + kx*3 + c, i.e. the 21 taps of kernel row ky are 21 CONTIGUOUS bytes of the HWC
+// image row.  CTA = 64 consecutive tokens of one token row: the 7 image rows it needs are staged in shared memory with
+// aligned 32-bit loads, converted, and the 64 x 304-byte operand rows (contiguous in global memory) are written with
+// linear 16-byte stores.
+constexpr int IM_TOK = 64, IM_WORDS = 196;  // 195 words cover bytes [12*x0 - 12, 12*x0 + 768)
+__global__ void __launch_bounds__(256) k_im2col_u8raw(const uint8_t* __restrict__ img, int S, int swap_rb, int fp16,
                                                       __nv_bfloat16* __restrict__ out) {
-  constexpr int CH = PE_K / 8;  // 19 chunks per token
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
+  __shared__ uint32_t in[7][IM_WORDS];
+  __shared__ __align__(16) uint16_t outs[IM_TOK * PE_K];
   const int G = S / 4;
-  long long tok = idx / CH;
-  const int j = (int)(idx - tok * CH);
-  const int x = (int)(tok % G);
-  const int y = (int)((tok / G) % G);
-  const long long b = tok / ((long long)G * G);
-  const uint8_t* im = img + b * (long long)S * S * 3;
-  uint32_t w[4];
-#pragma unroll
-  for (int h = 0; h < 4; h++) {
-    float v2[2];
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const int k = j * 8 + h * 2 + u;
-      float v = 0.f;
-      if (k < 147) {
-        const int c = k / 49, rem = k - c * 49;
-        const int ky = rem / 7, kx = rem - ky * 7;
-        const int iy = y * 4 - 3 + ky, ix = x * 4 - 3 + kx;
-        if (iy >= 0 && iy < S && ix >= 0 && ix < S) v = (float)__ldg(im + ((long long)iy * S + ix) * 3 + (swap_rb ? 2 - c : c));
-      }
-      v2[u] = v;
-    }
-    w[h] = tc::pack16(fp16, v2[0], v2[1]);
+  const int x0 = blockIdx.x * IM_TOK, y = blockIdx.y, b = blockIdx.z;
+  const uint8_t* im = img + (size_t)b * S * S * 3;
+  const int row_words = S * 3 / 4;
+  for (int i = threadIdx.x; i < 7 * 195; i += 256) {
+    const int ky = i / 195, wi = i - ky * 195;
+    const int iy = y * 4 - 3 + ky, gw = 3 * x0 - 3 + wi;  // word index inside the image row
+    uint32_t v = 0u;
+    if (iy >= 0 && iy < S && gw >= 0 && gw < row_words) v = __ldg((const uint32_t*)(im + (size_t)iy * S * 3) + gw);
+    in[ky][wi] = v;
   }
-  *(uint4*)(out + tok * PE_K + j * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  __syncthreads();
+  const uint8_t* inb = (const uint8_t*)&in[0][0];
+  for (int e = threadIdx.x; e < IM_TOK * PE_K; e += 256) {
+    const int j = e / PE_K, k = e - j * PE_K;
+    float v = 0.f;
+    if (k < 147) {
+      const int ky = k / 21, t = k - ky * 21;
+      const int kx = t / 3, c = t - kx * 3;
+      // byte (pixel 4*(x0+j) - 3 + kx, channel c) relative to the staged range that starts at byte 12*x0 - 12
+      v = (float)inb[ky * (IM_WORDS * 4) + 12 * j + 3 + 3 * kx + (swap_rb ? 2 - c : c)];
+    }
+    outs[e] = (uint16_t)(tc::pack16(fp16, v, 0.f) & 0xFFFFu);
+  }
+  __syncthreads();
+  const size_t tok0 = ((size_t)b * G + y) * G + x0;
+  uint4* dst = (uint4*)(out + tok0 * PE_K);
+  const uint4* src = (const uint4*)outs;
+  const int n_tok = min(IM_TOK, G - x0);
+  for (int i = threadIdx.x; i < n_tok * PE_K / 8; i += 256) dst[i] = src[i];
 }
 
 int launch_im2col_u8raw(const uint8_t* img, int B, int S, int swap_rb, int fp16, __nv_bfloat16* out, cudaStream_t st) {
-  long long total = (long long)B * (S / 4) * (S / 4) * (PE_K / 8);
-  cvb_next_work((double)B * S * S * 3 + (double)B * (S / 4) * (S / 4) * PE_K * 2);
-  CVB_LAUNCH(k_im2col_u8raw, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, img, S, swap_rb, fp16, total, out);
+  if (S % 4 || ((uintptr_t)img & 3)) return cvb_fail(CV_ERR_INVALID, "im2col: image side must be a multiple of 4 and 4-byte aligned");
+  const int G = S / 4;
+  cvb_next_work((double)B * S * S * 3 + (double)B * G * G * PE_K * 2);
+  CVB_LAUNCH(k_im2col_u8raw, dim3((G + IM_TOK - 1) / IM_TOK, G, B), dim3(256), 0, st, img, S, swap_rb, fp16, out);
   return CV_OK;
 }
+
 int launch_im2col_f32(const float* img, int B, int S, int fp16, __nv_bfloat16* out, cudaStream_t st) {
   long long total = (long long)B * (S / 4) * (S / 4) * 8;
   cvb_next_work((double)B * S * S * 12 + (double)B * (S / 4) * (S / 4) * 2 * PE_K * 2);

@@ -276,8 +276,9 @@ def fold_state_dict(sd: dict, variant: dict, use_refinement: bool, operand_dtype
     #   NORMALISED image: out-of-bounds taps contribute nothing).
     w4 = g("image_encoder.trunk.patch_embed.proj.weight")  # [E,3,7,7]
     std = torch.tensor(STD, dtype=torch.float64)[None, :, None, None]
-    w8 = _bf16(F.pad((w4 / (255.0 * std)).reshape(E, 147), (0, PE_K - 147)))
-    out["pe.w8"] = w8
+    w8 = _bf16(F.pad((w4 / (255.0 * std)).reshape(E, 147), (0, PE_K - 147)))  # K order (c, ky, kx) for the mean term
+    # the uint8 operand is written with K order (ky, kx, c): a kernel row's 21 taps are contiguous bytes of the HWC image
+    out["pe.w8"] = F.pad(w8[:, :147].reshape(E, 3, 7, 7).permute(0, 2, 3, 1).reshape(E, 147), (0, PE_K - 147)).contiguous()
     # the mean term uses the SAME bf16-rounded weights, so the sum equals round(w') . (p - 255 mean): the rounding error
     # stays relative to the normalised pixel value instead of to the raw 0..255 value
     mean_img = (255.0 * torch.tensor(MEAN, dtype=torch.float64))[None, :, None, None].expand(1, 3, 1024, 1024)
