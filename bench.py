@@ -38,6 +38,7 @@ def _args():
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--variant", default="tiny")
+    ap.add_argument("--chunk", type=int, default=64, help="crops per SAM 2.1 engine pass (workspace is sized for this many)")
     ap.add_argument("--operands", default="fp16", choices=["fp16", "bf16"],
                     help="16-bit tensor-core operand format of the SAM 2.1 path (DESIGN.md section 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -252,7 +253,7 @@ def main():
     if use_sam2:
         from circuitvision_b200 import sam2_infer
         import torch as _t
-        sam = sam2_infer.build_random_init(a.variant, device=dev, seed=0, max_batch=B,
+        sam = sam2_infer.build_random_init(a.variant, device=dev, seed=0, max_batch=min(B, a.chunk),
                                            operand_dtype=_t.float16 if a.operands == "fp16" else _t.bfloat16)
     d_masks = [torch.from_numpy(m).to(dev) for m in pool_masks]
     h_masks = [torch.from_numpy(m).pin_memory() for m in pool_masks]

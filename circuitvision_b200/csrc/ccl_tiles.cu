@@ -56,11 +56,13 @@ __device__ __forceinline__ void gunion(int* L, int a, int b) {
 }
 
 // ---- shared-memory union-find on sub-run start positions (tile-local pixel index)
+// Slot of element x = x >> 1: two horizontally adjacent pixels are never both the first pixel of a (sub-)run, so the
+// parent array needs one slot per pixel PAIR (8 KB per tile instead of 16 KB: twice the resident tiles per SM).
 __device__ __forceinline__ int sfind(const volatile int* P, int x) {
-  int y = P[x];
+  int y = P[x >> 1];
   while (y != x) {
     x = y;
-    y = P[x];
+    y = P[x >> 1];
   }
   return x;
 }
@@ -70,11 +72,11 @@ __device__ __forceinline__ void sunion(int* P, int a, int b) {
     a = sfind(P, a);
     b = sfind(P, b);
     if (a < b) {
-      int old = atomicMin(P + b, a);
+      int old = atomicMin(P + (b >> 1), a);
       done = (old == b);
       b = old;
     } else if (b < a) {
-      int old = atomicMin(P + a, b);
+      int old = atomicMin(P + (a >> 1), b);
       done = (old == a);
       a = old;
     } else {
@@ -159,7 +161,7 @@ __device__ __forceinline__ uint32_t tile_label(const uint8_t* __restrict__ im, i
   if (cin) starts &= ~1u;  // a continued run is not an element of its own
   for (uint32_t s = starts; s; s &= s - 1) {
     int i = __ffs(s) - 1;
-    P[base + i] = base + i;
+    P[(base + i) >> 1] = base + i;
   }
   __syncthreads();
   if (w && r > 0) {
@@ -198,12 +200,12 @@ __device__ __forceinline__ uint32_t tile_label(const uint8_t* __restrict__ im, i
 // touches the tile border — only such components can be merged by the seam pass, so only those words are revisited by
 // pass C.  Components that stay inside their tile are final after pass A and are counted here.
 template <int CONN>
-__global__ void __launch_bounds__(CT_THREADS) k_ccl_tile_label(const uint8_t* __restrict__ masks, int* __restrict__ labels,
+__global__ void __launch_bounds__(CT_THREADS, 12) k_ccl_tile_label(const uint8_t* __restrict__ masks, int* __restrict__ labels,
                                                                 int H, int W, int vec_ok, uint32_t* __restrict__ dirty,
                                                                 int* __restrict__ ncomp, int* __restrict__ partial) {
   __shared__ uint32_t bits[CT_H][CT_WORDS];
   __shared__ int fid[CT_H][CT_WORDS];
-  __shared__ int P[CT_H * CT_W];
+  __shared__ int P[CT_H * CT_W / 2];
   __shared__ uint32_t touch[CT_H * CT_W / 32];  // bit per tile-local pixel: root of a border-touching component
   __shared__ int closed_roots;
   const int b = blockIdx.z, x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
@@ -218,24 +220,24 @@ __global__ void __launch_bounds__(CT_THREADS) k_ccl_tile_label(const uint8_t* __
   const bool cin = carries_in(bits, r, c);
   const uint32_t sub = w & ~(w << 1);  // every sub-run of my word, continued or not
   // root and global label of every sub-run; roots of components that touch the tile border are marked.  The root is
-  // parked in P[base + i]: for a run element that is path compression, for a continued sub-run the slot is unused.
+  // parked in the slot of base + i: for a run element that is path compression, for a continued sub-run the slot is unused.
   for (uint32_t s = sub; s; s &= s - 1) {
     const int i = __ffs(s) - 1;
     const int root = sfind(P, (i == 0 && cin) ? fid[r][c] : base + i);
     const bool edge = r == 0 || r == CT_H - 1 || (c == 0 && i == 0) || (c == CT_WORDS - 1 && i + run_len(w, i) == 32);
     if (edge) atomicOr(&touch[root >> 5], 1u << (root & 31));
-    if (root != base + i) P[base + i] = root;
+    if (root != base + i) P[(base + i) >> 1] = root;
   }
   __syncthreads();
   bool my_dirty = false;
   int n_closed = 0;
   for (uint32_t s = sub; s; s &= s - 1) {
     const int i = __ffs(s) - 1;
-    const int root = P[base + i];
+    const int root = P[(base + i) >> 1];
     const bool t = (touch[root >> 5] >> (root & 31)) & 1u;
     my_dirty |= t;
     n_closed += (!t && root == base + i);  // first pixel of a component that cannot change any more
-    G[base + i] = (y0 + root / CT_W) * W + x0 + (root % CT_W) + 1;  // nobody else reads my slots any more
+    G[(base + i) >> 1] = (y0 + root / CT_W) * W + x0 + (root % CT_W) + 1;  // nobody else reads my slots any more
   }
   if (my_dirty) n_closed = 0;  // pass C revisits this word and counts every root in it
   const uint32_t dmask = __ballot_sync(0xffffffffu, my_dirty);
@@ -262,11 +264,11 @@ __global__ void __launch_bounds__(CT_THREADS) k_ccl_tile_label(const uint8_t* __
     if (nib) {
       const int gb = rr * CT_W + wc * 32;
       if (nib == 0xFu) {
-        out[0] = out[1] = out[2] = out[3] = G[gb + run_start(word, sh)];
+        out[0] = out[1] = out[2] = out[3] = G[(gb + run_start(word, sh)) >> 1];
       } else {
 #pragma unroll
         for (int k = 0; k < 4; k++)
-          if ((nib >> k) & 1u) out[k] = G[gb + run_start(word, sh + k)];
+          if ((nib >> k) & 1u) out[k] = G[(gb + run_start(word, sh + k)) >> 1];
       }
     }
     const int x = x0 + lane * 4;
@@ -407,6 +409,13 @@ static int ccl_run(const uint8_t* masks, int B, int H, int W, int32_t* labels, i
   dim3 tg((W + CT_W - 1) / CT_W, (H + CT_H - 1) / CT_H, B);
   const double px = (double)B * H * W;
   cvb_next_work(5.0 * px);
+  static bool carveout_set = false;
+  if (!carveout_set) {
+    // 12 resident tiles x ~9.7 KB: ask for the large shared-memory split (the default heuristic left room for 6)
+    CVB_CHECK(cudaFuncSetAttribute(k_ccl_tile_label<CONN>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
+    carveout_set = true;
+  }
   CVB_LAUNCH((k_ccl_tile_label<CONN>), tg, dim3(CT_THREADS), 0, st, masks, labels, H, W, vec_ok, dirty, n_components, partial);
   const long long seam_px = max((long long)((H - 1) / CT_H) * W, (long long)((W - 1) / CT_W) * H);
   if (seam_px > 0) {

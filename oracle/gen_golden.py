@@ -20,6 +20,8 @@ sys.path.insert(0, ROOT)
 from circuitvision_b200 import synth  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden", "node_golden.npz")
+GOLDEN_TERMINALS = os.path.join(ROOT, "tests", "golden", "terminal_golden.npz")
+CLASS_NAMES = {4: "terminal", 7: "voltage.dc", 10: "resistor"}  # subset of the reference's classes.json ids
 
 
 def _box(cls, x0, y0, x1, y1):
@@ -72,6 +74,85 @@ def golden_cases():
     return cases
 
 
+def terminal_cases():
+    """name -> (rgb u8 [H,W,3], boxes with 'terminal' entries).  Deterministic (seeded); no file reads."""
+    cases = {}
+
+    def paper(seed, size, noise, grid=None):
+        m, b, rgb = synth.make_schematic(seed, size, grid=grid, dense=False, render_rgb=True)
+        rng = np.random.default_rng(7000 + seed)
+        img = rgb.astype(np.float32)
+        if noise:
+            yy, xx = np.mgrid[0:size, 0:size].astype(np.float32)
+            shade = 30.0 * np.sin(xx / size * 3.1) * np.cos(yy / size * 2.3)  # uneven illumination
+            img = img * 0.85 + shade[..., None] + rng.normal(0.0, noise, img.shape).astype(np.float32)
+        return m, b, np.clip(img, 0, 255).astype(np.uint8), rng
+
+    def add_terminals(m, b, rng, n, size):
+        ys, xs = np.nonzero(m)
+        out = list(b)
+        for k in range(n):
+            j = int(rng.integers(len(ys)))
+            cx, cy = int(xs[j]), int(ys[j])
+            w, h = int(rng.integers(8, 40)), int(rng.integers(8, 40))
+            if k % 5 == 4:  # off-wire terminal
+                cx, cy = int(rng.integers(size)), int(rng.integers(size))
+            out.append(_box("terminal", cx - w // 2, cy - h // 2, cx + w - w // 2, cy + h - h // 2))
+        return out
+
+    for seed, size, noise in ((0, 1024, 0.0), (1, 1024, 6.0), (2, 1024, 12.0), (3, 768, 6.0)):
+        m, b, rgb, rng = paper(seed, size, noise)
+        cases[f"paper{size}_s{seed}_n{int(noise)}"] = (rgb, add_terminals(m, b, rng, 10, size))
+    m, b, rgb, rng = paper(4, 2048, 5.0, grid=10)
+    cases["paper2048_s4"] = (rgb, add_terminals(m, b, rng, 24, 2048))
+    # non-square crop, terminals clipped by the image border, duplicate terminal, boxes partly outside
+    m, b, rgb, rng = paper(5, 1024, 4.0)
+    bb = add_terminals(m, b, rng, 8, 1024)
+    crop = np.ascontiguousarray(rgb[40:800, 100:1000])
+    bb = [dict(x, xmin=x["xmin"] - 100, xmax=x["xmax"] - 100, ymin=x["ymin"] - 40, ymax=x["ymax"] - 40) for x in bb]
+    bb.append(_box("terminal", -12, 300, 14, 330))
+    bb.append(_box("terminal", 880, 740, 930, 790))
+    bb.append(dict(bb[-1]))
+    cases["crop_760x900"] = (crop, bb)
+    # no terminals at all / only terminals / blank page / inverted page (dark paper: mean of the mask > 127)
+    m, b, rgb, rng = paper(6, 1024, 3.0)
+    cases["no_terminals"] = (rgb, b)
+    cases["only_terminals"] = (rgb, [x for x in add_terminals(m, [], rng, 12, 1024)])
+    cases["blank_page"] = (np.full((512, 640, 3), 250, np.uint8), [_box("terminal", 100, 100, 140, 130)])
+    chk = np.indices((600, 600)).sum(0) % 2 * 255  # checkerboard: the adaptive threshold marks half the pixels
+    cases["checkerboard"] = (np.repeat(chk[..., None], 3, 2).astype(np.uint8), [_box("terminal", 200, 200, 260, 240),
+                                                                               _box("resistor", 300, 300, 420, 340)])
+    # channel-dependent colours: exercises the RGB/BGR swap of segment_circuit
+    col = np.zeros((512, 512, 3), np.uint8)
+    col[..., 0] = 200
+    col[..., 2] = 40
+    col[100:110, 50:450] = (10, 10, 250)
+    col[300:310, 50:450] = (250, 10, 10)
+    col[100:310, 240:250] = (10, 250, 10)
+    cases["colour_channels"] = (col, [_box("terminal", 230, 190, 262, 222), _box("terminal", 40, 90, 70, 120)])
+    return cases
+
+
+def main_terminals():
+    from oracle import ref_loader
+    store, meta = {}, {}
+    for name, (rgb, boxes) in terminal_cases().items():
+        out, n_contours, counts = ref_loader.reference_reclassify(rgb, boxes, CLASS_NAMES)
+        A = ref_loader.load_reference_analyzer()
+        mask = A.segment_circuit(cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR))
+        meta[name] = {"shape": list(rgb.shape), "rgb_sha256": _sha(rgb), "mask_sha256": _sha(mask),
+                      "n_contours": n_contours, "terminal_counts": counts,
+                      "classes": [b["class"] for b in out],
+                      "reclassified": [bool(b.get("was_reclassified_from_terminal", False)) for b in out],
+                      "yolo_ids": [b.get("_yolo_class_id_temp") for b in out],
+                      "orig": [b.get("original_yolo_class_if_reclassified") for b in out]}
+        print(name, rgb.shape, len(boxes), "boxes ->", sum(meta[name]["reclassified"]), "reclassified of",
+              sum(b["class"] == "terminal" for b in boxes), "terminals")
+    store["meta_json"] = np.frombuffer(json.dumps(meta, sort_keys=True).encode(), np.uint8)
+    np.savez_compressed(GOLDEN_TERMINALS, **store)
+    print("wrote", GOLDEN_TERMINALS, os.path.getsize(GOLDEN_TERMINALS), "bytes; cv2", cv2.__version__)
+
+
 def _sha(a: np.ndarray) -> str:
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
@@ -104,4 +185,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--terminals" in sys.argv:
+        main_terminals()
+    else:
+        main()

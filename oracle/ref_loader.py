@@ -68,3 +68,22 @@ def reference_node_analysis(mask, boxes):
         except Exception as e:  # consumer failure is itself a parity artifact
             text = f"<netlist error: {type(e).__name__}>"
     return nodes, emptied, enhanced, cimg, fviz, cpts, text
+
+
+def reference_reclassify(image_rgb, boxes, class_names=None):
+    """Run the reference reclassify_terminals_based_on_connectivity (circuit_analyzer.py:2217) in place on a deep copy
+    of `boxes`; returns the modified list.  `class_names` stands in for `self.yolo.model.names` (ultralytics is absent)."""
+    import copy
+    A = load_reference_analyzer()
+    out = copy.deepcopy(boxes)
+    A.yolo = MagicMock()
+    A.yolo.model.names = dict(class_names or {})
+    log = io.StringIO()
+    with contextlib.redirect_stdout(log):
+        A.reclassify_terminals_based_on_connectivity(image_rgb.copy(), out)
+    # the reference prints (debug=True) the contour count and, per terminal in list order, its distinct-contour count
+    import re
+    text = log.getvalue()
+    found = re.search(r"Prelim Reclass: Found (\d+) contours", text)
+    counts = [int(x) for x in re.findall(r"connected to (\d+) distinct contours", text)]
+    return out, (int(found.group(1)) if found else None), counts

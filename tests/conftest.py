@@ -47,3 +47,15 @@ def has_cuda():
         return torch.cuda.is_available()
     except Exception:
         return False
+
+
+@pytest.fixture(scope="session")
+def terminal_golden():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "terminal_golden.npz"))
+    return json.loads(bytes(z["meta_json"]).decode())
+
+
+@pytest.fixture(scope="session")
+def terminal_cases():
+    from oracle.gen_golden import terminal_cases as tc
+    return tc()

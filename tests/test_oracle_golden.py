@@ -54,3 +54,28 @@ def test_ccl_oracle_canonical_labels():
     assert lab[2, 2] == 0
     lab4 = node_oracle.ccl_labels_min_index(m, 4)
     assert lab4[1, 1] == 1 * 8 + 1 + 1
+
+
+def test_terminal_oracle_matches_reference_golden(terminal_golden, terminal_cases):
+    """oracle/terminal_oracle.py against the fixtures of the unmodified reference reclassify_terminals_based_on_connectivity
+    (circuit_analyzer.py:2217): adaptive-threshold mask, contour count, per-terminal distinct-contour counts, final
+    classes and the bookkeeping keys."""
+    import copy
+    import cv2
+    from oracle import terminal_oracle
+    from oracle.gen_golden import CLASS_NAMES
+    assert set(terminal_golden) == set(terminal_cases)
+    for name, (rgb, boxes) in terminal_cases.items():
+        g = terminal_golden[name]
+        assert _sha(rgb) == g["rgb_sha256"], f"{name}: generator drifted"
+        assert _sha(terminal_oracle.segment_circuit_from_rgb(rgb)) == g["mask_sha256"], name
+        counts, mask, contours = terminal_oracle.terminal_contact_counts(rgb, boxes)
+        assert len(contours) == g["n_contours"], name
+        if g["n_contours"]:  # the reference's debug build returns before the per-terminal loop when nothing was found
+            assert [c for c in counts if c >= 0] == g["terminal_counts"], name
+        out = copy.deepcopy(boxes)
+        terminal_oracle.reclassify_terminals(rgb, out, CLASS_NAMES)
+        assert [b["class"] for b in out] == g["classes"], name
+        assert [bool(b.get("was_reclassified_from_terminal", False)) for b in out] == g["reclassified"], name
+        assert [b.get("_yolo_class_id_temp") for b in out] == g["yolo_ids"], name
+        assert [b.get("original_yolo_class_if_reclassified") for b in out] == g["orig"], name
