@@ -35,7 +35,7 @@ RESULT_DTYPE = np.dtype([("n_external", "<i4"), ("n_contours", "<i4"), ("n_point
 assert BOX_DTYPE.itemsize == 48 and CONTOUR_DTYPE.itemsize == 64 and PAIR_DTYPE.itemsize == 16
 assert RESULT_DTYPE.itemsize == 32
 
-CV_BOX_ZERO_IN_MASK, CV_BOX_IS_COMPONENT, CV_BOX_IS_SOURCE = 1, 2, 4
+CV_BOX_ZERO_IN_MASK, CV_BOX_IS_COMPONENT, CV_BOX_IS_SOURCE, CV_BOX_IS_TERMINAL = 1, 2, 4, 8
 DEFAULT_CAPS = dict(max_external=32768, max_contours=2560, max_points=262144, max_pairs=8192)
 
 
@@ -50,6 +50,10 @@ def _declare(lib):
     lib.cv_nodes_workspace_bytes.restype = sz
     lib.cv_nodes_analyze.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp,
                                      C.POINTER(cv_nodes_caps), vp, sz, vp]
+    lib.cv_terminals_workspace_bytes.argtypes = [i32, i32, i32, C.POINTER(cv_nodes_caps)]
+    lib.cv_terminals_workspace_bytes.restype = sz
+    lib.cv_terminals_analyze.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, vp, vp, vp, vp, vp, C.POINTER(cv_nodes_caps),
+                                         vp, sz, vp]
     lib.cv_ccl_workspace_bytes.argtypes = [i32, i32, i32]
     lib.cv_ccl_workspace_bytes.restype = sz
     lib.cv_ccl_label.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, sz, vp]

@@ -35,7 +35,7 @@ class CircuitAnalyzer:
     source_components = set(_nodes.SOURCE_COMPONENTS)
 
     def __init__(self, sam2_model=None, sam2_transforms=None, use_sam2=None, debug=False, device=0,
-                 render_debug_images=True):
+                 render_debug_images=True, class_names=None):
         self.debug = debug
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         self.sam2_model = sam2_model
@@ -46,6 +46,40 @@ class CircuitAnalyzer:
         self.render_debug_images = render_debug_images
         self._lock = threading.Lock()  # the app shares one analyzer across session threads (app.py:134)
         self._node_analyzer = None
+        self._terminal_analyzer = None
+        # {numeric id: class name}: what the reference reads from self.yolo.model.names (:2259); YOLO itself is out of scope
+        self.class_names = dict(class_names or {})
+
+    # ------------------------------------------------------------------ terminal reclassification
+    def _ta(self):
+        if self._terminal_analyzer is None:
+            from . import terminals as _terminals
+            self._terminal_analyzer = _terminals.TerminalAnalyzer(self.device)
+        return self._terminal_analyzer
+
+    def reclassify_terminals_based_on_connectivity(self, image_rgb_original, bboxes_list_to_modify):
+        """Reference :2217.  Modifies `bboxes_list_to_modify` in place: a 'terminal' whose box is near two or more
+        distinct wire contours of the page becomes 'voltage.dc' (keys set exactly as :2295-2307).  Returns None."""
+        from . import terminals as _terminals
+        page = np.ascontiguousarray(np.asarray(image_rgb_original))
+        if page.ndim != 3 or page.shape[2] != 3 or page.dtype != np.uint8:
+            raise CvError("image_rgb_original must be an (H, W, 3) uint8 array")
+        with self._lock:
+            r = self._ta().analyze(page[None], [list(bboxes_list_to_modify)])
+            if int(r.status()[0]):
+                raise CvError(f"terminal analysis overflowed a capacity (status {int(r.status()[0])})")
+            counts = r.counts(0)
+        _terminals.apply_reclassification(bboxes_list_to_modify, counts, self.class_names)
+
+    def reclassify_terminals_batch(self, pages_rgb, boxes_list):
+        """Batched form: pages [B,H,W,3] uint8 (numpy or cuda tensor); relabels every list in place and returns the
+        device-resident `TerminalBatchResult`."""
+        from . import terminals as _terminals
+        with self._lock:
+            r = self._ta().analyze(pages_rgb, boxes_list)
+        for b, boxes in enumerate(boxes_list):
+            _terminals.apply_reclassification(boxes, r.counts(b), self.class_names)
+        return r
 
     # ------------------------------------------------------------------ node analysis
     def _na(self):

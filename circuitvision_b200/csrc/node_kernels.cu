@@ -24,8 +24,10 @@ __global__ void k_copy16(const uint4* __restrict__ src, uint4* __restrict__ dst,
   for (size_t k = n16 * 16 + i; k < n; k += stride) dst8[k] = src8[k];
 }
 
+// numpy_slices: the terminal-reclassification caller (:2245-2249) writes mask[max(0,ymin):min(H,ymax), ...] = 0 without
+// the emptiness guard of :1341, so a negative upper bound wraps like a Python slice (end = H + ymax).
 __global__ void k_zero_boxes(uint8_t* __restrict__ emptied, int H, int W, const cv_box* __restrict__ boxes,
-                             const int32_t* __restrict__ box_offsets) {
+                             const int32_t* __restrict__ box_offsets, int numpy_slices) {
   int b = blockIdx.y;
   int i = box_offsets[b] + blockIdx.x;
   if (i >= box_offsets[b + 1]) return;
@@ -33,6 +35,10 @@ __global__ void k_zero_boxes(uint8_t* __restrict__ emptied, int H, int W, const 
   if (!(bx.flags & CV_BOX_ZERO_IN_MASK)) return;
   int y0 = max(0, bx.ymin), y1 = min(H, bx.ymax);
   int x0 = max(0, bx.xmin), x1 = min(W, bx.xmax);
+  if (numpy_slices) {
+    if (y1 < 0) y1 = max(0, H + y1);
+    if (x1 < 0) x1 = max(0, W + x1);
+  }
   if (y0 >= y1 || x0 >= x1) return;
   uint8_t* img = emptied + (size_t)b * H * W;
   int bw = x1 - x0;
@@ -146,7 +152,7 @@ __global__ void k_binarize(const uint8_t* __restrict__ enh_raw, uint8_t* __restr
   if (i >= n_per_image) return;
   size_t p = (size_t)b * n_per_image + i;
   uint8_t v = enh_raw[p];
-  enhanced_out[p] = inv ? v : (v == 255 ? (uint8_t)1 : v);
+  if (enhanced_out) enhanced_out[p] = inv ? v : (v == 255 ? (uint8_t)1 : v);
   bin[p] = inv ? (uint8_t)(v != 255) : (uint8_t)(v != 0);
 }
 
@@ -274,12 +280,12 @@ __global__ void k_frame_flags(const uint8_t* __restrict__ bin, const int* __rest
 
 // External components (cv2 RETR_EXTERNAL) listed in cv2's order = descending raster index of the first pixel.
 // One CTA per image.
-#define CVB_MAX_ROWS 1024
+#define CVB_MAX_ROWS 12000  // row counters live in dynamic shared memory (4 B per image row, below the 48 KB default)
 __global__ void __launch_bounds__(1024) k_list_external(const uint8_t* __restrict__ bin, const int* __restrict__ Lall,
                                                         const uint8_t* __restrict__ frame, int h, int w,
                                                         int* __restrict__ cand, int max_external,
                                                         cv_image_result* __restrict__ results) {
-  __shared__ int s_cnt[CVB_MAX_ROWS];
+  extern __shared__ int s_cnt[];  // [h]
   __shared__ int s_total;
   int b = blockIdx.x;
   size_t base = (size_t)b * h * w;
@@ -610,6 +616,120 @@ __global__ void k_init_results(cv_image_result* results, unsigned long long* sum
   sums[b] = 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Terminal reclassification (circuit_analyzer.py:2217-2310): page -> grey -> adaptive threshold ->
+// box masking -> external contours at NATIVE resolution -> per-terminal count of contours with a "near" vertex.
+// ------------------------------------------------------------------------------------------------
+// grey value of the RGB page with the reference's channel swap; thread = 4 pixels (12 B in, 4 B out)
+__global__ void __launch_bounds__(256) k_gray_page(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ gray, size_t n_px,
+                                                   int aligned) {
+  size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t p0 = q * 4;
+  if (p0 >= n_px) return;
+  if (aligned && p0 + 4 <= n_px) {
+    const uint32_t* src = (const uint32_t*)(rgb + p0 * 3);
+    uint32_t a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+    // bytes: a = R0 G0 B0 R1 | b = G1 B1 R2 G2 | c = B2 R3 G3 B3
+    int g0 = gray_of_rgb_page(a & 255, (a >> 8) & 255, (a >> 16) & 255);
+    int g1 = gray_of_rgb_page(a >> 24, b & 255, (b >> 8) & 255);
+    int g2 = gray_of_rgb_page((b >> 16) & 255, b >> 24, c & 255);
+    int g3 = gray_of_rgb_page((c >> 8) & 255, (c >> 16) & 255, c >> 24);
+    *(uint32_t*)(gray + p0) = (uint32_t)g0 | ((uint32_t)g1 << 8) | ((uint32_t)g2 << 16) | ((uint32_t)g3 << 24);
+  } else {
+    for (size_t p = p0; p < p0 + 4 && p < n_px; p++)
+      gray[p] = (uint8_t)gray_of_rgb_page(rgb[3 * p], rgb[3 * p + 1], rgb[3 * p + 2]);
+  }
+}
+
+// cv2.adaptiveThreshold(MEAN_C, BINARY_INV, 31, 21): 64 x 32 output tile, replicate-border halo of 15 in shared memory,
+// separable sliding-window sums (rows: thread = (row, 16-column segment); columns: thread = (column, 8-row segment)).
+#define ADT_W 64
+#define ADT_H 32
+__global__ void __launch_bounds__(256) k_adaptive31(const uint8_t* __restrict__ gray, uint8_t* __restrict__ out, int H, int W) {
+  __shared__ uint8_t s_in[ADT_H + 30][ADT_W + 32];   // 94 used columns, padded row pitch
+  __shared__ uint16_t s_row[ADT_H + 30][ADT_W + 2];  // horizontal 31-sums (<= 7905)
+  const int b = blockIdx.z, x0 = blockIdx.x * ADT_W, y0 = blockIdx.y * ADT_H;
+  const uint8_t* im = gray + (size_t)b * H * W;
+  for (int t = threadIdx.x; t < (ADT_H + 30) * (ADT_W + 30); t += 256) {
+    int ly = t / (ADT_W + 30), lx = t - ly * (ADT_W + 30);
+    int gy = min(max(y0 + ly - 15, 0), H - 1), gx = min(max(x0 + lx - 15, 0), W - 1);
+    s_in[ly][lx] = im[(size_t)gy * W + gx];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < (ADT_H + 30) * 4; t += 256) {
+    int ly = t >> 2, seg = (t & 3) * 16;
+    int acc = 0;
+#pragma unroll
+    for (int k = 0; k < 31; k++) acc += s_in[ly][seg + k];
+    s_row[ly][seg] = (uint16_t)acc;
+#pragma unroll
+    for (int j = 1; j < 16; j++) {
+      acc += (int)s_in[ly][seg + j + 30] - (int)s_in[ly][seg + j - 1];
+      s_row[ly][seg + j] = (uint16_t)acc;
+    }
+  }
+  __syncthreads();
+  {
+    int lx = threadIdx.x & 63, seg = (threadIdx.x >> 6) * 8;
+    int gx = x0 + lx;
+    int acc = 0;
+#pragma unroll
+    for (int k = 0; k < 31; k++) acc += s_row[seg + k][lx];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (j) acc += (int)s_row[seg + j + 30][lx] - (int)s_row[seg + j - 1][lx];
+      int gy = y0 + seg + j;
+      if (gx < W && gy < H) out[(size_t)b * H * W + (size_t)gy * W + gx] = adaptive_inv_31_21(s_in[seg + j + 15][lx + 15], acc);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_image_sum(const uint8_t* __restrict__ img, int n_per_image,
+                                                   unsigned long long* __restrict__ sums) {
+  int b = blockIdx.y;
+  const uint8_t* im = img + (size_t)b * n_per_image;
+  unsigned int local = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_per_image; i += gridDim.x * blockDim.x) local += im[i];
+  for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(&sums[b], (unsigned long long)local);
+}
+
+// counts[box] = number of contours (id order irrelevant) with at least one vertex "near" the box in the reference's
+// sense (:811-846, threshold 10, NO bounding-rectangle pre-test here — :2279-2285), -1 for boxes that are not terminals.
+// One CTA per image, one warp per box; lanes scan a contour's vertices 32 at a time.
+__global__ void __launch_bounds__(1024) k_terminal_counts(const cv_box* __restrict__ boxes, const int32_t* __restrict__ box_offsets,
+                                                          const cv_contour* __restrict__ contours, int max_contours,
+                                                          const int32_t* __restrict__ points, int max_points,
+                                                          const cv_image_result* __restrict__ results, int thresh,
+                                                          int32_t* __restrict__ counts) {
+  int b = blockIdx.x;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int bo = box_offsets[b], nb = box_offsets[b + 1] - bo;
+  int nK = results[b].n_contours;
+  const cv_contour* cts = contours + (size_t)b * max_contours;
+  const int32_t* pts = points + (size_t)b * max_points * 2;
+  for (int bi = warp; bi < nb; bi += 32) {
+    cv_box bx = boxes[bo + bi];
+    int n = -1;
+    if (bx.flags & CV_BOX_IS_TERMINAL) {
+      n = 0;
+      for (int k = 0; k < nK; k++) {
+        const cv_contour& ct = cts[k];
+        const int32_t* cp = pts + (size_t)ct.offset * 2;
+        bool hit = false;
+        for (int v0 = 0; v0 < ct.nverts && !hit; v0 += 32) {
+          int v = v0 + lane;
+          bool near = v < ct.nverts && point_near_box(cp[2 * v], cp[2 * v + 1], bx.xmin, bx.ymin, bx.xmax, bx.ymax, thresh);
+          hit = __ballot_sync(0xffffffffu, near) != 0u;
+        }
+        n += hit ? 1 : 0;
+      }
+    }
+    if (lane == 0) counts[bo + bi] = n;
+  }
+}
+
 }  // namespace cvb
 
 using namespace cvb;
@@ -690,7 +810,7 @@ extern "C" int cv_nodes_analyze(const uint8_t* masks, int B, int H, int W, const
     cvb_next_work(2.0 * (double)n_full);  // read mask + write emptied
     CVB_LAUNCH(k_copy16, dim3(grid), dim3(256), 0, st, (const uint4*)masks, (uint4*)emptied, n16, masks, emptied, n_full);
     if (max_boxes_per_image > 0 && boxes)
-      CVB_LAUNCH(k_zero_boxes, dim3(max_boxes_per_image, B), dim3(256), 0, st, emptied, H, W, boxes, box_offsets);
+      CVB_LAUNCH(k_zero_boxes, dim3(max_boxes_per_image, B), dim3(256), 0, st, emptied, H, W, boxes, box_offsets, 0);
   }
   // a13: each destination row reads two source rows (whole 32-byte sectors when down-scaling < 32x) + writes itself
   cvb_next_work((double)B * h * (2.0 * W + w));
@@ -712,8 +832,8 @@ extern "C" int cv_nodes_analyze(const uint8_t* masks, int B, int H, int W, const
   CVB_LAUNCH((k_ccl_flatten<0, true>), dim3((n_small + 255) / 256, B), dim3(256), 0, st, ws.bin, ws.labels, n_small,
              (int*)nullptr);
   CVB_LAUNCH(k_frame_flags, dim3((2 * w + 2 * h + 255) / 256, B), dim3(256), 0, st, ws.bin, ws.labels, ws.frame, h, w);
-  CVB_LAUNCH(k_list_external, dim3(B), dim3(1024), 0, st, ws.bin, ws.labels, ws.frame, h, w, ws.cand, c.max_external,
-             results);
+  CVB_LAUNCH(k_list_external, dim3(B), dim3(1024), (size_t)h * sizeof(int), st, ws.bin, ws.labels, ws.frame, h, w, ws.cand,
+             c.max_external, results);
   CVB_LAUNCH(k_trace_stats, dim3((c.max_external + 63) / 64, B), dim3(64), 0, st, ws.bin, h, w, ws.cand, c.max_external,
              results, ws.stats);
   CVB_LAUNCH(k_filter_contours, dim3(B), dim3(1024), 0, st, ws.cand, ws.stats, c.max_external, h, w, 0.0004, contours,
@@ -727,6 +847,89 @@ extern "C" int cv_nodes_analyze(const uint8_t* masks, int B, int H, int W, const
     CVB_LAUNCH(k_assemble, dim3((B + 31) / 32), dim3(32), 0, st, boxes, box_offsets, contours, c.max_contours, pairs,
                c.max_pairs, results, B);
   }
+  return CV_OK;
+}
+
+// ------------------------------------------------------------------ terminal reclassification entry point
+struct TermWs {
+  uint8_t* gray; uint8_t* bin; uint8_t* frame; int* labels; int* cand; CandStat* stats; unsigned long long* sums;
+  size_t total;
+};
+
+static TermWs carve_term_ws(void* base, int B, int H, int W, const cv_nodes_caps& c) {
+  TermWs ws;
+  size_t n = (size_t)B * H * W, off = 0;
+  char* p = (char*)base;
+  ws.gray = (uint8_t*)(p + off); off += align256(n);
+  ws.bin = (uint8_t*)(p + off); off += align256(n);
+  ws.frame = (uint8_t*)(p + off); off += align256(n);
+  ws.labels = (int*)(p + off); off += align256(n * 4);
+  ws.cand = (int*)(p + off); off += align256((size_t)B * c.max_external * 4);
+  ws.stats = (CandStat*)(p + off); off += align256((size_t)B * c.max_external * sizeof(CandStat));
+  ws.sums = (unsigned long long*)(p + off); off += align256((size_t)B * 8);
+  ws.total = off;
+  return ws;
+}
+
+extern "C" size_t cv_terminals_workspace_bytes(int B, int H, int W, const cv_nodes_caps* caps) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return carve_term_ws(nullptr, B, H, W, resolve_caps(caps)).total;
+}
+
+extern "C" int cv_terminals_analyze(const uint8_t* pages_rgb, int B, int H, int W, const cv_box* boxes,
+                                    const int32_t* box_offsets, int max_boxes_per_image, int n_boxes_total,
+                                    uint8_t* wire_mask, int32_t* box_counts, cv_contour* contours, int32_t* points,
+                                    cv_image_result* results, const cv_nodes_caps* caps, void* workspace,
+                                    size_t workspace_bytes, void* stream_) {
+  cvb_reset_launches();
+  if (!pages_rgb || !wire_mask || !contours || !points || !results || !box_offsets || !workspace || B <= 0 || H <= 0 || W <= 0)
+    return cvb_fail(CV_ERR_INVALID, "cv_terminals_analyze: null pointer or non-positive size");
+  if (n_boxes_total > 0 && (!boxes || !box_counts)) return cvb_fail(CV_ERR_INVALID, "cv_terminals_analyze: boxes without a count array");
+  if (H > CVB_MAX_ROWS) return cvb_fail(CV_ERR_INVALID, "cv_terminals_analyze: more than 12000 image rows");
+  if ((long long)H * W >= (1ll << 30)) return cvb_fail(CV_ERR_INVALID, "cv_terminals_analyze: image too large");
+  cv_nodes_caps c = resolve_caps(caps);
+  TermWs ws = carve_term_ws(workspace, B, H, W, c);
+  if (workspace_bytes < ws.total) return cvb_fail(CV_ERR_INVALID, "cv_terminals_analyze: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream_;
+  const int n_img = H * W;
+  const size_t n_px = (size_t)B * n_img;
+
+  CVB_LAUNCH(k_init_results, dim3((B + 127) / 128), dim3(128), 0, st, results, ws.sums, B);
+  // segment_circuit (:313-319 via :2231-2234)
+  cvb_next_work(4.0 * (double)n_px);
+  CVB_LAUNCH(k_gray_page, dim3((unsigned)((n_px / 4 + 256) / 256)), dim3(256), 0, st, pages_rgb, ws.gray, n_px,
+             (int)(((uintptr_t)pages_rgb & 3) == 0 && ((uintptr_t)ws.gray & 3) == 0));
+  cvb_next_work(2.0 * (double)n_px);
+  CVB_LAUNCH(k_adaptive31, dim3((W + ADT_W - 1) / ADT_W, (H + ADT_H - 1) / ADT_H, B), dim3(256), 0, st, ws.gray, wire_mask, H, W);
+  // :2238-2249 box masking with NumPy slice semantics
+  if (max_boxes_per_image > 0 && boxes)
+    CVB_LAUNCH(k_zero_boxes, dim3(max_boxes_per_image, B), dim3(256), 0, st, wire_mask, H, W, boxes, box_offsets, 1);
+  // get_contours(prelim_wire_mask, 0.0001) at native resolution (:2252, :388-412)
+  cvb_next_work((double)n_px);
+  CVB_LAUNCH(k_image_sum, dim3(min((n_img + 255) / 256, 148 * 8), B), dim3(256), 0, st, wire_mask, n_img, ws.sums);
+  CVB_LAUNCH(k_binarize, dim3((n_img + 255) / 256, B), dim3(256), 0, st, wire_mask, (uint8_t*)nullptr, ws.bin, n_img, ws.sums,
+             results);
+  CVB_CHECK(cudaMemsetAsync(ws.frame, 0, n_px, st));
+  dim3 cg((W + 31) / 32, (H + 7) / 8, B), cb(32, 8);
+  cvb_next_work(5.0 * (double)n_px);
+  CVB_LAUNCH((k_ccl_init<0, true>), cg, cb, 0, st, ws.bin, ws.labels, H, W);
+  cvb_next_work(5.0 * (double)n_px);
+  CVB_LAUNCH((k_ccl_merge<0, true, 8>), cg, cb, 0, st, ws.bin, ws.labels, H, W);
+  cvb_next_work(9.0 * (double)n_px);
+  CVB_LAUNCH((k_ccl_flatten<0, true>), dim3((n_img + 255) / 256, B), dim3(256), 0, st, ws.bin, ws.labels, n_img, (int*)nullptr);
+  CVB_LAUNCH(k_frame_flags, dim3((2 * W + 2 * H + 255) / 256, B), dim3(256), 0, st, ws.bin, ws.labels, ws.frame, H, W);
+  CVB_LAUNCH(k_list_external, dim3(B), dim3(1024), (size_t)H * sizeof(int), st, ws.bin, ws.labels, ws.frame, H, W, ws.cand,
+             c.max_external, results);
+  CVB_LAUNCH(k_trace_stats, dim3((c.max_external + 63) / 64, B), dim3(64), 0, st, ws.bin, H, W, ws.cand, c.max_external,
+             results, ws.stats);
+  CVB_LAUNCH(k_filter_contours, dim3(B), dim3(1024), 0, st, ws.cand, ws.stats, c.max_external, H, W, 0.0001, contours,
+             c.max_contours, c.max_points, results);
+  CVB_LAUNCH(k_trace_points, dim3((c.max_contours + 63) / 64, B), dim3(64), 0, st, ws.bin, H, W, contours, c.max_contours,
+             c.max_points, results, points);
+  // :2270-2287 contacts of the terminals, threshold 10
+  if (n_boxes_total > 0)
+    CVB_LAUNCH(k_terminal_counts, dim3(B), dim3(1024), 0, st, boxes, box_offsets, contours, c.max_contours, points,
+               c.max_points, results, 10, box_counts);
   return CV_OK;
 }
 

@@ -198,6 +198,18 @@ CV_HD bool centroid_y(long long a00, long long a01, int* cy) {
 
 // reference is_point_near_bbox (circuit_analyzer.py:811-846): inside (inclusive) OR within t of any
 // of the four infinite edge lines.
+// ---------------------------------------------------------------- segment_circuit (circuit_analyzer.py:313-319)
+// cv2.cvtColor(COLOR_RGB2GRAY) on u8: 15-bit fixed point, first channel weighted 0.299 (OpenCV 4.13; exhaustively
+// checked over all 2^24 triples in tests/test_node_prims_cpu.py).
+CV_HD int gray_rgb2gray(int c0, int c1, int c2) { return (c0 * 9798 + c1 * 19235 + c2 * 3735 + 16384) >> 15; }
+// The reference feeds RGB2GRAY a BGR copy of the RGB page (:2231 + :316): in terms of the RGB input the red channel
+// gets the blue coefficient and vice versa.
+CV_HD int gray_of_rgb_page(int r, int g, int b) { return gray_rgb2gray(b, g, r); }
+// cv2.adaptiveThreshold(ADAPTIVE_THRESH_MEAN_C, THRESH_BINARY_INV, 31, 21): mean = boxFilter 31x31 (BORDER_REPLICATE)
+// rounded to nearest (no ties: 961 is odd), foreground where src - mean <= -21.
+CV_HD int box_mean_31(int window_sum) { return (2 * window_sum + 961) / 1922; }
+CV_HD uint8_t adaptive_inv_31_21(int src, int window_sum) { return (src - box_mean_31(window_sum) <= -21) ? 255 : 0; }
+
 CV_HD bool point_near_box(int px, int py, int xmin, int ymin, int xmax, int ymax, int t) {
   if (xmin <= px && px <= xmax && ymin <= py && py <= ymax) return true;
   int dl = px - xmin; dl = dl < 0 ? -dl : dl;

@@ -39,6 +39,7 @@ int cv_device_is_sm100(int device);
 #define CV_BOX_ZERO_IN_MASK 1 /* class not in ('crossover','junction','circuit','vss')  (:1326) */
 #define CV_BOX_IS_COMPONENT 2 /* class not in non_components                           (:51,:1381) */
 #define CV_BOX_IS_SOURCE 4    /* class in source_components                            (:52,:1408) */
+#define CV_BOX_IS_TERMINAL 8  /* class == 'terminal'                                   (:2273)     */
 
 typedef struct cv_box {
   int32_t xmin, ymin, xmax, ymax;     /* int()-truncated mask-space coords            (:1339-1340) */
@@ -100,6 +101,22 @@ int cv_nodes_analyze(const uint8_t* masks, int B, int H, int W, const cv_box* bo
                      int max_boxes_per_image, uint8_t* emptied, uint8_t* resized, uint8_t* enhanced,
                      cv_contour* contours, int32_t* points, cv_pair* pairs, cv_image_result* results,
                      const cv_nodes_caps* caps, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ terminal reclassification
+ * replaces the numeric part of circuit_analyzer.py:2217-2310 (reclassify_terminals_based_on_connectivity) with its
+ * helpers segment_circuit :313-319, get_contours(area_threshold=0.0001) :388-412 and is_point_near_bbox(.., 10) :811-846,
+ * called from analysis_pipeline.py:127 on the full RGB page: B pages [B,H,W,3] u8 ->
+ *   wire_mask [B,H,W] u8   the adaptive-threshold mask after box masking (prelim_wire_mask, :2238-2249)
+ *   box_counts [n_boxes_total] i32   distinct contours with a vertex near the box (-1 for boxes without CV_BOX_IS_TERMINAL);
+ *                                    the caller relabels terminals with a count >= 2 as 'voltage.dc' (:2291)
+ *   contours / points / results      the page's external contours at native resolution (same tables as cv_nodes_analyze;
+ *                                    only n_external, n_contours, n_points, inverted and status are meaningful).
+ * cv_box uses xmin..ymax (page coordinates) and flags CV_BOX_ZERO_IN_MASK | CV_BOX_IS_TERMINAL; H <= 12000.           */
+size_t cv_terminals_workspace_bytes(int B, int H, int W, const cv_nodes_caps* caps);
+int cv_terminals_analyze(const uint8_t* pages_rgb, int B, int H, int W, const cv_box* boxes, const int32_t* box_offsets,
+                         int max_boxes_per_image, int n_boxes_total, uint8_t* wire_mask, int32_t* box_counts,
+                         cv_contour* contours, int32_t* points, cv_image_result* results, const cv_nodes_caps* caps,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* Native-resolution connected-component labelling (BASELINE.json cfg 4; SURVEY §8(d): not a reference code
  * path — oracle is cv2.connectedComponents up to renaming).  labels[p] = 1 + min linear index of p's component,

@@ -136,4 +136,20 @@ int hh_point_near_box(int px, int py, int xmin, int ymin, int xmax, int ymax, in
   return point_near_box(px, py, xmin, ymin, xmax, ymax, t) ? 1 : 0;
 }
 
+// segment_circuit on the RGB page: grey (with the reference's RGB/BGR swap) + adaptive threshold 31 / 21
+void hh_segment_circuit(const uint8_t* rgb, int H, int W, uint8_t* out) {
+  std::vector<int> g((size_t)H * W);
+  for (size_t i = 0; i < (size_t)H * W; i++) g[i] = gray_of_rgb_page(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+  auto cl = [](int v, int n) { return v < 0 ? 0 : (v >= n ? n - 1 : v); };
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+      int s = 0;
+      for (int dy = -15; dy <= 15; dy++)
+        for (int dx = -15; dx <= 15; dx++) s += g[(size_t)cl(y + dy, H) * W + cl(x + dx, W)];
+      out[(size_t)y * W + x] = adaptive_inv_31_21(g[(size_t)y * W + x], s);
+    }
+}
+
+int hh_gray(int c0, int c1, int c2) { return gray_rgb2gray(c0, c1, c2); }
+
 }  // extern "C"

@@ -97,3 +97,24 @@ def test_point_near_box_matches_reference_rule(host_harness):
         t = int(rng.choice([6, 8, 20]))
         b = {"xmin": x0, "ymin": y0, "xmax": x1, "ymax": y1}
         assert bool(host_harness.hh_point_near_box(px, py, x0, y0, x1, y1, t)) == is_point_near_bbox(px, py, b, t)
+
+
+def test_segment_circuit_bit_exact(host_harness):
+    """grey conversion (incl. the reference's RGB/BGR swap, circuit_analyzer.py:2231+316) and the 31/21 adaptive
+    threshold, executed from node_prims.cuh on the host, against cv2."""
+    rng = np.random.default_rng(3)
+    for (h, w) in [(97, 131), (31, 31), (12, 40), (200, 64)]:
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        if h == 200:
+            rgb = cv2.GaussianBlur(rgb, (0, 0), 3)
+        out = np.empty((h, w), np.uint8)
+        host_harness.hh_segment_circuit(rgb.ctypes.data_as(u8p), h, w, out.ctypes.data_as(u8p))
+        bgr = cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR)
+        grey = cv2.cvtColor(bgr, cv2.COLOR_RGB2GRAY)
+        ref = cv2.adaptiveThreshold(grey, 255, cv2.ADAPTIVE_THRESH_MEAN_C, cv2.THRESH_BINARY_INV, 31, 21)
+        assert np.array_equal(out, ref), (h, w)
+    # grey formula on a lattice of triples + random triples
+    tri = rng.integers(0, 256, (4096, 3), dtype=np.uint8)
+    ref = cv2.cvtColor(tri.reshape(64, 64, 3), cv2.COLOR_RGB2GRAY).reshape(-1)
+    got = np.array([host_harness.hh_gray(int(a), int(b), int(c)) for a, b, c in tri], np.uint8)
+    assert np.array_equal(got, ref)
