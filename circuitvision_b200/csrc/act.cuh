@@ -67,5 +67,48 @@ __device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
   up2(fma2(hx, pk2(copysignf(r0, x0), copysignf(r1, x1)), hx), x0, x1);
 }
 
+// GELU for the epilogue-bound fc1 GEMMs whose output is rounded to 16 bits anyway.  ncu (profiles/r1_gemm_gelu_ncu_summary.md):
+// the epilogue warps are ISSUE-bound (472 instructions per 32-column chunk, 336 of them the A&S GELU above); moving the
+// exponential from MUFU to the FMA pipe made it slower (more instructions), so this form minimises the instruction count
+// instead: GELU(x) = x * sigmoid(x * P(min(x^2, 30.25))) with an odd minimax polynomial in the logit,
+// max |error| 2.3e-5 over the whole real line (fit: scripts/fit_gelu_sigmoid.py) — below half an fp16 ulp for every
+// |GELU(x)| > 0.05 and 40x below a bf16 ulp there.  13 instructions per pair instead of 21, 4 MUFU per pair as before.
+// The coefficients carry the factor -log2(e) so that the MUFU computes 2^(-g) directly.
+__device__ __forceinline__ void gelu_sig2(float& x0, float& x1) {
+  const uint64_t x = pk2(x0, x1);
+  float u0, u1;
+  up2(mul2(x, x), u0, u1);
+  const uint64_t u = pk2(fminf(u0, 30.25f), fminf(u1, 30.25f));
+  uint64_t g = fma2(u, pk2(3.8351773e-05f, 3.8351773e-05f), pk2(5.5078946e-04f, 5.5078946e-04f));
+  g = fma2(g, u, pk2(-1.0535588e-01f, -1.0535588e-01f));
+  g = fma2(g, u, pk2(-2.3020522e+00f, -2.3020522e+00f));
+  float a0, a1, e0, e1, d0, d1, r0, r1;
+  up2(mul2(g, x), a0, a1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  up2(fma2(pk2(e0, e1), pk2(1.0f, 1.0f), pk2(1.0f, 1.0f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+  up2(mul2(x, pk2(r0, r1)), x0, x1);
+}
+
+// Same logit polynomial, sigmoid evaluated as 0.5 + 0.5 tanh(g / 2) with ONE MUFU (tanh.approx, relative error 2^-11)
+// per element: |GELU error| <= |x| * 2.5e-4 * |tanh|, below half an fp16 ulp of the result everywhere.
+__device__ __forceinline__ void gelu_tanh2(float& x0, float& x1) {
+  const uint64_t x = pk2(x0, x1);
+  float u0, u1;
+  up2(mul2(x, x), u0, u1);
+  const uint64_t u = pk2(fminf(u0, 30.25f), fminf(u1, 30.25f));
+  // g / 2 with g = x (c1 + c3 u + c5 u^2 + c7 u^3)
+  uint64_t g = fma2(u, pk2(-1.3291712e-05f, -1.3291712e-05f), pk2(-1.9088908e-04f, -1.9088908e-04f));
+  g = fma2(g, u, pk2(3.6513564e-02f, 3.6513564e-02f));
+  g = fma2(g, u, pk2(7.9783049e-01f, 7.9783049e-01f));
+  float a0, a1, t0, t1;
+  up2(mul2(g, x), a0, a1);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a1));
+  const uint64_t hx = mul2(x, pk2(0.5f, 0.5f));
+  up2(fma2(hx, pk2(t0, t1), hx), x0, x1);
+}
 
 }  // namespace cvb

@@ -24,43 +24,47 @@ namespace cvb {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 384;
-constexpr int GEMM_EPI_BUF = 4096;  // one 32 x 32 fp32 box
 constexpr int GEMM_SMEM_MAX = 232448;
 
 // CG = CTAs cooperating on one accumulator tile (cta_group): 1 = 128 x BN per CTA; 2 = a CTA pair computes 256 x BN,
 // each CTA holding its own 128 rows of A and HALF of the B tile, so the operand bytes per CTA and k-block drop from
 // 16 + BN/8 KB to 16 + BN/16 KB — more k-blocks in flight for the same shared memory and less L2->SM traffic per flop,
 // which is what bounds the K >= 384 shapes (ncu: the MMA thread spins on the full barriers, not on the epilogue).
+//
+// EW = epilogue warps (8 or 16).  Every configuration runs 8: 16 warps (640 threads; the 16-bit residual-free epilogues
+// fit 92 registers) were measured on the small-K shapes and changed nothing (profiles/r1_gemm_epilogue_experiments.md) —
+// those epilogues are bound by instruction + MUFU count per element, not by latency hiding.
+// EB = bytes of one 32 x 32 staging box (fp32 4096, 16-bit 2048).
 template <int BN, int CG>
 constexpr int gemm_stage_bytes() { return GEMM_BM * 128 + (BN / CG) * 128; }
-template <int BN, int CG>
-constexpr int gemm_epi_bufs() { return (CG == 2 && BN == 256) ? 1 : 2; }
-template <int BN, int CG>
+template <int BN, int CG, int EW>
+constexpr int gemm_epi_bufs() { return (CG == 2 && BN == 256 && EW == 8) ? 1 : 2; }
+template <int BN, int CG, int EW, int EB>
 constexpr int gemm_stages() {
-  int s = (GEMM_SMEM_MAX - 1024 - 256 - 8 * gemm_epi_bufs<BN, CG>() * GEMM_EPI_BUF) / gemm_stage_bytes<BN, CG>();
+  int s = (GEMM_SMEM_MAX - 1024 - 256 - EW * gemm_epi_bufs<BN, CG, EW>() * EB) / gemm_stage_bytes<BN, CG>();
   return s > 8 ? 8 : (CG == 1 && s > 4 ? 4 : s);
 }
-template <int BN, int CG>
+template <int BN, int CG, int EW, int EB>
 constexpr int gemm_smem_bytes() {
-  return 1024 /*align slack*/ + gemm_stages<BN, CG>() * gemm_stage_bytes<BN, CG>() + 8 * gemm_epi_bufs<BN, CG>() * GEMM_EPI_BUF + 256;
+  return 1024 /*align slack*/ + gemm_stages<BN, CG, EW, EB>() * gemm_stage_bytes<BN, CG>() + EW * gemm_epi_bufs<BN, CG, EW>() * EB + 256;
 }
 
-__device__ __forceinline__ long long gemm_dest_row(const GemmEpilogue& e, int map, long long r) {
+// Row indices fit 32 bits (M is an int and a destination row never exceeds the source row count): the remap runs on
+// 32-bit unsigned divisions — the 64-bit ones cost ~1300 instructions per thread and tile on the windowed proj GEMMs.
+__device__ __forceinline__ long long gemm_dest_row(const GemmEpilogue& e, int map, long long r64) {
   if (map == GEMM_MAP_UNWINDOW) {
-    int w2 = e.ws * e.ws;
-    long long win = r / w2;
-    int t = (int)(r - win * w2);
-    int per_img = e.nwx * e.nwy;
-    long long b = win / per_img;
-    int wi = (int)(win - b * per_img);
-    int wy = wi / e.nwx, wx = wi - wy * e.nwx;
-    int ty = t / e.ws, tx = t - ty * e.ws;
-    int y = wy * e.ws + ty, x = wx * e.ws + tx;
-    if (y >= e.H || x >= e.W) return -1;
-    return (b * e.H + y) * e.W + x;
+    const unsigned r = (unsigned)r64;
+    const unsigned ws = (unsigned)e.ws, w2 = ws * ws;
+    const unsigned win = r / w2, t = r - win * w2;
+    const unsigned per_img = (unsigned)(e.nwx * e.nwy);
+    const unsigned b = win / per_img, wi = win - b * per_img;
+    const unsigned wy = wi / (unsigned)e.nwx, wx = wi - wy * (unsigned)e.nwx;
+    const unsigned ty = t / ws, tx = t - ty * ws;
+    const unsigned y = wy * ws + ty, x = wx * ws + tx;
+    if (y >= (unsigned)e.H || x >= (unsigned)e.W) return -1;
+    return (long long)((b * (unsigned)e.H + y) * (unsigned)e.W + x);
   }
-  return r;
+  return r64;
 }
 
 template <int V>
@@ -71,8 +75,14 @@ __device__ __forceinline__ float apply_act(int act, float x) {
   if (act == GEMM_ACT_RELU) return fmaxf(x, 0.f);
   return x;
 }
+constexpr int GEMM_ACT_GELU_TANH = 4;  // internal: tanh-form GELU for 16-bit outputs, one MUFU per element (act.cuh)
+constexpr int GEMM_ACT_GELU_SIG = 3;  // internal: sigmoid-form GELU for 16-bit outputs (act.cuh)
 __device__ __forceinline__ void apply_act2(int act, float& a, float& b) {
-  if (act == GEMM_ACT_GELU) {
+  if (act == GEMM_ACT_GELU_TANH) {
+    gelu_tanh2(a, b);
+  } else if (act == GEMM_ACT_GELU_SIG) {
+    gelu_sig2(a, b);
+  } else if (act == GEMM_ACT_GELU) {
     gelu_fast2(a, b);
   } else if (act == GEMM_ACT_RELU) {
     a = fmaxf(a, 0.f);
@@ -82,14 +92,17 @@ __device__ __forceinline__ void apply_act2(int act, float& a, float& b) {
 
 // ACT / RES / OUT / MAP / RBA: compile-time epilogue configuration, -1 = read from GemmEpilogue at run time.
 // OUT: 0 = fp32, 1 = bf16, 2 = both (runtime-only).
-template <int BN, int ACT, int RES, int OUT, int MAP, int RBA, int CG>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int ACT, int RES, int OUT, int MAP, int RBA, int CG, int EW>
+__global__ void __launch_bounds__(128 + 32 * EW, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
           const __grid_constant__ CUtensorMap tmap_out, GemmProblem p, GemmEpilogue e) {
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
   static_assert(CG == 1 || CG == 2, "CG");
-  constexpr int GEMM_STAGES = gemm_stages<BN, CG>();
-  constexpr int EPI_BUFS = gemm_epi_bufs<BN, CG>();
+  static_assert(EW == 8 || EW == 16, "EW");
+  constexpr int GEMM_EPI_BUF = (OUT == 1 && MAP == GEMM_MAP_IDENTITY) ? 2048 : 4096;  // 16-bit TMA box or fp32 staging
+  constexpr int GEMM_STAGES = gemm_stages<BN, CG, EW, GEMM_EPI_BUF>();
+  constexpr int EPI_BUFS = gemm_epi_bufs<BN, CG, EW>();
+  static_assert(GEMM_STAGES >= 2, "smem ring");
   constexpr int A_BYTES = GEMM_BM * 128, B_BYTES = (BN / CG) * 128;
   constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   constexpr bool TMA_OUT = (MAP == GEMM_MAP_IDENTITY) && (OUT == 0 || OUT == 1);
@@ -97,8 +110,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + GEMM_STAGES * A_BYTES;
-  uint8_t* epi = smem + GEMM_STAGES * (A_BYTES + B_BYTES);  // [8 warps][EPI_BUFS][4096], 1024-byte aligned
-  uint64_t* bars = (uint64_t*)(epi + 8 * EPI_BUFS * GEMM_EPI_BUF);
+  uint8_t* epi = smem + GEMM_STAGES * (A_BYTES + B_BYTES);  // [EW warps][EPI_BUFS][GEMM_EPI_BUF], 1024-byte aligned
+  uint64_t* bars = (uint64_t*)(epi + EW * EPI_BUFS * GEMM_EPI_BUF);
   uint64_t* full = bars;                     // [STAGES]
   uint64_t* empty = bars + GEMM_STAGES;      // [STAGES]
   uint64_t* tfull = bars + 2 * GEMM_STAGES;  // [2]
@@ -124,7 +137,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
     }
     for (int i = 0; i < 2; i++) {
       tc::mbar_init(&tfull[i], 1);
-      tc::mbar_init(&tempty[i], 8 * CG);  // the leader collects the epilogue warps of both CTAs
+      tc::mbar_init(&tempty[i], EW * CG);  // the leader collects the epilogue warps of both CTAs
     }
     tc::fence_barrier_init();
   }
@@ -197,7 +210,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: 8 warps; warp handles TMEM lanes 32*(warp%4).. and column chunks c with c%2 == ew/4
+    // ===================== epilogue: EW warps; warp handles TMEM lanes 32*(warp%4).. and column chunks c == ew/4 (mod EW/4)
     const int act = pick<ACT>(e.act);
     const bool has_res = pick<RES>(e.res != nullptr) != 0;
     const int map = pick<MAP>(e.map_mode);
@@ -228,7 +241,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
       tc::mbar_wait(&tfull[acc], acc_phase);
       tc::tc_fence_after();
 #pragma unroll 1
-      for (int c = cgroup; c < BN / 32; c += 2) {
+      for (int c = cgroup; c < BN / 32; c += EW / 4) {
         const int col0 = nb * BN + c * 32;
         const int ncols = p.N - col0;  // valid columns of this chunk: >= 32, 16 (N % 32 == 16) or <= 0
         uint8_t* buf = bufs + (nbuf % EPI_BUFS) * GEMM_EPI_BUF;
@@ -378,13 +391,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
   }
 }
 
-template <int BN, int ACT, int RES, int OUT, int MAP, int RBA, int CG = 1>
+template <int BN, int ACT, int RES, int OUT, int MAP, int RBA, int CG = 1, int EW = 8>
 static int launch_cfg(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M, int N, int K,
                       const GemmEpilogue& epi, int num_sms, cudaStream_t st) {
   static bool attr_set = false;
-  constexpr int smem = gemm_smem_bytes<BN, CG>();
+  constexpr int GEMM_THREADS = 128 + 32 * EW;
+  constexpr int smem = gemm_smem_bytes<BN, CG, EW, (OUT == 1 && MAP == GEMM_MAP_IDENTITY) ? 2048 : 4096>();
   static_assert(smem <= GEMM_SMEM_MAX, "shared memory budget");
-  auto kern = k_gemm_tc<BN, ACT, RES, OUT, MAP, RBA, CG>;
+  auto kern = k_gemm_tc<BN, ACT, RES, OUT, MAP, RBA, CG, EW>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cvb_fail_cuda(e, "cudaFuncSetAttribute(k_gemm_tc)");
@@ -414,8 +428,8 @@ static int launch_cfg(const __nv_bfloat16* A, long long lda, const __nv_bfloat16
   cvb_next_work(2.0 * (double)M * (double)N * (double)K);
   if (cvb_profile_on()) {
     char nm[96];
-    snprintf(nm, sizeof(nm), "gemm M%d N%d K%d bn%d%s%s%s%s%s", M, N, K, BN, epi.out_bf16 ? " ->bf16" : "", epi.out_f32 ? " ->f32" : "",
-             epi.res ? " +res" : "", ACT < 0 ? " generic" : "", CG == 2 ? " 2cta" : "");
+    snprintf(nm, sizeof(nm), "gemm M%d N%d K%d bn%d%s%s%s%s%s%s", M, N, K, BN, epi.out_bf16 ? " ->bf16" : "", epi.out_f32 ? " ->f32" : "",
+             epi.res ? " +res" : "", ACT < 0 ? " generic" : "", CG == 2 ? " 2cta" : "", EW == 16 ? " ew16" : "");
     cvb_next_name(nm);
   }
   if (CG == 2) {
@@ -455,13 +469,20 @@ static int launch_bn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16*
     // CTA pairs for the K >= 256 shapes that are bound by operand delivery, not by HBM
     static const bool pairs_on = getenv("CVB_GEMM_PAIRS") ? atoi(getenv("CVB_GEMM_PAIRS")) != 0 : true;
     static const int pair_min_bn = getenv("CVB_PAIR_MINBN") ? atoi(getenv("CVB_PAIR_MINBN")) : 256;
+    // GELU form of the 16-bit-output epilogues (act.cuh): 2 = tanh form (default), 1 = sigmoid form, 0 = A&S erf
+    static const int gelu_form = getenv("CVB_GELU_FORM") ? atoi(getenv("CVB_GELU_FORM")) : 2;
+    const bool gelu_sig = gelu_form == 1, gelu_tanh = gelu_form == 2;
     if (pairs_on && BN >= 128 && BN >= pair_min_bn && K >= 256 && M >= 1024) {
       if (b16 && !res && e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 0, 1, 0, 0, 2>(CVB_GEMM_ARGS);
+      if (b16 && !res && e.act == GEMM_ACT_GELU && gelu_tanh) return launch_cfg<BN, 4, 0, 1, 0, 0, 2>(CVB_GEMM_ARGS);
+      if (b16 && !res && e.act == GEMM_ACT_GELU && gelu_sig) return launch_cfg<BN, 3, 0, 1, 0, 0, 2>(CVB_GEMM_ARGS);
       if (b16 && !res && e.act == GEMM_ACT_GELU) return launch_cfg<BN, 1, 0, 1, 0, 0, 2>(CVB_GEMM_ARGS);
       if (f32 && res && e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 1, 0, 0, 0, 2>(CVB_GEMM_ARGS);
       if (f32 && !res && e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 0, 0, 0, 0, 2>(CVB_GEMM_ARGS);
     }
     if (b16 && !res && e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 0, 1, 0, 0>(CVB_GEMM_ARGS);  // qkv
+    if (b16 && !res && e.act == GEMM_ACT_GELU && gelu_tanh) return launch_cfg<BN, 4, 0, 1, 0, 0>(CVB_GEMM_ARGS);
+    if (b16 && !res && e.act == GEMM_ACT_GELU && gelu_sig) return launch_cfg<BN, 3, 0, 1, 0, 0>(CVB_GEMM_ARGS);
     if (b16 && !res && e.act == GEMM_ACT_GELU) return launch_cfg<BN, 1, 0, 1, 0, 0>(CVB_GEMM_ARGS);  // mlp fc1
     if (f32 && res && e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 1, 0, 0, 0>(CVB_GEMM_ARGS);   // fc2, global proj, tables
     if (f32 && !res && e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 0, 0, 0, 0>(CVB_GEMM_ARGS);  // shortcut, neck
