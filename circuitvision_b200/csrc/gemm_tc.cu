@@ -230,13 +230,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
       const int mb = tm * CG + rank;
       const long long row0 = (long long)mb * GEMM_BM + quad * 32;
       const long long myrow = row0 + lane;
-      long long dest[8];
+      // remapped destination rows: every lane maps its own row once, the row-segment owners fetch it by shuffle
+      // (a destination row index never exceeds the source row count, so it fits an int)
+      int dest[8];
       if (!TMA_OUT) {
+        const int dmine = (myrow < p.M) ? (int)gemm_dest_row(e, map, myrow) : -1;
 #pragma unroll
-        for (int it = 0; it < 8; it++) {
-          long long r = row0 + it * 4 + sub_row;
-          dest[it] = (r < p.M) ? gemm_dest_row(e, map, r) : -1;
-        }
+        for (int it = 0; it < 8; it++) dest[it] = __shfl_sync(0xffffffffu, dmine, it * 4 + sub_row);
       }
       tc::mbar_wait(&tfull[acc], acc_phase);
       tc::tc_fence_after();
