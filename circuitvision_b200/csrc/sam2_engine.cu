@@ -451,7 +451,7 @@ extern "C" int cv_sam2_forward(cv_sam2* h, const void* images, int input_kind, i
     GemmEpilogue e;
     e.res = WF(h, "pos8"); e.ld_res = E; e.res_row_mod = 65536;
     e.out_f32 = X[0]; e.ld_f32 = E;
-    TRY(gemm(h, A, PE_K, WB(h, "pe.w8"), B * 65536, E, PE_K, e, st));
+    TRY(gemm(h, A, PE_K8, WB(h, "pe.w8"), B * 65536, E, PE_K8, e, st));
   } else {
     TRY(launch_im2col_f32((const float*)images, B, 1024, h->f16, A, st));
     GemmEpilogue e;

@@ -88,52 +88,58 @@ int launch_im2col_u8(const uint8_t* img, int B, int S, const float* mean, const 
 // Raw-pixel patch operand: out[tok, k] = fp16/bf16(pixel value) (0..255 is exact in both), zero outside the image and in
 // the K padding.  ToTensor's 1/255 and Normalize's mean/std are folded into the GEMM weights and the per-token additive
 // table at load time (sam2_weights.fold_state_dict: "pe.w8", "pos8").
-// K order of the u8 path: k = ky*21 + kx*3 + c, i.e. the 21 taps of kernel row ky are 21 CONTIGUOUS bytes of the HWC
-// image row.  CTA = 64 consecutive tokens of one token row: the 7 image rows it needs are staged in shared memory with
-// aligned 32-bit loads, converted, and the 64 x 304-byte operand rows (contiguous in global memory) are written with
-// linear 16-byte stores.
-constexpr int IM_TOK = 64, IM_WORDS = 196;  // 195 words cover bytes [12*x0 - 12, 12*x0 + 768)
-__global__ void __launch_bounds__(256) k_im2col_u8raw(const uint8_t* __restrict__ img, int S, int swap_rb, int fp16,
-                                                      __nv_bfloat16* __restrict__ out) {
-  __shared__ uint32_t in[7][IM_WORDS];
-  __shared__ __align__(16) uint16_t outs[IM_TOK * PE_K];
+// K order of the u8 path: k = ky*24 + kx*3 + c (21 taps of kernel row ky + 3 zeros): the 21 taps are 21 CONTIGUOUS bytes
+// of the HWC image row 4y-3+ky starting at byte 12x-9, which is byte 3 of an aligned 32-bit word for every token, and the
+// 24 converted values are three aligned 16-byte stores.  Thread = (token, ky); consecutive threads write consecutive
+// 48-byte pieces of the operand (row pitch 336 B), so the 22 MB/image write stream is fully coalesced.
+// (The previous version — 152-wide rows built element by element through shared memory — was issue-bound at 90 % issue
+// utilisation and 1.1 TB/s: ~30 instructions per element for the index arithmetic; this one needs ~3.)
+template <bool SWAP, bool FP16>
+__global__ void __launch_bounds__(224) k_im2col_u8raw(const uint8_t* __restrict__ img, int S, __nv_bfloat16* __restrict__ out) {
   const int G = S / 4;
-  const int x0 = blockIdx.x * IM_TOK, y = blockIdx.y, b = blockIdx.z;
-  const uint8_t* im = img + (size_t)b * S * S * 3;
-  const int row_words = S * 3 / 4;
-  for (int i = threadIdx.x; i < 7 * 195; i += 256) {
-    const int ky = i / 195, wi = i - ky * 195;
-    const int iy = y * 4 - 3 + ky, gw = 3 * x0 - 3 + wi;  // word index inside the image row
-    uint32_t v = 0u;
-    if (iy >= 0 && iy < S && gw >= 0 && gw < row_words) v = __ldg((const uint32_t*)(im + (size_t)iy * S * 3) + gw);
-    in[ky][wi] = v;
+  const int t = blockIdx.x * 224 + threadIdx.x;  // (token in row, ky), ky fastest
+  const int x = t / 7, ky = t - x * 7;
+  const int y = blockIdx.y, b = blockIdx.z;
+  if (x >= G) return;
+  const int iy = y * 4 - 3 + ky;
+  uint32_t w[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) w[i] = 0u;
+  if (iy >= 0 && iy < S) {
+    const uint32_t* row = (const uint32_t*)(img + ((size_t)b * S + iy) * S * 3);
+    const int w0 = 3 * x - 3;  // word that holds byte 12x - 9 in its top byte
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+      if (w0 + i >= 0) w[i] = __ldg(row + w0 + i);  // only token 0 has words left of the row (pixels -3..-1)
   }
-  __syncthreads();
-  const uint8_t* inb = (const uint8_t*)&in[0][0];
-  for (int e = threadIdx.x; e < IM_TOK * PE_K; e += 256) {
-    const int j = e / PE_K, k = e - j * PE_K;
-    float v = 0.f;
-    if (k < 147) {
-      const int ky = k / 21, t = k - ky * 21;
-      const int kx = t / 3, c = t - kx * 3;
-      // byte (pixel 4*(x0+j) - 3 + kx, channel c) relative to the staged range that starts at byte 12*x0 - 12
-      v = (float)inb[ky * (IM_WORDS * 4) + 12 * j + 3 + 3 * kx + (swap_rb ? 2 - c : c)];
-    }
-    outs[e] = (uint16_t)(tc::pack16(fp16, v, 0.f) & 0xFFFFu);
-  }
-  __syncthreads();
-  const size_t tok0 = ((size_t)b * G + y) * G + x0;
-  uint4* dst = (uint4*)(out + tok0 * PE_K);
-  const uint4* src = (const uint4*)outs;
-  const int n_tok = min(IM_TOK, G - x0);
-  for (int i = threadIdx.x; i < n_tok * PE_K / 8; i += 256) dst[i] = src[i];
+  // byte j of the 21-byte segment -> fp32 by the 2^23 trick (PRMT builds 0x4B0000bb), exact for 0..255
+  auto val = [&](int j) -> float {
+    if (j >= 21) return 0.f;
+    if (SWAP) j = 3 * (j / 3) + 2 - (j % 3);  // BGR input: channel c of pixel kx lives at byte 2 - c
+    const int byte = j + 3;                    // position inside the 24 loaded bytes
+    return __uint_as_float(__byte_perm(w[byte >> 2], 0x4B000000u, 0x7540 + (byte & 3))) - 8388608.0f;
+  };
+  uint32_t o[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) o[i] = tc::pack16(FP16 ? 1 : 0, val(2 * i), val(2 * i + 1));
+  uint4* dst = (uint4*)(out + (((size_t)b * G + y) * G + x) * PE_K8 + ky * 24);
+  dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+  dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
 }
 
 int launch_im2col_u8raw(const uint8_t* img, int B, int S, int swap_rb, int fp16, __nv_bfloat16* out, cudaStream_t st) {
   if (S % 4 || ((uintptr_t)img & 3)) return cvb_fail(CV_ERR_INVALID, "im2col: image side must be a multiple of 4 and 4-byte aligned");
   const int G = S / 4;
-  cvb_next_work((double)B * S * S * 3 + (double)B * G * G * PE_K * 2);
-  CVB_LAUNCH(k_im2col_u8raw, dim3((G + IM_TOK - 1) / IM_TOK, G, B), dim3(256), 0, st, img, S, swap_rb, fp16, out);
+  cvb_next_work((double)B * S * S * 3 + (double)B * G * G * PE_K8 * 2);
+  dim3 grid((G * 7 + 223) / 224, G, B), blk(224);
+  if (swap_rb) {
+    if (fp16) { CVB_LAUNCH((k_im2col_u8raw<true, true>), grid, blk, 0, st, img, S, out); }
+    else { CVB_LAUNCH((k_im2col_u8raw<true, false>), grid, blk, 0, st, img, S, out); }
+  } else {
+    if (fp16) { CVB_LAUNCH((k_im2col_u8raw<false, true>), grid, blk, 0, st, img, S, out); }
+    else { CVB_LAUNCH((k_im2col_u8raw<false, false>), grid, blk, 0, st, img, S, out); }
+  }
   return CV_OK;
 }
 
@@ -960,7 +966,10 @@ int launch_select_mask(const float* masks, const float* iou, const unsigned int*
 // 1024^2 image: Conv2d padding='same' pads the upsampled map with zeros).  Thread = 4 consecutive pixels of a row.
 constexpr int TL = 32, THALO = 5, TUP = TL + 2 * THALO;
 // weights tap-major with the 4 channels of a tap contiguous, so one broadcast LDS.128 feeds 16 FMAs (4 channels x 4
-// pixels); with scalar weight loads the kernel was LSU-bound (one shared-memory wavefront per 4 FMAs)
+// pixels); with scalar weight loads the kernel was LSU-bound (one shared-memory wavefront per 4 FMAs).
+// A packed-fp32x2 (FFMA2) version of this stencil — channel pairs as accumulators, tile stored duplicated — issues
+// half the instructions and runs at the same speed (3.72 vs 3.58 ms for 64 images; ncu: FMA pipe 60 % busy at 4 warps
+// per sub-partition, FFMA2 occupies the pipe for two cycles), so the scalar form stays.
 struct __align__(16) TailConst {
   float4 w3[9], w5[25], w7[49], w11[121];
   float b[16], cw[16], cb;

@@ -12,9 +12,10 @@ namespace cvb {
 // ---- a1 + patch-embed operand: u8 HWC image (already 1024x1024) -> normalised 7x7/stride-4 patches as a
 // two-term bf16 split [B*256*256, 2*PE_K] (hi | lo), K = 147 padded to PE_K.
 constexpr int PE_K = 152;
+constexpr int PE_K8 = 168;  // uint8 path: 7 kernel rows x (21 taps + 3 zeros), see k_im2col_u8raw
 int launch_im2col_u8(const uint8_t* img, int B, int S, const float* mean, const float* inv_std, int swap_rb,
                      __nv_bfloat16* out, cudaStream_t st);
-// raw-pixel variant: out [B*256*256, PE_K] = bf16(pixel value), normalisation folded into "pe.w8" / "pos8"
+// raw-pixel variant: out [B*256*256, PE_K8] = bf16(pixel value), normalisation folded into "pe.w8" / "pos8"
 // Every `fp16` argument below selects IEEE half (saturating conversion) instead of bf16 for the 16-bit operand
 // buffers; the `__nv_bfloat16*` types are then just opaque 16-bit storage.
 int launch_im2col_u8raw(const uint8_t* img, int B, int S, int swap_rb, int fp16, __nv_bfloat16* out, cudaStream_t st);

@@ -37,6 +37,7 @@ VARIANTS = {
 }
 MEAN = (0.485, 0.456, 0.406)  # sam2_infer.py:41-42
 STD = (0.229, 0.224, 0.225)
+PE_K8 = 168  # uint8 patch operand: 7 kernel rows x (21 taps + 3 zeros); must equal csrc/sam2_kernels.cuh PE_K8
 PE_K = 152  # patch-embed K (3*7*7 = 147) padded to a multiple of 8; must equal csrc/sam2_kernels.cuh PE_K
 REFINE_KERNELS = (3, 5, 7, 11)  # the kernel sizes the fused tail kernel is built for (circuit_analyzer.py:218)
 
@@ -277,8 +278,9 @@ def fold_state_dict(sd: dict, variant: dict, use_refinement: bool, operand_dtype
     w4 = g("image_encoder.trunk.patch_embed.proj.weight")  # [E,3,7,7]
     std = torch.tensor(STD, dtype=torch.float64)[None, :, None, None]
     w8 = _bf16(F.pad((w4 / (255.0 * std)).reshape(E, 147), (0, PE_K - 147)))  # K order (c, ky, kx) for the mean term
-    # the uint8 operand is written with K order (ky, kx, c): a kernel row's 21 taps are contiguous bytes of the HWC image
-    out["pe.w8"] = F.pad(w8[:, :147].reshape(E, 3, 7, 7).permute(0, 2, 3, 1).reshape(E, 147), (0, PE_K - 147)).contiguous()
+    # the uint8 operand is written with K order (ky, kx, c), each kernel row padded from 21 to 24 entries: a kernel row's
+    # 21 taps are contiguous bytes of the HWC image and land as three aligned 16-byte stores (k_im2col_u8raw)
+    out["pe.w8"] = F.pad(w8[:, :147].reshape(E, 3, 7, 7).permute(0, 2, 3, 1).reshape(E, 7, 21), (0, 3)).reshape(E, PE_K8).contiguous()
     # the mean term uses the SAME bf16-rounded weights, so the sum equals round(w') . (p - 255 mean): the rounding error
     # stays relative to the normalised pixel value instead of to the raw 0..255 value
     mean_img = (255.0 * torch.tensor(MEAN, dtype=torch.float64))[None, :, None, None].expand(1, 3, 1024, 1024)
