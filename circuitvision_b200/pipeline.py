@@ -2,11 +2,12 @@
 
 This is the call a batch user makes (bench.py's `e2e` number goes through it).  The two hot calls of the reference's
 pipeline (`/root/reference/src/analysis_pipeline.py:206` segment_with_sam2, `:234` get_node_connections) are chained on
-the device: the uint8 mask never visits the host between them.  Host<->device traffic is software-pipelined over three
+the device: the uint8 mask never visits the host between them.  Host<->device traffic is software-pipelined over four
 CUDA streams with `depth` slots in flight:
 
     copy-in stream : H2D of crop batch i+1         (pinned host memory -> slot buffer)
-    compute stream : cv_sam2_forward + cv_nodes_analyze of batch i
+    compute stream : cv_sam2_forward of batch i
+    nodes stream   : cv_nodes_analyze of batch i-1 (small grids, latency-bound border tracers: hides under the forward)
     copy-out stream: D2H of batch i-1's node tables, emptied masks and enhanced images into pinned host buffers
 
 Nothing here computes on the CPU; without libcv_b200.so and an sm_100 device construction raises CvError.
@@ -37,7 +38,7 @@ class _Slot:
         self.h_masks = pin((B, S, S), torch.uint8) if want_images else None
         self.h_emptied = pin((B, S, S), torch.uint8) if want_images else None
         self.h_enhanced = None  # allocated on first use (width depends on the aspect ratio)
-        self.ev_in, self.ev_done, self.ev_out = (torch.cuda.Event() for _ in range(3))
+        self.ev_in, self.ev_mask, self.ev_done, self.ev_out = (torch.cuda.Event() for _ in range(4))
         self.busy = False
         self.result = None
         self.rboxes = None
@@ -73,7 +74,7 @@ class CropPipeline:
         model.set_max_batch(max(model.max_batch, self.B))
         self.points_prefix, self.want_images = points_prefix, want_images
         with torch.cuda.device(self.dev):
-            self.s_in, self.s_compute, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
+            self.s_in, self.s_compute, self.s_nodes, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(4))
             self.slots = [_Slot(self.dev, self.B, self.S, caps, points_prefix, want_images) for _ in range(depth)]
         self._next, self._oldest, self._inflight = 0, 0, 0
         self.h2d_bytes = self.d2h_bytes = 0
@@ -93,13 +94,17 @@ class CropPipeline:
                 s.d_rgb.copy_(host_crops, non_blocking=True)
                 s.ev_in.record(self.s_in)
             with torch.cuda.stream(self.s_compute):
-                d_rec, d_off, rboxes, max_per = s.na.upload_boxes(boxes_list, self.S, self.S)
                 self.s_compute.wait_event(s.ev_in)
                 masks = self.model.segment_batch_u8(s.d_rgb)
                 ext = self.model.last_extents
+                s.ev_mask.record(self.s_compute)
+            with torch.cuda.stream(self.s_nodes):
+                d_rec, d_off, rboxes, max_per = s.na.upload_boxes(boxes_list, self.S, self.S)
+                self.s_nodes.wait_event(s.ev_mask)
                 r = s.na.run(masks, d_rec, d_off, max_per, rboxes)
+                masks.record_stream(self.s_nodes)
                 s.launches = self.model.last_launches + r.launches
-                s.ev_done.record(self.s_compute)
+                s.ev_done.record(self.s_nodes)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(s.ev_done)
                 s.h_results.copy_(r.results, non_blocking=True)
