@@ -554,17 +554,19 @@ extern "C" int cv_sam2_forward(cv_sam2* h, const void* images, int input_kind, i
       }
       rw.cw = WF(h, "refc.w");
       rw.cb = h->refc_b;
+      rw.comp = h->w.count("ref.comp") ? WF(h, "ref.comp") : nullptr;
     } else {
       for (int j = 0; j < 4; j++) { rw.w[j] = nullptr; rw.b[j] = nullptr; }
       rw.cw = nullptr;
       rw.cb = 0.f;
+      rw.comp = nullptr;
     }
     const bool native = (out_h == 1024 && out_w == 1024);
     const bool need_resize = (mask_u8 || out_logits) && !native;
     float* hi = high_res ? high_res : ((need_resize || (out_logits && native)) ? BUF<float>(h, "high") : nullptr);
     if (out_logits && native && !high_res) hi = out_logits;
     TRY(launch_tail(low, 0, B, rw, hi, native ? mask_u8 : nullptr, native ? extents : nullptr, st));
-    h->launches += 1 + (extents && native ? 1 : 0);
+    h->launches += 1 + (extents && native ? 1 : 0) + (rw.use_refine && rw.comp ? 1 : 0);  // k_tail (+ k_init_extents) (+ k_tail_phase)
     if (out_logits && native && high_res)
       CVB_CHECK(cudaMemcpyAsync(out_logits, high_res, (size_t)B * 1024 * 1024 * 4, cudaMemcpyDeviceToDevice, st));
     if (need_resize) {
@@ -614,5 +616,6 @@ extern "C" int cv_sam2_refine(const float* x, int B, const float* const* w, cons
   rw.cw = cw;
   rw.cb = cb;
   rw.use_refine = 1;
+  rw.comp = nullptr;
   return launch_tail(x, 1, B, rw, out, nullptr, nullptr, (cudaStream_t)stream);
 }

@@ -2,6 +2,8 @@
 // (sam2 package modules as called from /root/reference/src/sam2_infer.py:220-275) and sam2_infer.py:29-189.
 #include "sam2_kernels.cuh"
 
+#include <stdlib.h>
+
 #include <math.h>
 
 #include "common.cuh"
@@ -976,9 +978,11 @@ struct __align__(16) TailConst {
 };
 
 __global__ void __launch_bounds__(256) k_tail(const float* __restrict__ low, int src_full, RefineWeights rw, float* __restrict__ high,
-                                              uint8_t* __restrict__ mask, int* __restrict__ extents) {
+                                              uint8_t* __restrict__ mask, int* __restrict__ extents, int border_only) {
   __shared__ __align__(16) float up[TUP][TUP + 2];
   __shared__ TailConst tc_;
+  // the interior tiles belong to k_tail_phase
+  if (border_only && blockIdx.x > 0 && blockIdx.x < gridDim.x - 1 && blockIdx.y > 0 && blockIdx.y < gridDim.y - 1) return;
   const int S = 1024, LS = 256;
   const int b = blockIdx.z;
   const int X0 = blockIdx.x * TL, Y0 = blockIdx.y * TL;
@@ -1112,6 +1116,124 @@ __global__ void __launch_bounds__(256) k_tail(const float* __restrict__ low, int
   }
 }
 
+// Interior of the fused tail on the LOW-RES grid (sam2_weights.refine_phase_tables): away from the image border the
+// composition  conv_k(upsample_x4(low))  is, for each of the 16 output phases (Y % 4, X % 4), one position-independent
+// 5 x 5 stencil on the 256^2 logits — 25 taps x 16 channels = 400 FMA per output pixel instead of 816.
+// CTA = 64 x 32 output pixels = 16 x 8 low-res cells; warp w evaluates phases 2w and 2w+1 (so the composite-weight
+// address is warp-uniform: one broadcast LDS.128 feeds 16 FMAs), lane = cell row x group of 4 cells in a row.
+// The 32 border tiles of each side keep the general kernel above (k_tail, border_only).
+constexpr int TP_W = 64, TP_H = 32, TP_CX = TP_W / 4, TP_CY = TP_H / 4, TP_LD = TP_W + 1;
+__global__ void __launch_bounds__(256, 2) k_tail_phase(const float* __restrict__ low, const float* __restrict__ comp,
+                                                       RefineWeights rw, float* __restrict__ high, uint8_t* __restrict__ mask,
+                                                       int* __restrict__ extents) {
+  __shared__ __align__(16) float s_comp[16 * 25 * 16];
+  __shared__ float s_low[TP_CY + 4][TP_CX + 4 + 1];
+  __shared__ float s_out[TP_H][TP_LD];
+  __shared__ float s_b[16], s_cw[16];
+  const int S = 1024, LS = 256;
+  const int b = blockIdx.z;
+  const int X0 = 32 + blockIdx.x * TP_W, Y0 = 32 + blockIdx.y * TP_H;
+  const int cx0 = X0 >> 2, cy0 = Y0 >> 2;
+  const float* lo = low + (size_t)b * LS * LS;
+  for (int i = threadIdx.x; i < 16 * 25 * 16 / 4; i += 256) ((float4*)s_comp)[i] = __ldg((const float4*)comp + i);
+  for (int i = threadIdx.x; i < (TP_CY + 4) * (TP_CX + 4); i += 256) {
+    const int r = i / (TP_CX + 4), c = i - r * (TP_CX + 4);
+    s_low[r][c] = lo[(cy0 - 2 + r) * LS + cx0 - 2 + c];
+  }
+  if (threadIdx.x < 16) {
+    s_b[threadIdx.x] = rw.b[threadIdx.x >> 2][threadIdx.x & 3];
+    s_cw[threadIdx.x] = rw.cw[threadIdx.x];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cy = lane >> 2, cg = (lane & 3) * 4;
+  float win[5][8];  // low-res rows cy-2 .. cy+2, columns cg-2 .. cg+5 of the tile
+#pragma unroll
+  for (int tu = 0; tu < 5; tu++)
+#pragma unroll
+    for (int c = 0; c < 8; c++) win[tu][c] = s_low[cy + tu][cg + c];
+#pragma unroll 1
+  for (int ph = 0; ph < 2; ph++) {
+    const int p = warp * 2 + ph;
+    const int py = p >> 2, px = p & 3;
+    const float4* T = (const float4*)s_comp + p * 25 * 4;
+    float acc[16][4];
+#pragma unroll
+    for (int c = 0; c < 16; c++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[c][j] = 0.f;
+#pragma unroll
+    for (int tu = 0; tu < 5; tu++)
+#pragma unroll
+      for (int tv = 0; tv < 5; tv++) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const float4 w = T[(tu * 5 + tv) * 4 + q];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const float v = win[tu][j + tv];
+            acc[4 * q + 0][j] = fmaf(w.x, v, acc[4 * q + 0][j]);
+            acc[4 * q + 1][j] = fmaf(w.y, v, acc[4 * q + 1][j]);
+            acc[4 * q + 2][j] = fmaf(w.z, v, acc[4 * q + 2][j]);
+            acc[4 * q + 3][j] = fmaf(w.w, v, acc[4 * q + 3][j]);
+          }
+        }
+      }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float o = rw.cb;
+#pragma unroll
+      for (int c = 0; c < 16; c += 2) {
+        float g0 = acc[c][j] + s_b[c], g1 = acc[c + 1][j] + s_b[c + 1];
+        gelu_fast2(g0, g1);
+        o = fmaf(s_cw[c], g0, o);
+        o = fmaf(s_cw[c + 1], g1, o);
+      }
+      s_out[cy * 4 + py][(cg + j) * 4 + px] = o;
+    }
+  }
+  __syncthreads();
+  // write-out: thread = 8 consecutive pixels of one tile row
+  const int ty = threadIdx.x >> 3, tx = (threadIdx.x & 7) * 8;
+  const int Y = Y0 + ty, X = X0 + tx;
+  const size_t o = ((size_t)b * S + Y) * S + X;
+  float r[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) r[k] = s_out[ty][tx + k];
+  if (high) {
+    *(float4*)(high + o) = make_float4(r[0], r[1], r[2], r[3]);
+    *(float4*)(high + o + 4) = make_float4(r[4], r[5], r[6], r[7]);
+  }
+  if (mask) {
+    uint32_t m0 = 0, m1 = 0;
+    int xmin = INT_MAX, xmax = -1;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (r[k] > 0.0f) {
+        if (k < 4) m0 |= 0xFFu << (8 * k);
+        else m1 |= 0xFFu << (8 * (k - 4));
+        xmin = min(xmin, X + k);
+        xmax = max(xmax, X + k);
+      }
+    *(uint2*)(mask + o) = make_uint2(m0, m1);
+    if (extents) {
+      int ymin = xmax >= 0 ? Y : INT_MAX, ymax = xmax >= 0 ? Y : -1;
+      for (int k = 16; k; k >>= 1) {
+        xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, k));
+        xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, k));
+        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, k));
+        ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, k));
+      }
+      if ((threadIdx.x & 31) == 0 && xmax >= 0) {
+        atomicMin(extents + 4 * b, xmin);
+        atomicMin(extents + 4 * b + 1, ymin);
+        atomicMax(extents + 4 * b + 2, xmax);
+        atomicMax(extents + 4 * b + 3, ymax);
+      }
+    }
+  }
+}
+
 __global__ void k_init_extents(int* e, int B) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) { e[4 * i] = INT_MAX; e[4 * i + 1] = INT_MAX; e[4 * i + 2] = -1; e[4 * i + 3] = -1; }
@@ -1121,7 +1243,14 @@ int launch_tail(const float* low_res, int src_full, int B, const RefineWeights& 
                 int* extents, cudaStream_t st) {
   if (extents) CVB_LAUNCH(k_init_extents, dim3((B + 127) / 128), dim3(128), 0, st, extents, B);
   cvb_next_work((double)B * (256.0 * 256 * 4 + 1024.0 * 1024 * ((high_res ? 4 : 0) + (mask_u8 ? 1 : 0))));
-  CVB_LAUNCH(k_tail, dim3(1024 / TL, 1024 / TL, B), dim3(256), 0, st, low_res, src_full, rw, high_res, mask_u8, extents);
+  // low-res source + refinement: interior on the phase tables, the one-tile border frame on the general stencil
+  static const bool phase_on = getenv("CVB_TAIL_PHASE") ? atoi(getenv("CVB_TAIL_PHASE")) != 0 : true;
+  const bool phase = phase_on && !src_full && rw.use_refine && rw.comp != nullptr;
+  CVB_LAUNCH(k_tail, dim3(1024 / TL, 1024 / TL, B), dim3(256), 0, st, low_res, src_full, rw, high_res, mask_u8, extents,
+             phase ? 1 : 0);
+  if (phase)
+    CVB_LAUNCH(k_tail_phase, dim3((1024 - 64) / TP_W, (1024 - 64) / TP_H, B), dim3(256), 0, st, low_res, rw.comp, rw, high_res,
+               mask_u8, extents);
   return CV_OK;
 }
 

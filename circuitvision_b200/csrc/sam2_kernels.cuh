@@ -79,6 +79,7 @@ struct RefineWeights {
   const float* cw;     // [16]
   float cb;
   int use_refine;
+  const float* comp = nullptr;  // [16 phases][25 taps][16 channels] composite low-res stencils ("ref.comp"), optional
 };
 // src_full = 1: `low_res` is already a [B,1,1024,1024] map (no upsample; MultiKernelRefinement.forward alone)
 int launch_tail(const float* low_res, int src_full, int B, const RefineWeights& rw, float* high_res, uint8_t* mask_u8, int* extents,

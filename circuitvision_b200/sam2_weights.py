@@ -249,6 +249,44 @@ def _attn_tokens(q, k, v, heads):
     return (a @ vh).transpose(0, 1).reshape(T, -1)
 
 
+def upsample4_taps(rel: int):
+    """Bilinear x4 (align_corners=False) away from the borders: output row 4*Y0 + rel reads low-res rows Y0 + i0 and
+    Y0 + i0 + 1 with weights (1 - f, f); src = (4 Y0 + rel + 0.5) / 4 - 0.5 = Y0 + (rel - 1.5) / 4."""
+    t = (rel - 1.5) / 4.0
+    i0 = int(np.floor(t))
+    return i0, t - i0
+
+
+def refine_phase_tables(branch_weights) -> torch.Tensor:
+    """Composite weights of  conv_k( upsample_x4(low) )  for the interior of the image, where the composition is a
+    position-independent 5 x 5 stencil on the LOW-RES grid for each of the 16 output phases (py, px) = (Y % 4, X % 4):
+
+        Z[a,c][4 Y0 + py][4 X0 + px] = sum_{tu,tv} T[py,px][tu,tv][a*4+c] * low[Y0 - 2 + tu][X0 - 2 + tv]
+
+    (every tap dy in [-5,5] of the widest 11 x 11 branch reads low-res rows Y0-2 .. Y0+2; phases 0 and 3 leave one
+    border row of the window at zero).  204 taps per channel group collapse to 25: csrc/sam2_kernels.cu k_tail_phase.
+    Evaluated in float64.  branch_weights: four [4,k,k] tensors (k = 3,5,7,11).
+    Returns [16 phases, 25 taps, 16 channels] float32."""
+    T = np.zeros((4, 4, 5, 5, 16), np.float64)  # [py][px][tu][tv][ch]
+    for a, w in enumerate(branch_weights):
+        w = np.asarray(w.detach().cpu().double().numpy()) if hasattr(w, "detach") else np.asarray(w, np.float64)
+        k = w.shape[-1]
+        r = (k - 1) // 2
+        B = np.zeros((4, k, 5))  # [phase][tap d + r][window position]
+        for p in range(4):
+            for d in range(-r, r + 1):
+                i0, f = upsample4_taps(p + d)
+                for ii, wt in ((i0, 1.0 - f), (i0 + 1, f)):
+                    if wt != 0.0:
+                        assert 0 <= ii + 2 < 5, (p, d, ii)
+                        B[p, d + r, ii + 2] += wt
+        for py in range(4):
+            for px in range(4):
+                for c in range(4):
+                    T[py, px, :, :, a * 4 + c] = B[py].T @ w[c] @ B[px]
+    return torch.from_numpy(T.reshape(16, 25, 16)).float()
+
+
 def fold_state_dict(sd: dict, variant: dict, use_refinement: bool, operand_dtype=torch.bfloat16) -> dict:
     """Wrapper state dict (keys `sam2_model.…`, `dense_embedding1/2`, `sparse_embedding`, `refinement_layer.…`)
     -> {engine tensor name: contiguous CPU tensor (float32, or `operand_dtype` for tensor-core operands)}.
@@ -385,6 +423,7 @@ def fold_state_dict(sd: dict, variant: dict, use_refinement: bool, operand_dtype
                                  f"kernel sizes {REFINE_KERNELS} with 4 channels per branch")
             out[f"ref{j}.w"] = _f32(wj.reshape(4, k, k))
             out[f"ref{j}.b"] = _f32(sd[f"refinement_layer.conv_branches.{j}.bias"].detach().cpu())
+        out["ref.comp"] = _f32(refine_phase_tables([out[f"ref{j}.w"] for j in range(4)]))
         out["refc.w"] = _f32(sd["refinement_layer.combiner_conv.weight"].detach().cpu().reshape(16))
         out["refc.b"] = _f32(sd["refinement_layer.combiner_conv.bias"].detach().cpu().reshape(1))
     return out
