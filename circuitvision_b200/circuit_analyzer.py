@@ -81,6 +81,17 @@ class CircuitAnalyzer:
             _terminals.apply_reclassification(boxes, r.counts(b), self.class_names)
         return r
 
+    # ------------------------------------------------------------------ netlist lines
+    def generate_netlist_from_nodes(self, node_list):
+        """Reference :1607 — host bookkeeping on the node table (circuitvision_b200/netlist.py)."""
+        from . import netlist as _netlist
+        return _netlist.generate_netlist_from_nodes(node_list)
+
+    def stringify_line(self, netlist_line):
+        """Reference :1909."""
+        from . import netlist as _netlist
+        return _netlist.stringify_line(netlist_line)
+
     # ------------------------------------------------------------------ node analysis
     def _na(self):
         if self._node_analyzer is None:

@@ -47,6 +47,10 @@ def test_golden_fixtures_from_unmodified_reference(analyzer, golden, golden_case
             assert np.array_equal(n["contour"].reshape(-1, 2), z[f"{name}/contour{gn['id']}"]), name
             assert n["contour"].dtype == np.int32 and n["contour"].shape[1:] == (1, 2)
         assert cviz.shape == enhanced.shape + (3,) and fviz.shape == cviz.shape and pviz.shape == cviz.shape
+        # netlist connectivity: the drop-in's own generate_netlist_from_nodes / stringify_line on the device-produced
+        # node table against the text the unmodified reference printed for this case
+        text = "\n".join(analyzer.stringify_line(l) for l in analyzer.generate_netlist_from_nodes(nodes))
+        assert text == g["netlist"], name
 
 
 def test_oracle_parity_fresh_seeds(analyzer):
