@@ -433,6 +433,18 @@ def main():
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"}
         roofline["avg_launch_us"] = avg_s * 1e6
         roofline["share_of_step"] = top["ms"] / tot
+        # DRAM bytes per launch of that kernel from the committed ncu pass of this same command (profiles/), when the
+        # workload matches the one that was profiled
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic_pipeline_b64.json")))
+            k = tr["kernels"].get(top["name"])
+            if k and workload == "pipeline" and B == 64 and a.variant == "tiny" and S == 1024:
+                roofline["traffic"] = k["traffic_bytes_per_launch"]
+                roofline["traffic_source"] = "profiles/r1_ncu_traffic_pipeline_b64.json (ncu dram__bytes_read+write, per launch)"
+                if tensor:
+                    roofline["traffic_GBps"] = k["traffic_bytes_per_launch"] / avg_s / 1e9
+        except Exception:
+            pass
 
     # ---- CPU baseline on this box's host cores (bounded sample)
     cpu = None
