@@ -197,6 +197,26 @@ def workload_name(workload, a):
     return f"node analysis only: {a.batch} wire masks {a.size}^2 (SAM2 stage excluded), per GPU"
 
 
+def _shape_row(r, steps, tens_peak, hbm_peak):
+    """One launch group of the timed region: achieved rate and — for GEMM shapes, whose algorithmic bytes follow from the
+    shape tag — its fraction of BOTH rooflines (most encoder GEMMs at K <= 192 are HBM-bound, not tensor-bound)."""
+    import re
+    row = {"name": r["name"], "launches": r["launches"], "ms_per_step": r["ms"] / steps,
+           "rate_T_per_s": r["work"] / max(r["ms"], 1e-9) / 1e9}
+    m = re.match(r"gemm M(\d+) N(\d+) K(\d+) bn\d+(.*)", r["name"])
+    if m:
+        M, N, K = (int(x) for x in m.groups()[:3])
+        tag = m.group(4)
+        byts = M * K * 2 + N * K * 2 + M * N * (2 if "->b" in tag else 4) + (M * N * 4 if "+r" in tag else 0)
+        sec = r["ms"] / 1e3 / max(1, r["launches"])
+        row["tensor_frac"] = 2.0 * M * N * K / sec / 1e12 / tens_peak
+        row["hbm_frac"] = byts / sec / 1e9 / hbm_peak
+        row["bound"] = "hbm" if row["hbm_frac"] > row["tensor_frac"] else "tensor"
+    elif r["name"].startswith("attn"):
+        row["tensor_frac"] = row["rate_T_per_s"] / tens_peak
+    return row
+
+
 # ------------------------------------------------------------------------------------------ GPU side
 def main():
     a = _args()
@@ -315,16 +335,25 @@ def main():
         step_resident(i)
     torch.cuda.synchronize()
 
+    # `value`: K steps with nothing but the kernels on the streams.  The per-kernel table (roofline.achieved) comes from a
+    # second, identical K-step region in which every launch is bracketed by CUDA events on its own stream
+    # (cv_profile_*): the brackets cost a few percent of the step, so they stay out of the headline region; the profiled
+    # region's own ms/step is reported next to it (`profiled_ms_per_step`).
     prof = not a.no_profile
-    lib.cv_profile_reset()
-    lib.cv_profile_enable(1 if prof else 0)
+    lib.cv_profile_enable(0)
     clocks = ClockSampler(local) if rank == 0 else None
     total_ms = timed(step_resident, a.steps)
     clk = clocks.stop() if clocks else None
-    lib.cv_profile_enable(0)
-    table = _lib.profile_table() if prof else []
     imgs = B * a.steps * world
     value = imgs / (total_ms / 1e3)
+    prof_ms = None
+    table = []
+    if prof:
+        lib.cv_profile_reset()
+        lib.cv_profile_enable(1)
+        prof_ms = timed(step_resident, a.steps)
+        lib.cv_profile_enable(0)
+        table = _lib.profile_table()
 
     # ---- e2e through the public API with host buffers
     h2d = d2h = 0
@@ -411,7 +440,7 @@ def main():
             f["launches"] += r["launches"]
             f["ms"] += r["ms"]
             f["work"] += r["work"]
-        shapes = sorted(table, key=lambda r: -r["ms"])[:8]
+        shapes = sorted(table, key=lambda r: -r["ms"])[:16]
         table = list(folded.values())
         tot = sum(r["ms"] for r in table) or 1.0
         for r in sorted(table, key=lambda r: -r["ms"]):
@@ -474,12 +503,12 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
         "gpu_launches": int(launches_per_step[0] * a.steps),
+        "profiled_ms_per_step": (prof_ms / a.steps) if prof_ms else None,
         "clocks": clk,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "kernels": kern_rows[:12],
-        "top_shapes": [{"name": r["name"], "launches": r["launches"], "ms_per_step": r["ms"] / a.steps,
-                        "rate_T_per_s": r["work"] / max(r["ms"], 1e-9) / 1e9} for r in shapes] if table else [],
+        "top_shapes": [_shape_row(r, a.steps, tens_peak, hbm_peak) for r in shapes] if table else [],
     }
     print(json.dumps(line))
     if world > 1:

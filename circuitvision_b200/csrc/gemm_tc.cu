@@ -516,6 +516,9 @@ int gemm_tc_launch(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W
   }
   if (N % 256 == 0 && K >= 256 && M >= 1024) return launch_bn<256>(A, lda, W, ldw, M, N, K, epi, num_sms, st);
   if (N % 192 == 0) return launch_bn<192>(A, lda, W, ldw, M, N, K, epi, num_sms, st);
+  // Hiera base+ widths (112 << s): 224 / 448 / 896 columns are whole 224-wide tiles (they used to fall to 64- or even
+  // 32-wide tiles: 26 % of the tensor peak on the base+ fc2 GEMM)
+  if (N % 224 == 0) return launch_bn<224>(A, lda, W, ldw, M, N, K, epi, num_sms, st);
   if (N % 128 == 0) return launch_bn<128>(A, lda, W, ldw, M, N, K, epi, num_sms, st);
   if (N % 96 == 0) return launch_bn<96>(A, lda, W, ldw, M, N, K, epi, num_sms, st);
   if (N % 64 == 0) return launch_bn<64>(A, lda, W, ldw, M, N, K, epi, num_sms, st);

@@ -569,6 +569,11 @@ __global__ void __launch_bounds__(256) k_tok_linear(const float* __restrict__ A,
 int launch_tok_linear(const float* A, long long lda, const float* W, const float* bias, int R, int N, int K, int act,
                       const float* res, long long ld_res, float* C, long long ldc, cudaStream_t st) {
   cvb_next_work(2.0 * R * (double)N * K);
+  if (cvb_profile_on()) {
+    char nm[64];
+    snprintf(nm, sizeof(nm), "tok_linear R%d N%d K%d act%d", R, N, K, act);
+    cvb_next_name(nm);
+  }
   CVB_LAUNCH(k_tok_linear, dim3((N + 63) / 64, (R + 63) / 64), dim3(256), 0, st, A, lda, W, bias, R, N, K, act, res, ld_res,
              C, ldc);
   return CV_OK;
