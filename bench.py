@@ -335,25 +335,19 @@ def main():
         step_resident(i)
     torch.cuda.synchronize()
 
-    # `value`: K steps with nothing but the kernels on the streams.  The per-kernel table (roofline.achieved) comes from a
-    # second, identical K-step region in which every launch is bracketed by CUDA events on its own stream
-    # (cv_profile_*): the brackets cost a few percent of the step, so they stay out of the headline region; the profiled
-    # region's own ms/step is reported next to it (`profiled_ms_per_step`).
+    # Every launch of the timed region is bracketed by CUDA events on its own stream (cv_profile_*): the kernel table and
+    # roofline.achieved come from the SAME K steps that give `value` (the brackets cost < 1 % of the step: 50.9 vs 51.4 ms
+    # measured with and without them, profiles/README.md).
     prof = not a.no_profile
-    lib.cv_profile_enable(0)
+    lib.cv_profile_reset()
+    lib.cv_profile_enable(1 if prof else 0)
     clocks = ClockSampler(local) if rank == 0 else None
     total_ms = timed(step_resident, a.steps)
     clk = clocks.stop() if clocks else None
+    lib.cv_profile_enable(0)
+    table = _lib.profile_table() if prof else []
     imgs = B * a.steps * world
     value = imgs / (total_ms / 1e3)
-    prof_ms = None
-    table = []
-    if prof:
-        lib.cv_profile_reset()
-        lib.cv_profile_enable(1)
-        prof_ms = timed(step_resident, a.steps)
-        lib.cv_profile_enable(0)
-        table = _lib.profile_table()
 
     # ---- e2e through the public API with host buffers
     h2d = d2h = 0
@@ -503,7 +497,6 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
         "gpu_launches": int(launches_per_step[0] * a.steps),
-        "profiled_ms_per_step": (prof_ms / a.steps) if prof_ms else None,
         "clocks": clk,
         "roofline": roofline,
         "cpu_baseline": cpu,
