@@ -35,7 +35,9 @@ def _args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "pipeline", "nodes", "nodes4096", "sam2"])
-    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=None,
+                    help="images per GPU per step (default 64; 256 for nodes4096, whose border walks are latency-bound "
+                         "chains that only a larger batch amortises)")
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--variant", default="tiny")
     ap.add_argument("--chunk", type=int, default=64, help="crops per SAM 2.1 engine pass (workspace is sized for this many)")
@@ -225,6 +227,8 @@ def main():
         workload = "pipeline" if have_sam2() else "nodes"
     if workload == "nodes4096":
         a.size = 4096
+    if a.batch is None:
+        a.batch = 256 if workload == "nodes4096" else 64
     if a.impl == "reference":
         return run_reference(a, workload)
 

@@ -597,20 +597,18 @@ template <int D>
 static int attn_launch_d(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, bool glob,
                          cudaStream_t st) {
   if (glob) {
-    static bool attr_set_g = false;
-    if (!attr_set_g) {
+    static std::atomic<unsigned long long> attr_set_g{0};
+    if (cvb_once_per_device(attr_set_g)) {
       cudaError_t e = cudaFuncSetAttribute(k_attn_global<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, ag_smem<D>());
       if (e != cudaSuccess) return cvb_fail_cuda(e, "cudaFuncSetAttribute(k_attn_global)");
-      attr_set_g = true;
     }
     CVB_LAUNCH((k_attn_global<D>), dim3(p.Mq / (2 * ATT_BM), p.heads), dim3(AG_THREADS), ag_smem<D>(), st, tq, tk, tv, p);
     return CV_OK;
   }
-  static bool attr_set_w = false;
-  if (!attr_set_w) {
+  static std::atomic<unsigned long long> attr_set_w{0};
+  if (cvb_once_per_device(attr_set_w)) {
     cudaError_t e = cudaFuncSetAttribute(k_attn_win<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, aw_smem<D>());
     if (e != cudaSuccess) return cvb_fail_cuda(e, "cudaFuncSetAttribute(k_attn_win)");
-    attr_set_w = true;
   }
   const int n_items = ((p.Mq + ATT_BM - 1) / ATT_BM) * p.heads;
   const int n_pairs = (n_items + 1) / 2;

@@ -409,12 +409,11 @@ static int ccl_run(const uint8_t* masks, int B, int H, int W, int32_t* labels, i
   dim3 tg((W + CT_W - 1) / CT_W, (H + CT_H - 1) / CT_H, B);
   const double px = (double)B * H * W;
   cvb_next_work(5.0 * px);
-  static bool carveout_set = false;
-  if (!carveout_set) {
+  static std::atomic<unsigned long long> carveout_set{0};
+  if (cvb_once_per_device(carveout_set)) {
     // 12 resident tiles x ~9.7 KB: ask for the large shared-memory split (the default heuristic left room for 6)
     CVB_CHECK(cudaFuncSetAttribute(k_ccl_tile_label<CONN>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                    cudaSharedmemCarveoutMaxShared));
-    carveout_set = true;
   }
   CVB_LAUNCH((k_ccl_tile_label<CONN>), tg, dim3(CT_THREADS), 0, st, masks, labels, H, W, vec_ok, dirty, n_components, partial);
   const long long seam_px = max((long long)((H - 1) / CT_H) * W, (long long)((W - 1) / CT_W) * H);

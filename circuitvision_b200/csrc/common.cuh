@@ -37,3 +37,14 @@ void cvb_next_name(const char* name);
     if (_e != cudaSuccess) return cvb_fail_cuda(_e, "launch " #kernel);    \
     cvb_count_launch();                                                    \
   } while (0)
+
+// Function attributes (dynamic shared-memory size, carve-out) are per DEVICE: a process that drives several GPUs must set
+// them once on each.  `mask` is a function-local static; returns true the first time it is called on the current device.
+#include <atomic>
+inline bool cvb_once_per_device(std::atomic<unsigned long long>& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  return (mask.fetch_or(bit) & bit) == 0;
+}
+

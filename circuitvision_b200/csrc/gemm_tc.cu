@@ -394,15 +394,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
 template <int BN, int ACT, int RES, int OUT, int MAP, int RBA, int CG = 1, int EW = 8>
 static int launch_cfg(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M, int N, int K,
                       const GemmEpilogue& epi, int num_sms, cudaStream_t st) {
-  static bool attr_set = false;
+  static std::atomic<unsigned long long> attr_set{0};
   constexpr int GEMM_THREADS = 128 + 32 * EW;
   constexpr int smem = gemm_smem_bytes<BN, CG, EW, (OUT == 1 && MAP == GEMM_MAP_IDENTITY) ? 2048 : 4096>();
   static_assert(smem <= GEMM_SMEM_MAX, "shared memory budget");
   auto kern = k_gemm_tc<BN, ACT, RES, OUT, MAP, RBA, CG, EW>;
-  if (!attr_set) {
+  if (cvb_once_per_device(attr_set)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cvb_fail_cuda(e, "cudaFuncSetAttribute(k_gemm_tc)");
-    attr_set = true;
   }
   CUtensorMap ta, tw, to;
   if (!tc_host::make_tmap_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM) ||

@@ -142,18 +142,25 @@ __global__ void __launch_bounds__(256) k_enhance(const uint8_t* __restrict__ src
 }
 
 // a15 prelude: mean>127 inversion, 255->1 mutation of the returned array, binary image for contouring
+// Also emits the binary image as BITS in flat pixel order (bit i of the image = pixel i, 32 per word): the border
+// tracers keep that copy in shared memory (600 x 600 pixels = 45 KB).
 __global__ void k_binarize(const uint8_t* __restrict__ enh_raw, uint8_t* __restrict__ enhanced_out,
                            uint8_t* __restrict__ bin, int n_per_image, const unsigned long long* __restrict__ sums,
-                           cv_image_result* __restrict__ results) {
+                           cv_image_result* __restrict__ results, uint32_t* __restrict__ bits, int words_per_image) {
   int b = blockIdx.y;
   bool inv = sums[b] > 127ull * (unsigned long long)n_per_image;  // cv2.mean(img)[0] > 127
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) results[b].inverted = inv ? 1 : 0;
-  if (i >= n_per_image) return;
-  size_t p = (size_t)b * n_per_image + i;
-  uint8_t v = enh_raw[p];
-  if (enhanced_out) enhanced_out[p] = inv ? v : (v == 255 ? (uint8_t)1 : v);
-  bin[p] = inv ? (uint8_t)(v != 255) : (uint8_t)(v != 0);
+  bool f = false;
+  if (i < n_per_image) {
+    size_t p = (size_t)b * n_per_image + i;
+    uint8_t v = enh_raw[p];
+    if (enhanced_out) enhanced_out[p] = inv ? v : (v == 255 ? (uint8_t)1 : v);
+    f = inv ? (v != 255) : (v != 0);
+    bin[p] = (uint8_t)f;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, f);
+  if (bits && (threadIdx.x & 31) == 0 && (i >> 5) < words_per_image) bits[(size_t)b * words_per_image + (i >> 5)] = m;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -358,6 +365,64 @@ __global__ void k_trace_stats(const uint8_t* __restrict__ bin, int h, int w, con
   cs.xmin = st.xmin; cs.ymin = st.ymin; cs.xmax = st.xmax; cs.ymax = st.ymax; cs.pad = 0;
   cs.a00 = st.a00; cs.a01 = st.a01;
   stats[(size_t)b * max_external + i] = cs;
+}
+
+// Shared-memory variants of the two border walks: the walk is a chain of dependent neighbour probes (latency-bound,
+// one thread per component), so each CTA first copies the image's BIT plane into shared memory and probes there
+// (~25 cycles instead of an L2 round trip per probe).  TRACE_CTAS CTAs per image share its candidates.
+constexpr int TRACE_CTAS = 8, TRACE_THREADS = 128;
+struct BitFg {
+  const uint32_t* bits;
+  int w, h;
+  __device__ __forceinline__ bool operator()(int x, int y) const {
+    if ((unsigned)x >= (unsigned)w || (unsigned)y >= (unsigned)h) return false;
+    const unsigned idx = (unsigned)y * (unsigned)w + (unsigned)x;
+    return (bits[idx >> 5] >> (idx & 31)) & 1u;
+  }
+};
+__device__ __forceinline__ void load_bits_to_smem(uint32_t* sm, const uint32_t* __restrict__ g, int words) {
+  for (int i = threadIdx.x; i < words / 4; i += blockDim.x) ((uint4*)sm)[i] = __ldg((const uint4*)g + i);
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_stats_bits(const uint32_t* __restrict__ bits, int words_per_image,
+                                                                    int h, int w, const int* __restrict__ cand,
+                                                                    int max_external,
+                                                                    const cv_image_result* __restrict__ results,
+                                                                    CandStat* __restrict__ stats) {
+  extern __shared__ __align__(16) uint32_t s_bits[];
+  const int b = blockIdx.y;
+  const int n = results[b].n_external;
+  if ((int)(blockIdx.x * TRACE_THREADS) >= n) return;  // whole CTA: nothing to walk
+  load_bits_to_smem(s_bits, bits + (size_t)b * words_per_image, words_per_image);
+  const BitFg fg{s_bits, w, h};
+  for (int i = blockIdx.x * TRACE_THREADS + threadIdx.x; i < n; i += TRACE_CTAS * TRACE_THREADS) {
+    const int p = cand[(size_t)b * max_external + i];
+    const ContourStats st = trace_outer_fg(fg, p % w, p / w, nullptr, 0);
+    CandStat cs;
+    cs.nverts = st.nverts;
+    cs.xmin = st.xmin; cs.ymin = st.ymin; cs.xmax = st.xmax; cs.ymax = st.ymax; cs.pad = 0;
+    cs.a00 = st.a00; cs.a01 = st.a01;
+    stats[(size_t)b * max_external + i] = cs;
+  }
+}
+
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_points_bits(const uint32_t* __restrict__ bits, int words_per_image,
+                                                                     int h, int w, const cv_contour* __restrict__ contours,
+                                                                     int max_contours, int max_points,
+                                                                     const cv_image_result* __restrict__ results,
+                                                                     int32_t* __restrict__ points) {
+  extern __shared__ __align__(16) uint32_t s_bits[];
+  const int b = blockIdx.y;
+  const int n = results[b].n_contours;
+  if ((int)(blockIdx.x * TRACE_THREADS) >= n) return;
+  load_bits_to_smem(s_bits, bits + (size_t)b * words_per_image, words_per_image);
+  const BitFg fg{s_bits, w, h};
+  for (int i = blockIdx.x * TRACE_THREADS + threadIdx.x; i < n; i += TRACE_CTAS * TRACE_THREADS) {
+    const cv_contour& ct = contours[(size_t)b * max_contours + i];
+    if (ct.offset + ct.nverts > max_points) continue;
+    trace_outer_fg(fg, ct.start_x, ct.start_y, points + ((size_t)b * max_points + ct.offset) * 2, ct.nverts);
+  }
 }
 
 // area filter (contourArea / (h*w) > 0.0004) + ids + point-pool offsets; one CTA per image
@@ -756,8 +821,46 @@ extern "C" int cv_nodes_resized_width(int H, int W) {
 
 struct NodesWs {
   uint8_t* enh_raw; uint8_t* bin; uint8_t* frame; int* labels; int* cand; CandStat* stats; unsigned long long* sums;
+  uint32_t* bits; int words;  // bit plane of `bin`, `words` 32-bit words per image (multiple of 4)
   size_t total;
 };
+
+static inline int bit_words(size_t n_pixels) { return (int)((((n_pixels + 31) / 32) + 3) & ~(size_t)3); }
+constexpr size_t TRACE_SMEM_MAX = 200 * 1024;  // bit planes up to 1.6 Mpixel stay in shared memory
+
+// the two border walks, from shared memory when the bit plane fits
+static int launch_traces_stats(const uint32_t* bits, int words, const uint8_t* bin, int h, int w, const int* cand,
+                               const cv_nodes_caps& c, int B, const cv_image_result* results, CandStat* stats,
+                               cudaStream_t st) {
+  const size_t smem = (size_t)words * 4;
+  if (smem <= TRACE_SMEM_MAX) {
+    static std::atomic<unsigned long long> attr{0};
+    if (cvb_once_per_device(attr))
+      CVB_CHECK(cudaFuncSetAttribute(k_trace_stats_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRACE_SMEM_MAX));
+    CVB_LAUNCH(k_trace_stats_bits, dim3(TRACE_CTAS, B), dim3(TRACE_THREADS), smem, st, bits, words, h, w, cand,
+               c.max_external, results, stats);
+  } else {
+    CVB_LAUNCH(k_trace_stats, dim3((c.max_external + 63) / 64, B), dim3(64), 0, st, bin, h, w, cand, c.max_external, results,
+               stats);
+  }
+  return CV_OK;
+}
+static int launch_traces_points(const uint32_t* bits, int words, const uint8_t* bin, int h, int w,
+                                const cv_contour* contours, const cv_nodes_caps& c, int B,
+                                const cv_image_result* results, int32_t* points, cudaStream_t st) {
+  const size_t smem = (size_t)words * 4;
+  if (smem <= TRACE_SMEM_MAX) {
+    static std::atomic<unsigned long long> attr{0};
+    if (cvb_once_per_device(attr))
+      CVB_CHECK(cudaFuncSetAttribute(k_trace_points_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRACE_SMEM_MAX));
+    CVB_LAUNCH(k_trace_points_bits, dim3(TRACE_CTAS, B), dim3(TRACE_THREADS), smem, st, bits, words, h, w, contours,
+               c.max_contours, c.max_points, results, points);
+  } else {
+    CVB_LAUNCH(k_trace_points, dim3((c.max_contours + 63) / 64, B), dim3(64), 0, st, bin, h, w, contours, c.max_contours,
+               c.max_points, results, points);
+  }
+  return CV_OK;
+}
 
 static NodesWs carve_nodes_ws(void* base, int B, int h, int w, const cv_nodes_caps& c) {
   NodesWs ws;
@@ -770,6 +873,8 @@ static NodesWs carve_nodes_ws(void* base, int B, int h, int w, const cv_nodes_ca
   ws.cand = (int*)(p + off); off += align256((size_t)B * c.max_external * 4);
   ws.stats = (CandStat*)(p + off); off += align256((size_t)B * c.max_external * sizeof(CandStat));
   ws.sums = (unsigned long long*)(p + off); off += align256((size_t)B * 8);
+  ws.words = bit_words((size_t)h * w);
+  ws.bits = (uint32_t*)(p + off); off += align256((size_t)B * ws.words * 4);
   ws.total = off;
   return ws;
 }
@@ -819,8 +924,8 @@ extern "C" int cv_nodes_analyze(const uint8_t* masks, int B, int H, int W, const
   cvb_next_work(2.0 * (double)B * n_small);
   CVB_LAUNCH(k_enhance, dim3((w + ENH_T - 1) / ENH_T, (h + ENH_T - 1) / ENH_T, B), dim3(256), 0, st, resized, ws.enh_raw,
              h, w, ws.sums);
-  CVB_LAUNCH(k_binarize, dim3((n_small + 255) / 256, B), dim3(256), 0, st, ws.enh_raw, enhanced, ws.bin, n_small,
-             ws.sums, results);
+  CVB_LAUNCH(k_binarize, dim3((ws.words * 32 + 255) / 256, B), dim3(256), 0, st, ws.enh_raw, enhanced, ws.bin, n_small,
+             ws.sums, results, ws.bits, ws.words);
   // a15: labelling (8-connected foreground, 4-connected background) -> external components -> borders
   CVB_CHECK(cudaMemsetAsync(ws.frame, 0, (size_t)B * n_small, st));
   dim3 cg((w + 31) / 32, (h + 7) / 8, B), cb(32, 8);
@@ -834,12 +939,10 @@ extern "C" int cv_nodes_analyze(const uint8_t* masks, int B, int H, int W, const
   CVB_LAUNCH(k_frame_flags, dim3((2 * w + 2 * h + 255) / 256, B), dim3(256), 0, st, ws.bin, ws.labels, ws.frame, h, w);
   CVB_LAUNCH(k_list_external, dim3(B), dim3(1024), (size_t)h * sizeof(int), st, ws.bin, ws.labels, ws.frame, h, w, ws.cand,
              c.max_external, results);
-  CVB_LAUNCH(k_trace_stats, dim3((c.max_external + 63) / 64, B), dim3(64), 0, st, ws.bin, h, w, ws.cand, c.max_external,
-             results, ws.stats);
+  if (int rc = launch_traces_stats(ws.bits, ws.words, ws.bin, h, w, ws.cand, c, B, results, ws.stats, st)) return rc;
   CVB_LAUNCH(k_filter_contours, dim3(B), dim3(1024), 0, st, ws.cand, ws.stats, c.max_external, h, w, 0.0004, contours,
              c.max_contours, c.max_points, results);
-  CVB_LAUNCH(k_trace_points, dim3((c.max_contours + 63) / 64, B), dim3(64), 0, st, ws.bin, h, w, contours, c.max_contours,
-             c.max_points, results, points);
+  if (int rc = launch_traces_points(ws.bits, ws.words, ws.bin, h, w, contours, c, B, results, points, st)) return rc;
   // a16, a17
   if (boxes) {
     CVB_LAUNCH(k_contact, dim3(B), dim3(1024), 0, st, boxes, box_offsets, contours, c.max_contours, points, c.max_points,
@@ -853,6 +956,7 @@ extern "C" int cv_nodes_analyze(const uint8_t* masks, int B, int H, int W, const
 // ------------------------------------------------------------------ terminal reclassification entry point
 struct TermWs {
   uint8_t* gray; uint8_t* bin; uint8_t* frame; int* labels; int* cand; CandStat* stats; unsigned long long* sums;
+  uint32_t* bits; int words;
   size_t total;
 };
 
@@ -867,6 +971,8 @@ static TermWs carve_term_ws(void* base, int B, int H, int W, const cv_nodes_caps
   ws.cand = (int*)(p + off); off += align256((size_t)B * c.max_external * 4);
   ws.stats = (CandStat*)(p + off); off += align256((size_t)B * c.max_external * sizeof(CandStat));
   ws.sums = (unsigned long long*)(p + off); off += align256((size_t)B * 8);
+  ws.words = bit_words((size_t)H * W);
+  ws.bits = (uint32_t*)(p + off); off += align256((size_t)B * ws.words * 4);
   ws.total = off;
   return ws;
 }
@@ -907,8 +1013,8 @@ extern "C" int cv_terminals_analyze(const uint8_t* pages_rgb, int B, int H, int 
   // get_contours(prelim_wire_mask, 0.0001) at native resolution (:2252, :388-412)
   cvb_next_work((double)n_px);
   CVB_LAUNCH(k_image_sum, dim3(min((n_img + 255) / 256, 148 * 8), B), dim3(256), 0, st, wire_mask, n_img, ws.sums);
-  CVB_LAUNCH(k_binarize, dim3((n_img + 255) / 256, B), dim3(256), 0, st, wire_mask, (uint8_t*)nullptr, ws.bin, n_img, ws.sums,
-             results);
+  CVB_LAUNCH(k_binarize, dim3((ws.words * 32 + 255) / 256, B), dim3(256), 0, st, wire_mask, (uint8_t*)nullptr, ws.bin, n_img,
+             ws.sums, results, ws.bits, ws.words);
   CVB_CHECK(cudaMemsetAsync(ws.frame, 0, n_px, st));
   dim3 cg((W + 31) / 32, (H + 7) / 8, B), cb(32, 8);
   cvb_next_work(5.0 * (double)n_px);
@@ -920,12 +1026,10 @@ extern "C" int cv_terminals_analyze(const uint8_t* pages_rgb, int B, int H, int 
   CVB_LAUNCH(k_frame_flags, dim3((2 * W + 2 * H + 255) / 256, B), dim3(256), 0, st, ws.bin, ws.labels, ws.frame, H, W);
   CVB_LAUNCH(k_list_external, dim3(B), dim3(1024), (size_t)H * sizeof(int), st, ws.bin, ws.labels, ws.frame, H, W, ws.cand,
              c.max_external, results);
-  CVB_LAUNCH(k_trace_stats, dim3((c.max_external + 63) / 64, B), dim3(64), 0, st, ws.bin, H, W, ws.cand, c.max_external,
-             results, ws.stats);
+  if (int rc = launch_traces_stats(ws.bits, ws.words, ws.bin, H, W, ws.cand, c, B, results, ws.stats, st)) return rc;
   CVB_LAUNCH(k_filter_contours, dim3(B), dim3(1024), 0, st, ws.cand, ws.stats, c.max_external, H, W, 0.0001, contours,
              c.max_contours, c.max_points, results);
-  CVB_LAUNCH(k_trace_points, dim3((c.max_contours + 63) / 64, B), dim3(64), 0, st, ws.bin, H, W, contours, c.max_contours,
-             c.max_points, results, points);
+  if (int rc = launch_traces_points(ws.bits, ws.words, ws.bin, H, W, contours, c, B, results, points, st)) return rc;
   // :2270-2287 contacts of the terminals, threshold 10
   if (n_boxes_total > 0)
     CVB_LAUNCH(k_terminal_counts, dim3(B), dim3(1024), 0, st, boxes, box_offsets, contours, c.max_contours, points,

@@ -104,16 +104,14 @@ struct ContourStats {
 // image where foreground = non-zero; pixels outside [0,w)x[0,h) read as background.
 // If `out` is non-null the vertices are written as (x,y) int32 pairs (capacity `cap` vertices).
 // Returns stats; nverts counts every vertex even beyond cap.
-template <typename Pix>
-CV_HD ContourStats trace_outer_simple(const Pix* img, int w, int h, int x0, int y0, int32_t* out, int cap) {
+// `fg(x, y)` is the foreground predicate (false outside the image); the byte-image wrapper follows below.
+template <typename Fg>
+CV_HD ContourStats trace_outer_fg(Fg fg, int x0, int y0, int32_t* out, int cap) {
   ContourStats st;
   st.nverts = 0;
   st.xmin = st.xmax = x0;
   st.ymin = st.ymax = y0;
   st.a00 = st.a01 = st.a10 = 0;
-  auto fg = [&](int x, int y) -> bool {
-    return x >= 0 && y >= 0 && x < w && y < h && img[(size_t)y * w + x] != 0;
-  };
   long long first_x = 0, first_y = 0, prev_x = 0, prev_y = 0;
   auto emit = [&](int x, int y) {
     if (out && st.nverts < cap) { out[2 * st.nverts] = x; out[2 * st.nverts + 1] = y; }
@@ -175,6 +173,13 @@ CV_HD ContourStats trace_outer_simple(const Pix* img, int w, int h, int x0, int 
     st.a10 += dxy * (prev_x + first_x);
   }
   return st;
+}
+
+template <typename Pix>
+CV_HD ContourStats trace_outer_simple(const Pix* img, int w, int h, int x0, int y0, int32_t* out, int cap) {
+  return trace_outer_fg(
+      [=](int x, int y) -> bool { return x >= 0 && y >= 0 && x < w && y < h && img[(size_t)y * w + x] != 0; }, x0, y0, out,
+      cap);
 }
 
 // cv2.contourArea(c) / (h*w) > thr  evaluated exactly as the reference does in Python doubles
