@@ -1,7 +1,7 @@
 #!/bin/bash
 O=gpurun_out
-SH="262144,384,1536,0,2,0 262144,384,384,0,2,0 262144,1152,384,0,0,1 313600,1152,384,0,0,1 1048576,192,768,0,2,0 1048576,768,192,1,0,1 1048576,576,192,0,0,1 65536,768,3072,0,2,0 262144,256,256,0,2,0"
-echo "== pairs for BN>=256 (default)" > $O/s17_pair.log; python scripts/gemm_probe.py $SH >> $O/s17_pair.log 2>&1
-echo "== pairs for BN>=192" >> $O/s17_pair.log; CVB_PAIR_MINBN=192 python scripts/gemm_probe.py $SH >> $O/s17_pair.log 2>&1
-echo "== pairs for BN>=128" >> $O/s17_pair.log; CVB_PAIR_MINBN=128 python scripts/gemm_probe.py $SH >> $O/s17_pair.log 2>&1
-cat $O/s17_pair.log
+SH="4194304,96,96,0,2,0 4194304,96,168,0,2,0 1048576,192,192,0,2,0 4194304,96,384,0,2,0"
+echo "== 8 epilogue warps" > $O/s22_ew.log; python scripts/gemm_probe.py $SH >> $O/s22_ew.log 2>&1
+echo "== 16 epilogue warps (K<=192, f32+res)" >> $O/s22_ew.log; CVB_GEMM_EW16_RES=1 python scripts/gemm_probe.py $SH >> $O/s22_ew.log 2>&1
+CVB_GEMM_EW16_RES=1 python -m pytest tests/test_gemm_gpu.py -m gpu -x -q 2>&1 | tail -2 >> $O/s22_ew.log
+cat $O/s22_ew.log
