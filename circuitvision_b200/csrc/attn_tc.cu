@@ -9,6 +9,8 @@
 //   S = Q K^T  (tcgen05.mma 128x128x96, S in TMEM)  ->  softmax warps read S, write P (bf16) into shared memory
 //   in the K-major 128B-swizzled layout  ->  O_tile = P V (tcgen05.mma 128x96x128, V consumed MN-major straight
 //   from its row-major tile)  ->  softmax warps fold O_tile into fp32 registers with the online-softmax rescale.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc05.cuh"
 #include "act.cuh"
@@ -27,6 +29,7 @@ struct AttnParams {
   int qcol0, kcol0, vcol0;  // column of head 0 inside the Q / K / V tensor maps
   float scale_log2;         // softmax scale * log2(e)
   int fp16;                 // q/k/v/P/out are IEEE half instead of bf16
+  int skip_chunks;          // windowed kernel: skip score chunks no row of the warp can see
   __nv_bfloat16* out;       // [Mq, heads*96]
   long long ld_out;
 };
@@ -494,12 +497,20 @@ k_attn_win(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUten
       float m_ref = -INFINITY, l = 0.f;
       for (int j = 0; j < it.n_kt; j++) {
         const int c_lo = max(vis0 - j * ATT_BN, 0), c_hi = row_ok ? min(vis0 + p.Wkv - j * ATT_BN, ATT_BN) : 0;
+        // 32-column chunks of this key tile that at least one row of the WARP can see: with small windows most of the
+        // 128 x 128 score tile is other windows' keys (a warp of the Q-pooled 16/64 case sees one key tile in four, a
+        // warp of the 8 x 8 case two chunks in four), and those chunks need neither the maximum nor the exponentials —
+        // only zeros in P.
+        const bool sees = c_hi > c_lo;
+        const int cb = p.skip_chunks ? (__reduce_min_sync(0xffffffffu, sees ? c_lo : ATT_BN) >> 5) : 0;
+        const int ce = p.skip_chunks ? ((__reduce_max_sync(0xffffffffu, sees ? c_hi : 0) + 31) >> 5) : ATT_BN / 32;
         tc::mbar_wait(&s_full[g], s_uses & 1);
         s_uses++;
         tc::tc_fence_after();
         float tmx = -INFINITY;
 #pragma unroll
         for (int c = 0; c < ATT_BN / 32; c++) {
+          if (c < cb || c >= ce) continue;
           uint32_t v[32];
           tc::tmem_ld_32x32(tS + c * 32, v);
           tc::tmem_ld_wait();
@@ -533,12 +544,18 @@ k_attn_win(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUten
         }
         float rowsum = 0.f;
         const float mr = (m_ref == -INFINITY) ? 0.f : m_ref;
+        // P overwrites S in place (16-bit, half the columns): every visible chunk is read before any chunk is written
+        uint32_t pk[ATT_BN / 32][16];
 #pragma unroll
         for (int c = 0; c < ATT_BN / 32; c++) {
+          if (c < cb || c >= ce) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) pk[c][i] = 0u;
+            continue;
+          }
           uint32_t v[32];
           tc::tmem_ld_32x32(tS + c * 32, v);
           tc::tmem_ld_wait();
-          uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const int col = c * 32 + i;
@@ -547,10 +564,11 @@ k_attn_win(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUten
             if (col < c_lo || col >= c_hi) p0 = 0.f;
             if (col + 1 < c_lo || col + 1 >= c_hi) p1 = 0.f;
             rowsum += p0 + p1;
-            pk[i >> 1] = tc::pack16(p.fp16, p0, p1);
+            pk[c][i >> 1] = tc::pack16(p.fp16, p0, p1);
           }
-          tc::tmem_st_32x16(tS + c * 16, pk);
         }
+#pragma unroll
+        for (int c = 0; c < ATT_BN / 32; c++) tc::tmem_st_32x16(tS + c * 16, pk[c]);
         tc::tmem_st_wait();
         tc::tc_fence_before();
         __syncwarp();
@@ -638,6 +656,12 @@ int attn_tc_launch(const __nv_bfloat16* q, long long ldq, int qcols, int qcol0, 
   p.qcol0 = qcol0; p.kcol0 = kcol0; p.vcol0 = vcol0;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.fp16 = fp16;
+  {
+    // same-box A/B (tiny, B = 64): 8x8 windows 1.06 -> 0.72 ms, 4x4 windows 0.52 -> 0.39 ms, every other case equal or
+    // slightly better; CVB_ATTN_SKIP = 0 turns it off
+    static const int force = getenv("CVB_ATTN_SKIP") ? atoi(getenv("CVB_ATTN_SKIP")) : 1;
+    p.skip_chunks = force != 0;
+  }
   p.out = out; p.ld_out = ld_out;
   const bool glob = Wq == Wkv && (Wkv % ATT_BN) == 0 && (Wq % (2 * ATT_BM)) == 0 && (Mq % (2 * ATT_BM)) == 0;
   // algorithmic flops: every query row against the keys of its own window, QK^T and PV (padded head dim as executed)
