@@ -355,6 +355,7 @@ def main():
 
     # ---- e2e through the public API with host buffers
     h2d = d2h = 0
+    pinned_out = {}
 
     def step_e2e(i):
         nonlocal h2d, d2h
@@ -370,9 +371,14 @@ def main():
         if use_nodes:
             r = na.analyze(masks, pool_boxes[p], grow=False)  # packs + uploads the boxes, runs, syncs on the tables
             host = r.tables_to_host()
-            emp = r.emptied.cpu()
-            enh = r.enhanced.cpu()
-            bo = sum(v.nbytes for v in host.values()) + emp.numel() + enh.numel()
+            # the two result images go to pinned host buffers (allocated on the first, untimed call)
+            if "emp" not in pinned_out:
+                pinned_out["emp"] = torch.empty(tuple(r.emptied.shape), dtype=torch.uint8, pin_memory=True)
+                pinned_out["enh"] = torch.empty(tuple(r.enhanced.shape), dtype=torch.uint8, pin_memory=True)
+            pinned_out["emp"].copy_(r.emptied, non_blocking=True)
+            pinned_out["enh"].copy_(r.enhanced, non_blocking=True)
+            torch.cuda.synchronize()
+            bo = sum(v.nbytes for v in host.values()) + pinned_out["emp"].numel() + pinned_out["enh"].numel()
             bi += sum(len(b) for b in pool_boxes[p]) * 48 + 4 * (B + 1)
         else:
             out = masks.cpu()

@@ -371,18 +371,89 @@ __global__ void k_trace_stats(const uint8_t* __restrict__ bin, int h, int w, con
 // one thread per component), so each CTA first copies the image's BIT plane into shared memory and probes there
 // (~25 cycles instead of an L2 round trip per probe).  TRACE_CTAS CTAs per image share its candidates.
 constexpr int TRACE_CTAS = 8, TRACE_THREADS = 128;
-struct BitFg {
-  const uint32_t* bits;
-  int w, h;
-  __device__ __forceinline__ bool operator()(int x, int y) const {
-    if ((unsigned)x >= (unsigned)w || (unsigned)y >= (unsigned)h) return false;
-    const unsigned idx = (unsigned)y * (unsigned)w + (unsigned)x;
-    return (bits[idx >> 5] >> (idx & 31)) & 1u;
-  }
-};
+constexpr int TRACE_PAD_WORDS = 4;  // one zero word in front of the plane (so pixel -1 is addressable) + 16-byte alignment
+
+// The shared-memory plane: word 0..3 are zero, pixel i of the image is bit (i + 128) of the array, one extra zero word at
+// the end (the funnel shift below reads the word after the one that holds pixel x+1).
 __device__ __forceinline__ void load_bits_to_smem(uint32_t* sm, const uint32_t* __restrict__ g, int words) {
-  for (int i = threadIdx.x; i < words / 4; i += blockDim.x) ((uint4*)sm)[i] = __ldg((const uint4*)g + i);
+  if (threadIdx.x < TRACE_PAD_WORDS) sm[threadIdx.x] = 0u;
+  if (threadIdx.x < 4) sm[TRACE_PAD_WORDS + words + threadIdx.x] = 0u;
+  for (int i = threadIdx.x; i < words / 4; i += blockDim.x) ((uint4*)(sm + TRACE_PAD_WORDS))[i] = __ldg((const uint4*)g + i);
   __syncthreads();
+}
+
+// 8-neighbour occupancy of pixel (x, y) in OpenCV chain-code order (bit 0 = E, 1 = NE, 2 = N, 3 = NW, 4 = W, 5 = SW, 6 = S,
+// 7 = SE; y grows downwards), pixels outside the image read as background.  Three independent row reads instead of up to
+// eight dependent probes: the border walk is one long dependency chain, so the probes' latency is its speed.
+__device__ __forceinline__ uint32_t neighbours8(const uint32_t* sm, int w, int h, int x, int y) {
+  auto row3 = [&](int yy) -> uint32_t {  // bits (x-1, x, x+1) of row yy
+    if ((unsigned)yy >= (unsigned)h) return 0u;
+    const uint32_t i = (uint32_t)yy * (uint32_t)w + (uint32_t)x + (TRACE_PAD_WORDS * 32 - 1);
+    const uint32_t lo = sm[i >> 5], hi = sm[(i >> 5) + 1];
+    return __funnelshift_r(lo, hi, i & 31) & 7u;
+  };
+  uint32_t up = row3(y - 1), mid = row3(y), dn = row3(y + 1);
+  const uint32_t keep = (x > 0 ? 1u : 0u) | 2u | (x + 1 < w ? 4u : 0u);  // flat bit order: row ends touch the next row
+  up &= keep; mid &= keep; dn &= keep;
+  return ((mid >> 2) & 1u) | (((up >> 2) & 1u) << 1) | (((up >> 1) & 1u) << 2) | ((up & 1u) << 3) | ((mid & 1u) << 4) |
+         ((dn & 1u) << 5) | (((dn >> 1) & 1u) << 6) | (((dn >> 2) & 1u) << 7);
+}
+__device__ __forceinline__ int chain_dx(int s) { return (int)((0x901Au >> (2 * s)) & 3u) - 1; }  // 1 1 0 -1 -1 -1 0 1
+__device__ __forceinline__ int chain_dy(int s) { return (int)((0xA901u >> (2 * s)) & 3u) - 1; }  // 0 -1 -1 -1 0 1 1 1
+
+// trace_outer_fg (node_prims.cuh) on the shared-memory bit plane: same visiting order, same vertex selection, same sums.
+__device__ ContourStats trace_outer_bits(const uint32_t* sm, int w, int h, int x0, int y0, int32_t* out, int cap) {
+  ContourStats st;
+  st.nverts = 0;
+  st.xmin = st.xmax = x0;
+  st.ymin = st.ymax = y0;
+  st.a00 = st.a01 = st.a10 = 0;
+  long long first_x = 0, first_y = 0, prev_x = 0, prev_y = 0;
+  auto emit = [&](int x, int y) {
+    if (out && st.nverts < cap) { out[2 * st.nverts] = x; out[2 * st.nverts + 1] = y; }
+    if (st.nverts == 0) { first_x = x; first_y = y; }
+    else {
+      long long dxy = prev_x * (long long)y - (long long)x * prev_y;
+      st.a00 += dxy;
+      st.a01 += dxy * (prev_y + y);
+      st.a10 += dxy * (prev_x + x);
+    }
+    prev_x = x; prev_y = y;
+    st.xmin = min(st.xmin, x); st.xmax = max(st.xmax, x);
+    st.ymin = min(st.ymin, y); st.ymax = max(st.ymax, y);
+    st.nverts++;
+  };
+  // first neighbour clockwise, starting just after West: directions 3, 2, 1, 0, 7, 6, 5, 4
+  const uint32_t n0 = neighbours8(sm, w, h, x0, y0);
+  if (n0 == 0u) {
+    emit(x0, y0);  // isolated pixel
+  } else {
+    // rotate so that direction 3 becomes the top bit of a byte and scan downwards
+    const uint32_t r0 = ((n0 | (n0 << 8)) >> 4) & 0xFFu;  // bit j = direction (j + 4) & 7
+    int s = (31 - __clz(r0) + 4) & 7;                      // highest j first: j = 7 is direction 3
+    const int x1 = x0 + chain_dx(s), y1 = y0 + chain_dy(s);
+    int x3 = x0, y3 = y0;
+    int prev_s = s ^ 4;
+    for (;;) {
+      // counter-clockwise search for the next border pixel, starting after the back-pointer
+      const uint32_t nb = neighbours8(sm, w, h, x3, y3);
+      const uint32_t rot = ((nb | (nb << 8)) >> (s + 1)) & 0xFFu;  // bit j = direction (s + 1 + j) & 7
+      const int sn = rot ? ((s + 1 + (__ffs(rot) - 1)) & 7) : (s & 7);
+      const int x4 = x3 + chain_dx(sn), y4 = y3 + chain_dy(sn);
+      if (sn != prev_s) emit(x3, y3);
+      prev_s = sn;
+      if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) break;
+      x3 = x4; y3 = y4;
+      s = (sn + 4) & 7;
+    }
+  }
+  if (st.nverts > 0) {
+    long long dxy = prev_x * first_y - first_x * prev_y;
+    st.a00 += dxy;
+    st.a01 += dxy * (prev_y + first_y);
+    st.a10 += dxy * (prev_x + first_x);
+  }
+  return st;
 }
 
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_stats_bits(const uint32_t* __restrict__ bits, int words_per_image,
@@ -395,10 +466,9 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_stats_bits(const uint32
   const int n = results[b].n_external;
   if ((int)(blockIdx.x * TRACE_THREADS) >= n) return;  // whole CTA: nothing to walk
   load_bits_to_smem(s_bits, bits + (size_t)b * words_per_image, words_per_image);
-  const BitFg fg{s_bits, w, h};
   for (int i = blockIdx.x * TRACE_THREADS + threadIdx.x; i < n; i += TRACE_CTAS * TRACE_THREADS) {
     const int p = cand[(size_t)b * max_external + i];
-    const ContourStats st = trace_outer_fg(fg, p % w, p / w, nullptr, 0);
+    const ContourStats st = trace_outer_bits(s_bits, w, h, p % w, p / w, nullptr, 0);
     CandStat cs;
     cs.nverts = st.nverts;
     cs.xmin = st.xmin; cs.ymin = st.ymin; cs.xmax = st.xmax; cs.ymax = st.ymax; cs.pad = 0;
@@ -417,11 +487,10 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_points_bits(const uint3
   const int n = results[b].n_contours;
   if ((int)(blockIdx.x * TRACE_THREADS) >= n) return;
   load_bits_to_smem(s_bits, bits + (size_t)b * words_per_image, words_per_image);
-  const BitFg fg{s_bits, w, h};
   for (int i = blockIdx.x * TRACE_THREADS + threadIdx.x; i < n; i += TRACE_CTAS * TRACE_THREADS) {
     const cv_contour& ct = contours[(size_t)b * max_contours + i];
     if (ct.offset + ct.nverts > max_points) continue;
-    trace_outer_fg(fg, ct.start_x, ct.start_y, points + ((size_t)b * max_points + ct.offset) * 2, ct.nverts);
+    trace_outer_bits(s_bits, w, h, ct.start_x, ct.start_y, points + ((size_t)b * max_points + ct.offset) * 2, ct.nverts);
   }
 }
 
@@ -832,7 +901,7 @@ constexpr size_t TRACE_SMEM_MAX = 200 * 1024;  // bit planes up to 1.6 Mpixel st
 static int launch_traces_stats(const uint32_t* bits, int words, const uint8_t* bin, int h, int w, const int* cand,
                                const cv_nodes_caps& c, int B, const cv_image_result* results, CandStat* stats,
                                cudaStream_t st) {
-  const size_t smem = (size_t)words * 4;
+  const size_t smem = ((size_t)words + TRACE_PAD_WORDS + 4) * 4;
   if (smem <= TRACE_SMEM_MAX) {
     static std::atomic<unsigned long long> attr{0};
     if (cvb_once_per_device(attr))
@@ -848,7 +917,7 @@ static int launch_traces_stats(const uint32_t* bits, int words, const uint8_t* b
 static int launch_traces_points(const uint32_t* bits, int words, const uint8_t* bin, int h, int w,
                                 const cv_contour* contours, const cv_nodes_caps& c, int B,
                                 const cv_image_result* results, int32_t* points, cudaStream_t st) {
-  const size_t smem = (size_t)words * 4;
+  const size_t smem = ((size_t)words + TRACE_PAD_WORDS + 4) * 4;
   if (smem <= TRACE_SMEM_MAX) {
     static std::atomic<unsigned long long> attr{0};
     if (cvb_once_per_device(attr))
