@@ -81,6 +81,12 @@ class CircuitAnalyzer:
             _terminals.apply_reclassification(boxes, r.counts(b), self.class_names)
         return r
 
+    # ------------------------------------------------------------------ YOLO-cluster crop (host geometry)
+    def crop_image_and_adjust_bboxes(self, image_to_crop, all_yolo_bboxes_input, padding=20):
+        """Reference :937 — (crop view, boxes shifted into it, crop_debug_info); circuitvision_b200/crop.py."""
+        from . import crop as _crop
+        return _crop.crop_image_and_adjust_bboxes(image_to_crop, all_yolo_bboxes_input, padding, self.non_components)
+
     # ------------------------------------------------------------------ netlist lines (SURVEY §8(f)4)
     def generate_netlist_from_nodes(self, node_list):
         """Reference :1607 — host bookkeeping on the node table (circuitvision_b200/netlist.py)."""

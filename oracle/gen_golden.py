@@ -153,6 +153,34 @@ def main_terminals():
     print("wrote", GOLDEN_TERMINALS, os.path.getsize(GOLDEN_TERMINALS), "bytes; cv2", cv2.__version__)
 
 
+GOLDEN_CROPS = os.path.join(ROOT, "tests", "golden", "crop_golden.json")
+
+
+def _jsonable(x):
+    return json.loads(json.dumps(x, default=lambda o: o.item() if hasattr(o, "item") else str(o)))
+
+
+def main_crops():
+    """tests/golden/crop_golden.json: the unmodified reference crop_image_and_adjust_bboxes (circuit_analyzer.py:937) on
+    the seeded pages of oracle/crop_cases.py, padding 80 (analysis_pipeline.py:181) and the default 20."""
+    import contextlib
+    import copy
+    import io
+    from oracle import ref_loader
+    from oracle.crop_cases import random_page
+    A = ref_loader.load_reference_analyzer()
+    out = {}
+    for seed in range(84):
+        img, boxes = random_page(seed)
+        for pad in (80, 20):
+            with contextlib.redirect_stdout(io.StringIO()):
+                rimg, rb, rinfo = A.crop_image_and_adjust_bboxes(img, copy.deepcopy(boxes), padding=pad)
+            out[f"{seed}/{pad}"] = {"shape": list(rimg.shape), "sha": _sha(rimg), "boxes": _jsonable(rb), "info": _jsonable(rinfo)}
+    json.dump(out, open(GOLDEN_CROPS, "w"), sort_keys=True)
+    n = sum(1 for v in out.values() if v["info"]["crop_applied"])
+    print("wrote", GOLDEN_CROPS, os.path.getsize(GOLDEN_CROPS), "bytes;", n, "of", len(out), "calls cropped")
+
+
 def _sha(a: np.ndarray) -> str:
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
@@ -185,7 +213,9 @@ def main():
 
 
 if __name__ == "__main__":
-    if "--terminals" in sys.argv:
+    if "--crops" in sys.argv:
+        main_crops()
+    elif "--terminals" in sys.argv:
         main_terminals()
     else:
         main()
