@@ -240,3 +240,48 @@ def test_forward_parity_other_variants(variant):
     assert _iou(low.cpu() > 0, rl > 0) >= 0.99 and _iou(high.cpu() > 0, rh > 0) >= 0.99
     del model, eng
     torch.cuda.empty_cache()
+
+
+def test_page_flow_reclassify_crop_segment_nodes_netlist(pair):
+    """The reference's call order on one page (analysis_pipeline.py:127, :177, :206, :234 and the netlist consumer) through
+    the drop-ins only: terminal reclassification -> YOLO-cluster crop (padding 80) -> SAM 2.1 on the crop -> node analysis
+    -> netlist lines.  Every stage is held to its own oracle on the SAME inputs (the SAM 2.1 mask by IoU, everything
+    downstream of a binary mask bit-exactly)."""
+    import copy
+    from oracle import node_oracle, sam2_oracle, terminal_oracle
+    from oracle.gen_golden import CLASS_NAMES
+    from circuitvision_b200 import netlist, sam2_infer
+    from circuitvision_b200.circuit_analyzer import CircuitAnalyzer
+    ref, model = pair
+    m, boxes, rgb = synth.make_schematic(33, 1024, render_rgb=True)
+    ys, xs = np.nonzero(m)
+    page = np.full((1300, 1500, 3), 255, np.uint8)  # the schematic sits inside a larger page
+    page[120:1144, 200:1224] = rgb
+    boxes = [dict(b, xmin=b["xmin"] + 200, xmax=b["xmax"] + 200, ymin=b["ymin"] + 120, ymax=b["ymax"] + 120) for b in boxes]
+    for k in (11, len(xs) // 3, len(xs) - 5):
+        x, y = int(xs[k]) + 200, int(ys[k]) + 120
+        boxes.append({"class": "terminal", "confidence": 0.6, "xmin": x - 12, "ymin": y - 9, "xmax": x + 12, "ymax": y + 9,
+                      "persistent_uid": f"terminal_{x - 12}_{y - 9}_{x + 12}_{y + 9}"})
+    A = CircuitAnalyzer(sam2_model=model, sam2_transforms=sam2_infer.SAM2Transforms(1024, 0.0), debug=True, device=0,
+                        class_names=CLASS_NAMES)
+    # 1. terminals
+    want = copy.deepcopy(boxes)
+    terminal_oracle.reclassify_terminals(page, want, CLASS_NAMES)
+    A.reclassify_terminals_based_on_connectivity(page, boxes)
+    assert boxes == want and any(b.get("was_reclassified_from_terminal") for b in boxes)
+    # 2. crop
+    crop_img, crop_boxes, info = A.crop_image_and_adjust_bboxes(page, copy.deepcopy(boxes), padding=80)
+    assert info["crop_applied"] and crop_img.shape[0] < 1300 and crop_img.shape[1] < 1500
+    # 3. SAM 2.1 on the crop (any size: antialiased resize on the device, logits resized back)
+    mask, colored, _ = A.segment_with_sam2(crop_img)
+    assert mask is not None and mask.shape == crop_img.shape[:2]
+    ref_mask, _, _ = sam2_oracle.segment(ref, crop_img)
+    assert _iou(torch.from_numpy(mask > 0), torch.from_numpy(ref_mask > 0)) >= 0.99
+    # 4. node analysis on that mask + 5. netlist
+    nodes, emptied, enhanced, *_ = A.get_node_connections(crop_img, mask, crop_boxes)
+    rn, remp, renh, _, _ = node_oracle.get_node_connections(mask, crop_boxes)
+    assert np.array_equal(emptied, remp) and np.array_equal(enhanced, renh)
+    a, b = node_oracle.node_signature(nodes), node_oracle.node_signature(rn)
+    assert len(a) == len(b) and all(x[0] == y[0] and x[1] == y[1] and np.array_equal(x[2], y[2]) for x, y in zip(a, b))
+    text = "\n".join(A.stringify_line(l) for l in A.generate_netlist_from_nodes(nodes))
+    assert text == netlist.netlist_text(rn)
