@@ -234,7 +234,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
       // (a destination row index never exceeds the source row count, so it fits an int)
       int dest[8];
       if (!TMA_OUT) {
-        const int dmine = (myrow < p.M) ? (int)gemm_dest_row(e, map, myrow) : -1;
+        int dmine = (myrow < p.M) ? (int)gemm_dest_row(e, map, myrow) : -1;
+        if (map == GEMM_MAP_SHUFFLE2 && dmine >= 0) {
+          // (b, y, x) on the H x W grid -> row of pixel (2y, 2x) on the 2H x 2W grid; the chunk's (dy, dx) is added below
+          const unsigned hw = (unsigned)(e.H * e.W);
+          const unsigned img = (unsigned)dmine / hw, rem = (unsigned)dmine - img * hw;
+          const unsigned y = rem / (unsigned)e.W, xx = rem - y * (unsigned)e.W;
+          dmine = (int)((img * 2u * (unsigned)e.H + 2u * y) * 2u * (unsigned)e.W + 2u * xx);
+        }
 #pragma unroll
         for (int it = 0; it < 8; it++) dest[it] = __shfl_sync(0xffffffffu, dmine, it * 4 + sub_row);
       }
@@ -272,12 +279,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
 #pragma unroll
           for (int it = 0; it < 8; it++) {
             long long d = dest[it];
-            if (d >= 0 && map == GEMM_MAP_SHUFFLE2) {
-              long long img = d / ((long long)e.H * e.W);
-              int rem = (int)(d - img * e.H * e.W);
-              int y = rem / e.W, xx = rem - y * e.W;
-              d = (img * 2 * e.H + 2 * y + (q >> 1)) * 2 * e.W + 2 * xx + (q & 1);
-            }
+            if (d >= 0 && map == GEMM_MAP_SHUFFLE2) d += (long long)(q >> 1) * 2 * e.W + (q & 1);
             dfin[it] = d;
             rres[it] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (has_res && d >= 0 && sub_c * 4 < ncols) {
@@ -302,10 +304,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
         float f[32];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-          f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bv[j].x;
-          f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bv[j].y;
-          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bv[j].z;
-          f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bv[j].w;
+          // packed fp32x2 adds: the accumulator registers of tcgen05.ld and the bias float4 are natural pairs
+          up2(add2(pk2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), pk2(bv[j].x, bv[j].y)), f[4 * j + 0],
+              f[4 * j + 1]);
+          up2(add2(pk2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), pk2(bv[j].z, bv[j].w)), f[4 * j + 2],
+              f[4 * j + 3]);
         }
         if (TMA_OUT) {
           if (has_res && rba) {
@@ -328,8 +331,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
 #pragma unroll
             for (int j = 0; j < 4; j++) {
               uint32_t w[4];
+              // one uniform branch per 8 values instead of a predicated pair of conversions per value pair
+              if (e.fp16) {
 #pragma unroll
-              for (int k = 0; k < 4; k++) w[k] = tc::pack16(e.fp16, f[8 * j + 2 * k], f[8 * j + 2 * k + 1]);
+                for (int k = 0; k < 4; k++) w[k] = tc::pack16(1, f[8 * j + 2 * k], f[8 * j + 2 * k + 1]);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) w[k] = tc::pack16(0, f[8 * j + 2 * k], f[8 * j + 2 * k + 1]);
+              }
               *(uint4*)(buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
