@@ -64,6 +64,20 @@ __device__ __forceinline__ long long gemm_dest_row(const GemmEpilogue& e, int ma
     if (y >= (unsigned)e.H || x >= (unsigned)e.W) return -1;
     return (long long)((b * (unsigned)e.H + y) * (unsigned)e.W + x);
   }
+  if (map == GEMM_MAP_POOL2) {
+    // anchor rows (even ty, even tx) own the pooled output row; every other row returns -1
+    const unsigned r = (unsigned)r64;
+    const unsigned ws = (unsigned)e.ws, w2 = ws * ws;
+    const unsigned win = r / w2, t = r - win * w2;
+    const unsigned per_img = (unsigned)(e.nwx * e.nwy);
+    const unsigned b = win / per_img, wi = win - b * per_img;
+    const unsigned wy = wi / (unsigned)e.nwx, wx = wi - wy * (unsigned)e.nwx;
+    const unsigned ty = t / ws, tx = t - ty * ws;
+    if ((ty | tx) & 1u) return -1;
+    const unsigned y = wy * ws + ty, x = wx * ws + tx;
+    if (y >= (unsigned)e.H || x >= (unsigned)e.W) return -1;
+    return (long long)((b * (unsigned)(e.H >> 1) + (y >> 1)) * (unsigned)(e.W >> 1) + (x >> 1));
+  }
   return r64;
 }
 
@@ -242,8 +256,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
           const unsigned y = rem / (unsigned)e.W, xx = rem - y * (unsigned)e.W;
           dmine = (int)((img * 2u * (unsigned)e.H + 2u * y) * 2u * (unsigned)e.W + 2u * xx);
         }
+        if (MAP == GEMM_MAP_POOL2) {
+          dest[0] = dmine;  // the anchor lane writes its pooled row itself
+        } else {
 #pragma unroll
-        for (int it = 0; it < 8; it++) dest[it] = __shfl_sync(0xffffffffu, dmine, it * 4 + sub_row);
+          for (int it = 0; it < 8; it++) dest[it] = __shfl_sync(0xffffffffu, dmine, it * 4 + sub_row);
+        }
       }
       tc::mbar_wait(&tfull[acc], acc_phase);
       tc::tc_fence_after();
@@ -275,7 +293,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
         // alias the residual, so the compiler cannot hoist these loads above the stores of an earlier iteration itself)
         long long dfin[8];
         float4 rres[8];
-        if (!TMA_OUT) {
+        if (!TMA_OUT && MAP != GEMM_MAP_POOL2) {
 #pragma unroll
           for (int it = 0; it < 8; it++) {
             long long d = dest[it];
@@ -347,6 +365,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
           if (lane == 0 && col0 < p.N && row0 < p.M) {
             tc::tma_store_2d(&tmap_out, buf, col0, (int)row0);
             tc::tma_store_commit();
+          }
+        } else if (MAP == GEMM_MAP_POOL2) {
+          // 2 x 2 max over lanes (l, l+1, l+ws, l+ws+1): valid on the anchor lanes, which store 32 contiguous floats
+          const int wsl = e.ws;
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            float m = fmaxf(f[i], __shfl_down_sync(0xffffffffu, f[i], 1));
+            f[i] = fmaxf(m, __shfl_down_sync(0xffffffffu, m, wsl));
+          }
+          if (dest[0] >= 0 && col0 < p.N) {
+            float4* o = (float4*)(e.out_f32 + (long long)dest[0] * e.ld_f32 + col0);
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+              if (4 * j < ncols) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           }
         } else {
           if (!rba) {
@@ -497,6 +529,11 @@ static int launch_bn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16*
   }
   if (e.map_mode == GEMM_MAP_UNWINDOW && f32 && !b16 && res && e.act == GEMM_ACT_NONE)
     return launch_cfg<BN, 0, 1, 0, 1, 0>(CVB_GEMM_ARGS);                                             // windowed proj
+  if (e.map_mode == GEMM_MAP_POOL2) {
+    if (!f32 || b16 || res || e.act != GEMM_ACT_NONE || (e.ws != 4 && e.ws != 8) || (e.H % e.ws) || (e.W % e.ws))
+      return cvb_fail(CV_ERR_INVALID, "gemm: POOL2 needs fp32 output, no residual / activation, windows of 4 or 8 without padding");
+    return launch_cfg<BN, 0, 0, 0, 3, 0>(CVB_GEMM_ARGS);                                             // Q-pool shortcut
+  }
   if (e.map_mode == GEMM_MAP_SHUFFLE2 && f32 && !b16 && res) {
     if (e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 1, 0, 2, 0>(CVB_GEMM_ARGS);                 // upscale 1
     if (e.act == GEMM_ACT_GELU && e.res_before_act) return launch_cfg<BN, 1, 1, 0, 2, 1>(CVB_GEMM_ARGS);  // upscale 2

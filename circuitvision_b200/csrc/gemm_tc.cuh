@@ -10,7 +10,7 @@
 namespace cvb {
 
 enum { GEMM_ACT_NONE = 0, GEMM_ACT_GELU = 1, GEMM_ACT_RELU = 2 };
-enum { GEMM_MAP_IDENTITY = 0, GEMM_MAP_UNWINDOW = 1, GEMM_MAP_SHUFFLE2 = 2 };
+enum { GEMM_MAP_IDENTITY = 0, GEMM_MAP_UNWINDOW = 1, GEMM_MAP_SHUFFLE2 = 2, GEMM_MAP_POOL2 = 3 };
 
 struct GemmEpilogue {
   const float* bias = nullptr;       // [N] (for SHUFFLE2: [N/4], indexed by output channel)
@@ -26,6 +26,10 @@ struct GemmEpilogue {
   int map_mode = GEMM_MAP_IDENTITY;
   // UNWINDOW: source row = ((b*nwy + wy)*nwx + wx)*ws*ws + ty*ws + tx  ->  dest row (b*H + wy*ws+ty)*W + wx*ws+tx,
   //           rows that fall in the window padding (y >= H or x >= W) are dropped.
+  // POOL2:    window-major source rows (ws = 4 or 8, no window padding); the output row (b, y/2, x/2) on the H/2 x W/2 grid
+  //           receives the MAXIMUM over the 2 x 2 source rows (Hiera's Q-pool shortcut: maxpool2x2(proj(norm(x)))),
+  //           fp32 output, no residual — the four rows of a group sit in one warp's TMEM lanes, so the pooling is two
+  //           shuffles per element in the epilogue and only a quarter of the rows is ever written.
   // SHUFFLE2: source row (b,y,x) on an H x W grid, column n = (dy*2+dx)*Cout + co -> dest row
   //           (b*2H + 2y+dy)*2W + 2x+dx, dest column co   (ConvTranspose2d kernel 2 stride 2)
   int ws = 0, nwx = 0, nwy = 0, H = 0, W = 0, cout = 0;

@@ -292,10 +292,20 @@ static int run_block(cv_sam2* h, int i, int B, float* X, float* Xn, cudaStream_t
     float* S = BUF<float>(h, "S");
     GemmEpilogue es;
     es.bias = WF(h, pre + ".sc.b");
-    es.out_f32 = S;
     es.ld_f32 = C;
-    TRY(gemm(h, A, Cin, WB(h, pre + ".sc.w"), (int)M, C, Cin, es, st));
-    TRY(launch_pool_shortcut(S, B, H, W, ws, C, Xn, st));
+    if ((ws == 4 || ws == 8) && H % ws == 0 && W % ws == 0) {
+      // windows of 4 / 8 tokens per side: the 2 x 2 pooling groups sit inside one warp of the epilogue, the GEMM
+      // writes the pooled rows directly (no [M, C] fp32 round trip through HBM)
+      es.out_f32 = Xn;
+      es.map_mode = GEMM_MAP_POOL2;
+      es.ws = ws; es.nwx = nwx; es.nwy = nwy; es.H = H; es.W = W;
+      TRY(gemm(h, A, Cin, WB(h, pre + ".sc.w"), (int)M, C, Cin, es, st));
+      h->launches--;  // one launch instead of two (the += 2 below counts pool_shortcut + pool_q)
+    } else {
+      es.out_f32 = S;
+      TRY(gemm(h, A, Cin, WB(h, pre + ".sc.w"), (int)M, C, Cin, es, st));
+      TRY(launch_pool_shortcut(S, B, H, W, ws, C, Xn, st));
+    }
     bf16* Qp = BUF<bf16>(h, "Qp");
     TRY(launch_pool_q(QKV, 3 * Cp, (int)(M / (ws * ws)), ws, Cp, h->f16, Qp, st));
     h->launches += 2;
