@@ -64,6 +64,14 @@ __device__ __forceinline__ long long gemm_dest_row(const GemmEpilogue& e, int ma
     if (y >= (unsigned)e.H || x >= (unsigned)e.W) return -1;
     return (long long)((b * (unsigned)e.H + y) * (unsigned)e.W + x);
   }
+  if (map == GEMM_MAP_QPOOL) {
+    const unsigned r = (unsigned)r64;
+    const unsigned ws = (unsigned)e.ws, w2 = ws * ws;
+    const unsigned win = r / w2, t = r - win * w2;
+    const unsigned ty = t / ws, tx = t - ty * ws;
+    if ((ty | tx) & 1u) return -1;
+    return (long long)(win * (w2 >> 2) + (ty >> 1) * (ws >> 1) + (tx >> 1));
+  }
   if (map == GEMM_MAP_POOL2) {
     // anchor rows (even ty, even tx) own the pooled output row; every other row returns -1
     const unsigned r = (unsigned)r64;
@@ -113,13 +121,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
   static_assert(CG == 1 || CG == 2, "CG");
   static_assert(EW == 8 || EW == 16, "EW");
-  constexpr int GEMM_EPI_BUF = (OUT == 1 && MAP == GEMM_MAP_IDENTITY) ? 2048 : 4096;  // 16-bit TMA box or fp32 staging
+  constexpr int GEMM_EPI_BUF = (OUT == 1 && (MAP == GEMM_MAP_IDENTITY || MAP == GEMM_MAP_QPOOL)) ? 2048 : 4096;  // 16-bit TMA box or fp32 staging
   constexpr int GEMM_STAGES = gemm_stages<BN, CG, EW, GEMM_EPI_BUF>();
   constexpr int EPI_BUFS = gemm_epi_bufs<BN, CG, EW>();
   static_assert(GEMM_STAGES >= 2, "smem ring");
   constexpr int A_BYTES = GEMM_BM * 128, B_BYTES = (BN / CG) * 128;
   constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  constexpr bool TMA_OUT = (MAP == GEMM_MAP_IDENTITY) && (OUT == 0 || OUT == 1);
+  constexpr bool TMA_OUT = (MAP == GEMM_MAP_IDENTITY && (OUT == 0 || OUT == 1)) || (MAP == GEMM_MAP_QPOOL && OUT == 1);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -247,6 +255,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
       // remapped destination rows: every lane maps its own row once, the row-segment owners fetch it by shuffle
       // (a destination row index never exceeds the source row count, so it fits an int)
       int dest[8];
+      if (MAP == GEMM_MAP_QPOOL) dest[0] = (myrow < p.M) ? (int)gemm_dest_row(e, map, myrow) : -1;
       if (!TMA_OUT) {
         int dmine = (myrow < p.M) ? (int)gemm_dest_row(e, map, myrow) : -1;
         if (map == GEMM_MAP_SHUFFLE2 && dmine >= 0) {
@@ -338,6 +347,26 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
           if (has_res && !rba) {
 #pragma unroll
             for (int j = 0; j < 8; j++) { f[4 * j] += rv[j].x; f[4 * j + 1] += rv[j].y; f[4 * j + 2] += rv[j].z; f[4 * j + 3] += rv[j].w; }
+          }
+          if (MAP == GEMM_MAP_QPOOL && col0 < e.pool_cols) {
+            // q columns of a Q-pooled block: 2 x 2 max over lanes (l, l+1, l+ws, l+ws+1), anchors store 32 values
+            const int wsl = e.ws;
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+              float m = fmaxf(f[i], __shfl_down_sync(0xffffffffu, f[i], 1));
+              f[i] = fmaxf(m, __shfl_down_sync(0xffffffffu, m, wsl));
+            }
+            if (dest[0] >= 0) {
+              uint4* o = (uint4*)(e.pool_out + (long long)dest[0] * e.ld_pool + col0);
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                uint32_t w[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) w[k] = tc::pack16(e.fp16, f[8 * j + 2 * k], f[8 * j + 2 * k + 1]);
+                o[j] = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+            }
+            continue;
           }
           if (OUT == 0) {
             // fp32 box: 128-byte rows, 128B swizzle (16-byte chunk j of row r lives at chunk j ^ (r & 7))
@@ -437,7 +466,7 @@ static int launch_cfg(const __nv_bfloat16* A, long long lda, const __nv_bfloat16
                       const GemmEpilogue& epi, int num_sms, cudaStream_t st) {
   static std::atomic<unsigned long long> attr_set{0};
   constexpr int GEMM_THREADS = 128 + 32 * EW;
-  constexpr int smem = gemm_smem_bytes<BN, CG, EW, (OUT == 1 && MAP == GEMM_MAP_IDENTITY) ? 2048 : 4096>();
+  constexpr int smem = gemm_smem_bytes<BN, CG, EW, (OUT == 1 && (MAP == GEMM_MAP_IDENTITY || MAP == GEMM_MAP_QPOOL)) ? 2048 : 4096>();
   static_assert(smem <= GEMM_SMEM_MAX, "shared memory budget");
   auto kern = k_gemm_tc<BN, ACT, RES, OUT, MAP, RBA, CG, EW>;
   if (cvb_once_per_device(attr_set)) {
@@ -448,7 +477,7 @@ static int launch_cfg(const __nv_bfloat16* A, long long lda, const __nv_bfloat16
   if (!tc_host::make_tmap_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM) ||
       !tc_host::make_tmap_bf16(&tw, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, BN / CG))
     return cvb_fail(CV_ERR_CUDA, "cuTensorMapEncodeTiled failed (GEMM operands)");
-  constexpr bool TMA_OUT = (MAP == GEMM_MAP_IDENTITY) && (OUT == 0 || OUT == 1);
+  constexpr bool TMA_OUT = (MAP == GEMM_MAP_IDENTITY && (OUT == 0 || OUT == 1)) || (MAP == GEMM_MAP_QPOOL && OUT == 1);
   if (TMA_OUT) {
     bool ok = OUT == 0 ? tc_host::make_tmap_2d(&to, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, epi.out_f32, (uint64_t)M, (uint64_t)N,
                                                (uint64_t)epi.ld_f32 * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)
@@ -529,6 +558,13 @@ static int launch_bn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16*
   }
   if (e.map_mode == GEMM_MAP_UNWINDOW && f32 && !b16 && res && e.act == GEMM_ACT_NONE)
     return launch_cfg<BN, 0, 1, 0, 1, 0>(CVB_GEMM_ARGS);                                             // windowed proj
+  if (e.map_mode == GEMM_MAP_QPOOL) {
+    const bool tma16 = b16 && !f32 && ((uintptr_t)e.out_bf16 & 15) == 0 && (e.ld_bf16 % 8) == 0;
+    if (!tma16 || res || e.act != GEMM_ACT_NONE || (e.ws != 4 && e.ws != 8) || !e.pool_out || (e.pool_cols % 32) ||
+        ((uintptr_t)e.pool_out & 15) || (e.ld_pool % 8))
+      return cvb_fail(CV_ERR_INVALID, "gemm: QPOOL needs a 16-bit TMA output, no residual / activation, windows of 4 or 8");
+    return launch_cfg<BN, 0, 0, 1, 4, 0>(CVB_GEMM_ARGS);                                             // qkv of a Q-pooled block
+  }
   if (e.map_mode == GEMM_MAP_POOL2) {
     if (!f32 || b16 || res || e.act != GEMM_ACT_NONE || (e.ws != 4 && e.ws != 8) || (e.H % e.ws) || (e.W % e.ws))
       return cvb_fail(CV_ERR_INVALID, "gemm: POOL2 needs fp32 output, no residual / activation, windows of 4 or 8 without padding");

@@ -10,7 +10,7 @@
 namespace cvb {
 
 enum { GEMM_ACT_NONE = 0, GEMM_ACT_GELU = 1, GEMM_ACT_RELU = 2 };
-enum { GEMM_MAP_IDENTITY = 0, GEMM_MAP_UNWINDOW = 1, GEMM_MAP_SHUFFLE2 = 2, GEMM_MAP_POOL2 = 3 };
+enum { GEMM_MAP_IDENTITY = 0, GEMM_MAP_UNWINDOW = 1, GEMM_MAP_SHUFFLE2 = 2, GEMM_MAP_POOL2 = 3, GEMM_MAP_QPOOL = 4 };
 
 struct GemmEpilogue {
   const float* bias = nullptr;       // [N] (for SHUFFLE2: [N/4], indexed by output channel)
@@ -30,9 +30,16 @@ struct GemmEpilogue {
   //           receives the MAXIMUM over the 2 x 2 source rows (Hiera's Q-pool shortcut: maxpool2x2(proj(norm(x)))),
   //           fp32 output, no residual — the four rows of a group sit in one warp's TMEM lanes, so the pooling is two
   //           shuffles per element in the epilogue and only a quarter of the rows is ever written.
+  // QPOOL:    16-bit identity output (TMA stores) for the columns >= pool_cols; the columns < pool_cols (the q part of a
+  //           Q-pooled block's qkv) are 2 x 2 max-pooled over window-major rows (ws = 4 or 8) and written to `pool_out`
+  //           in pooled window-major order (row = win*(ws/2)^2 + (ty/2)*(ws/2) + tx/2); their full-resolution copy is
+  //           never written (nothing reads it).
   // SHUFFLE2: source row (b,y,x) on an H x W grid, column n = (dy*2+dx)*Cout + co -> dest row
   //           (b*2H + 2y+dy)*2W + 2x+dx, dest column co   (ConvTranspose2d kernel 2 stride 2)
   int ws = 0, nwx = 0, nwy = 0, H = 0, W = 0, cout = 0;
+  int pool_cols = 0;                 // QPOOL
+  __nv_bfloat16* pool_out = nullptr;
+  long long ld_pool = 0;
   int fp16 = 0;                      // operands (A, W) and the 16-bit output are IEEE half instead of bf16
 };
 

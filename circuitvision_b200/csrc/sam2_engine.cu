@@ -282,6 +282,15 @@ static int run_block(cv_sam2* h, int i, int B, float* X, float* Xn, cudaStream_t
   e.out_bf16 = QKV;
   const int Cp = p.heads * h->D, D = h->D;  // q | k | v each Cp wide, head i at columns [i*D, i*D + hd) (+ zero padding)
   e.ld_bf16 = 3 * Cp;
+  // Q-pooled blocks with windows of 4 / 8: both 2 x 2 max-poolings (q and the shortcut) happen in the GEMM epilogues
+  const bool fuse_pool = p.pool && (ws == 4 || ws == 8) && H % ws == 0 && W % ws == 0 && Cp % 32 == 0;
+  if (fuse_pool) {
+    e.map_mode = GEMM_MAP_QPOOL;
+    e.ws = ws;
+    e.pool_cols = Cp;
+    e.pool_out = BUF<bf16>(h, "Qp");
+    e.ld_pool = Cp;
+  }
   TRY(gemm(h, A, Cin, WB(h, pre + ".qkv.w"), (int)M, 3 * Cp, Cin, e, st));
   float* Xo = X;
   long long To = T;
@@ -293,7 +302,7 @@ static int run_block(cv_sam2* h, int i, int B, float* X, float* Xn, cudaStream_t
     GemmEpilogue es;
     es.bias = WF(h, pre + ".sc.b");
     es.ld_f32 = C;
-    if ((ws == 4 || ws == 8) && H % ws == 0 && W % ws == 0) {
+    if (fuse_pool) {
       // windows of 4 / 8 tokens per side: the 2 x 2 pooling groups sit inside one warp of the epilogue, the GEMM
       // writes the pooled rows directly (no [M, C] fp32 round trip through HBM)
       es.out_f32 = Xn;
@@ -307,8 +316,8 @@ static int run_block(cv_sam2* h, int i, int B, float* X, float* Xn, cudaStream_t
       TRY(launch_pool_shortcut(S, B, H, W, ws, C, Xn, st));
     }
     bf16* Qp = BUF<bf16>(h, "Qp");
-    TRY(launch_pool_q(QKV, 3 * Cp, (int)(M / (ws * ws)), ws, Cp, h->f16, Qp, st));
-    h->launches += 2;
+    if (!fuse_pool) TRY(launch_pool_q(QKV, 3 * Cp, (int)(M / (ws * ws)), ws, Cp, h->f16, Qp, st));
+    h->launches += fuse_pool ? 1 : 2;
     TRY(attn_tc_launch(Qp, Cp, Cp, 0, QKV, 3 * Cp, 3 * Cp, Cp, QKV, 3 * Cp, 3 * Cp, 2 * Cp, (int)(M / 4), (int)M, Wkv / 4, Wkv,
                        p.heads, D, scale, AO, Cp, h->f16, st));
     Xo = Xn; Ho = H / 2; Wo = W / 2; wso = ws / 2; To = T / 4;
