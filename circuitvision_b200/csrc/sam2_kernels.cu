@@ -694,12 +694,15 @@ __global__ void __launch_bounds__(64) k_attn_t2i_part(const float* __restrict__ 
   if (t >= T) return;
   const int C = heads * 16;
   const float* qp = q + (long long)b * q_img_stride + (long long)t * C + h * 16;
-  float qv[16];
+  // packed fp32x2 arithmetic along the head dimension: q, k, v and the output accumulator are 8 pairs each, so a key
+  // costs 8 + 8 FFMA2 instead of 16 + 16 FFMA (the loop is issue-bound: one thread per query token)
+  uint64_t qv[8];
 #pragma unroll
-  for (int i = 0; i < 16; i++) qv[i] = __ldg(qp + i) * 0.36067376f;  // 1/sqrt(16) * log2(e)
-  float m = -INFINITY, l = 0.f, o[16];
+  for (int i = 0; i < 8; i++) qv[i] = pk2(__ldg(qp + 2 * i) * 0.36067376f, __ldg(qp + 2 * i + 1) * 0.36067376f);  // 1/sqrt(16) * log2(e)
+  float m = -INFINITY, l = 0.f;
+  uint64_t o[8];
 #pragma unroll
-  for (int i = 0; i < 16; i++) o[i] = 0.f;
+  for (int i = 0; i < 8; i++) o[i] = 0ull;
   for (int j0 = 0; j0 < nk; j0 += 8) {
     // 8 keys per step: one rescale per step instead of per key
     float sc[8], mx = m;
@@ -707,14 +710,17 @@ __global__ void __launch_bounds__(64) k_attn_t2i_part(const float* __restrict__ 
     for (int u = 0; u < 8; u++) {
       float sdot = -INFINITY;
       if (j0 + u < nk) {
-        const float4* kr = (const float4*)(sk + (j0 + u) * 16);
-        sdot = 0.f;
+        const ulonglong2* kr = (const ulonglong2*)(sk + (j0 + u) * 16);
+        uint64_t acc = 0ull;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-          float4 kk = kr[c];
-          sdot = fmaf(qv[c * 4], kk.x, sdot); sdot = fmaf(qv[c * 4 + 1], kk.y, sdot);
-          sdot = fmaf(qv[c * 4 + 2], kk.z, sdot); sdot = fmaf(qv[c * 4 + 3], kk.w, sdot);
+          const ulonglong2 kk = kr[c];
+          acc = fma2(qv[2 * c], kk.x, acc);
+          acc = fma2(qv[2 * c + 1], kk.y, acc);
         }
+        float a0, a1;
+        up2(acc, a0, a1);
+        sdot = a0 + a1;
       }
       sc[u] = sdot;
       mx = fmaxf(mx, sdot);
@@ -722,8 +728,9 @@ __global__ void __launch_bounds__(64) k_attn_t2i_part(const float* __restrict__ 
     float alpha;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(alpha) : "f"(m - mx));  // m = -inf -> 0
     l *= alpha;
+    const uint64_t al2 = pk2(alpha, alpha);
 #pragma unroll
-    for (int i = 0; i < 16; i++) o[i] *= alpha;
+    for (int i = 0; i < 8; i++) o[i] = mul2(o[i], al2);
     m = mx;
 #pragma unroll
     for (int u = 0; u < 8; u++) {
@@ -731,12 +738,13 @@ __global__ void __launch_bounds__(64) k_attn_t2i_part(const float* __restrict__ 
       asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe) : "f"(sc[u] - mx));  // masked keys: ex2(-inf) = 0
       l += pe;
       if (j0 + u < nk) {
-        const float4* vr = (const float4*)(sv + (j0 + u) * 16);
+        const ulonglong2* vr = (const ulonglong2*)(sv + (j0 + u) * 16);
+        const uint64_t pe2 = pk2(pe, pe);
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-          float4 vv = vr[c];
-          o[c * 4] = fmaf(pe, vv.x, o[c * 4]); o[c * 4 + 1] = fmaf(pe, vv.y, o[c * 4 + 1]);
-          o[c * 4 + 2] = fmaf(pe, vv.z, o[c * 4 + 2]); o[c * 4 + 3] = fmaf(pe, vv.w, o[c * 4 + 3]);
+          const ulonglong2 vv = vr[c];
+          o[2 * c] = fma2(pe2, vv.x, o[2 * c]);
+          o[2 * c + 1] = fma2(pe2, vv.y, o[2 * c + 1]);
         }
       }
     }
@@ -746,7 +754,7 @@ __global__ void __launch_bounds__(64) k_attn_t2i_part(const float* __restrict__ 
   pp[0] = m * 0.69314718056f;
   pp[1] = l;
 #pragma unroll
-  for (int i = 0; i < 16; i++) pp[2 + i] = o[i];
+  for (int i = 0; i < 8; i++) up2(o[i], pp[2 + 2 * i], pp[3 + 2 * i]);
 }
 
 __global__ void k_attn_t2i_combine(const float* __restrict__ part, int T, int heads, int nsplit, long long total,
