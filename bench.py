@@ -518,5 +518,15 @@ def main():
         dist.destroy_process_group()
 
 
+def _only_json_on_stdout():
+    """Libraries print to the process's stdout on their own (NCCL's version banner on the first collective, for one):
+    everything the run prints goes to stderr, and only the JSON line reaches the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 if __name__ == "__main__":
+    _only_json_on_stdout()
     main()
