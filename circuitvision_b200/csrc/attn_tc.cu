@@ -30,6 +30,8 @@ struct AttnParams {
   float scale_log2;         // softmax scale * log2(e)
   int fp16;                 // q/k/v/P/out are IEEE half instead of bf16
   int skip_chunks;          // windowed kernel: skip score chunks no row of the warp can see
+  int q_rows;               // windowed kernel: query rows per work item (<= 128), a whole number of windows or an even
+                            // split of one window, so that an item never straddles windows it does not need
   __nv_bfloat16* out;       // [Mq, heads*96]
   long long ld_out;
 };
@@ -323,8 +325,8 @@ __device__ __forceinline__ WinItem win_item(const AttnParams& p, int n_items, in
   w.valid = it < n_items;
   int qt = it / p.heads;
   w.head = it - qt * p.heads;
-  w.q0 = qt * ATT_BM;
-  int r_last = min(w.q0 + ATT_BM - 1, p.Mq - 1);
+  w.q0 = qt * p.q_rows;
+  int r_last = min(w.q0 + p.q_rows - 1, p.Mq - 1);
   w.kv_lo = (w.q0 / p.Wq) * p.Wkv;
   int kv_hi = (r_last / p.Wq + 1) * p.Wkv;
   w.n_kt = w.valid ? (kv_hi - w.kv_lo + ATT_BN - 1) / ATT_BN : 0;
@@ -491,7 +493,7 @@ k_attn_win(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUten
       const WinItem it = win_item(p, n_items, 2 * pp + g);
       if (it.n_kt == 0) continue;
       const int grow = it.q0 + r;
-      const bool row_ok = grow < p.Mq;
+      const bool row_ok = grow < p.Mq && r < p.q_rows;  // the TMA box always brings 128 rows; the tail belongs to the next item
       const int wq = (row_ok ? grow : it.q0) / p.Wq;
       const int vis0 = wq * p.Wkv - it.kv_lo;  // first visible key relative to the item's first key tile
       float m_ref = -INFINITY, l = 0.f;
@@ -628,7 +630,7 @@ static int attn_launch_d(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
     cudaError_t e = cudaFuncSetAttribute(k_attn_win<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, aw_smem<D>());
     if (e != cudaSuccess) return cvb_fail_cuda(e, "cudaFuncSetAttribute(k_attn_win)");
   }
-  const int n_items = ((p.Mq + ATT_BM - 1) / ATT_BM) * p.heads;
+  const int n_items = ((p.Mq + p.q_rows - 1) / p.q_rows) * p.heads;
   const int n_pairs = (n_items + 1) / 2;
   const int grid = n_pairs < device_sm_count() ? n_pairs : device_sm_count();
   CVB_LAUNCH((k_attn_win<D>), dim3(grid), dim3(AW_THREADS), aw_smem<D>(), st, tq, tk, tv, p, n_items);
@@ -661,6 +663,19 @@ int attn_tc_launch(const __nv_bfloat16* q, long long ldq, int qcols, int qcol0, 
     // slightly better; CVB_ATTN_SKIP = 0 turns it off
     static const int force = getenv("CVB_ATTN_SKIP") ? atoi(getenv("CVB_ATTN_SKIP")) : 1;
     p.skip_chunks = force != 0;
+    // window-aligned items: 14 x 14 windows (196 rows) -> two items of 98 rows with exactly the window's 196 keys (two key
+    // tiles instead of three to four); 7 x 7 windows (49 rows) -> 98 rows = two whole windows; windows that divide 128
+    // keep 128-row items.  CVB_ATTN_ALIGN = 0 restores 128-row items everywhere.
+    static const int align = getenv("CVB_ATTN_ALIGN") ? atoi(getenv("CVB_ATTN_ALIGN")) : 1;
+    p.q_rows = ATT_BM;
+    if (align) {
+      if (Wq > ATT_BM) {
+        const int parts = (Wq + ATT_BM - 1) / ATT_BM;
+        if (Wq % parts == 0) p.q_rows = Wq / parts;
+      } else if (ATT_BM % Wq) {
+        p.q_rows = (ATT_BM / Wq) * Wq;
+      }
+    }
   }
   p.out = out; p.ld_out = ld_out;
   const bool glob = Wq == Wkv && (Wkv % ATT_BN) == 0 && (Wq % (2 * ATT_BM)) == 0 && (Mq % (2 * ATT_BM)) == 0;
