@@ -313,9 +313,13 @@ k_attn_global(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
 // The running maximum is fixed at the first tile that has visible keys and O / l are rescaled only when a later tile
 // exceeds it by more than 2^8 (same exactness argument as the global kernel).
 constexpr int AW_THREADS = 384;
-constexpr int AW_RING = 4;
+// K/V ring depth: the ring feeds both slots in MMA consumption order and a V tile stays in it until its P is ready, so
+// a shallow ring serialises the TMA latency behind the softmax; 5 tiles of 32 KB (head dim 96) / 8 of 16 KB (64) fit.
 template <int D>
-constexpr int aw_smem() { return 1024 + att_tile_bytes<D>() * (2 + AW_RING) + 256; }
+constexpr int aw_ring() { return D > 64 ? 5 : 8; }
+static_assert(1024 + 32768 * (2 + 5) + 256 <= 232448, "windowed attention shared memory");
+template <int D>
+constexpr int aw_smem() { return 1024 + att_tile_bytes<D>() * (2 + aw_ring<D>()) + 256; }
 
 struct WinItem {
   int q0, kv_lo, n_kt, head, valid;
@@ -337,7 +341,7 @@ template <int D>
 __global__ void __launch_bounds__(AW_THREADS, 1)
 k_attn_win(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
            const __grid_constant__ CUtensorMap tv, AttnParams p, int n_items) {
-  constexpr int ATT_D = D, ATT_TILE_BYTES = att_tile_bytes<D>();
+  constexpr int ATT_D = D, ATT_TILE_BYTES = att_tile_bytes<D>(), AW_RING = aw_ring<D>();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;                       // [2]
