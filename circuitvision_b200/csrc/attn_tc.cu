@@ -221,16 +221,25 @@ k_attn_global(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
         tc::tmem_ld_wait();
         if (c + 1 < ATT_BN / 32) tc::tmem_ld_32x32(tS + (c + 1) * 32, v[(c + 1) & 1]);
         uint32_t pk[16];
+        float pe[32];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const float s0 = __uint_as_float(v[c & 1][i]), s1 = __uint_as_float(v[c & 1][i + 1]);
           asm("max.f32 %0, %0, %1, %2;" : "+f"(tmax) : "f"(s0), "f"(s1));
           float x0, x1;
           up2(fma2(pk2(s0, s1), sc2, mr2), x0, x1);
-          const float p0 = ex2(x0), p1 = ex2(x1);
-          const uint64_t pp = pk2(p0, p1);
+          pe[i] = ex2(x0);
+          pe[i + 1] = ex2(x1);
+          const uint64_t pp = pk2(pe[i], pe[i + 1]);
           asm("add.rn.f32x2 %0, %0, %1;" : "+l"(rs2) : "l"(pp));
-          pk[i >> 1] = tc::pack16(p.fp16, p0, p1);
+        }
+        // one uniform branch per chunk on the operand format instead of a predicated pair of conversions per score pair
+        if (p.fp16) {
+#pragma unroll
+          for (int i = 0; i < 16; i++) pk[i] = tc::pack16(1, pe[2 * i], pe[2 * i + 1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; i++) pk[i] = tc::pack16(0, pe[2 * i], pe[2 * i + 1]);
         }
         tc::tmem_st_32x16(tS + c * 16, pk);  // P over the already-consumed head of S
       }
