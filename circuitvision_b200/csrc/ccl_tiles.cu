@@ -4,15 +4,16 @@
 // canonical: labels[p] = 1 + min linear index of p's component, 0 for background.
 //
 // Traffic plan (the kernel is HBM-bound; algorithmic bytes = 1 B/px mask read + 4 B/px label write):
-//   pass A  k_ccl_tile_label : each CTA loads a 128 x 32 tile of the mask as BITS (one 32-pixel word per thread), labels it
+//   pass A  k_ccl_tile_label : each CTA loads a 256 x 32 tile of the mask as BITS (one 32-pixel word per thread), labels it
 //                              entirely in shared memory (elements = maximal horizontal runs; unions between adjacent
-//                              rows by bit overlap; atomicMin union-find on a 16 KB parent array) and writes the label
+//                              rows by bit overlap; atomicMin union-find on a 16 KB parent array, one slot per pixel pair) and writes the label
 //                              image once, fully coalesced: 1 + 4 B/px.  It also emits a per-word "dirty" bitmap
 //                              (word holds a run of a component that touches the tile border) and counts the
 //                              components that stay inside their tile.
-//   pass B  k_ccl_tile_seams : only pixels on tile seams (3.9 % of the image) merge components across tiles with the
+//   pass B  k_ccl_seams_h/_v : only the tile seams (3.5 % of the image; horizontal seams one 32-pixel word per thread, one
+//                              union per run contact) merge components across tiles with the
 //                              global atomicMin union-find on the label image (roots point at roots).
-//   pass B2 k_ccl_tile_compress: path halving from the same seam pixels so the trees pass C walks are one or two hops deep.
+//   pass B2 k_ccl_compress_h/_v: path halving from the same seam runs / pixels so the trees pass C walks are one or two hops deep.
 //   pass C  k_ccl_tile_fixup : one thread per 32-pixel word re-reads the mask bits (1 B/px, no full label read), takes
 //                              the tile-local root named at each sub-run's first pixel, looks up its global root and
 //                              rewrites only the runs whose component changed (sparse row segments); counts roots.
@@ -25,7 +26,7 @@
 
 namespace cvb {
 
-constexpr int CT_W = 128, CT_H = 32, CT_WORDS = CT_W / 32, CT_THREADS = CT_H * CT_WORDS;
+constexpr int CT_W = 256, CT_H = 32, CT_WORDS = CT_W / 32, CT_THREADS = CT_H * CT_WORDS;  // 256 x 32 tile, 256 threads
 
 // ---- global union-find on the label image (parent of x = L[x] - 1; 0 = background)
 __device__ __forceinline__ int gfind(const int* L, int x) {
@@ -200,7 +201,7 @@ __device__ __forceinline__ uint32_t tile_label(const uint8_t* __restrict__ im, i
 // touches the tile border — only such components can be merged by the seam pass, so only those words are revisited by
 // pass C.  Components that stay inside their tile are final after pass A and are counted here.
 template <int CONN>
-__global__ void __launch_bounds__(CT_THREADS, 12) k_ccl_tile_label(const uint8_t* __restrict__ masks, int* __restrict__ labels,
+__global__ void __launch_bounds__(CT_THREADS, 8) k_ccl_tile_label(const uint8_t* __restrict__ masks, int* __restrict__ labels,
                                                                 int H, int W, int vec_ok, uint32_t* __restrict__ dirty,
                                                                 int* __restrict__ ncomp, int* __restrict__ partial) {
   __shared__ uint32_t bits[CT_H][CT_WORDS];
@@ -252,93 +253,110 @@ __global__ void __launch_bounds__(CT_THREADS, 12) k_ccl_tile_label(const uint8_t
     if (partial) atomicAdd(partial + ((size_t)b * 32 + ((blockIdx.x + blockIdx.y) & 31)) * 32, closed_roots);
     else atomicAdd(ncomp + b, closed_roots);
   }
-  // coalesced label write: each warp takes rows warp, warp+4, ...; lane l owns pixels 4l..4l+3 of the row
+  // coalesced label write: each warp takes rows warp, warp + n_warps, ...; per 128-pixel segment of the row lane l owns
+  // pixels 4l..4l+3
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wc = lane >> 3, sh = (lane & 7) * 4;
+  const int sh = (lane & 7) * 4;
   for (int rr = warp; rr < CT_H; rr += CT_THREADS / 32) {
     const int y = y0 + rr;
     if (y >= H) break;
-    const uint32_t word = bits[rr][wc];
-    const uint32_t nib = (word >> sh) & 0xFu;
-    int out[4] = {0, 0, 0, 0};
-    if (nib) {
-      const int gb = rr * CT_W + wc * 32;
-      if (nib == 0xFu) {
-        out[0] = out[1] = out[2] = out[3] = G[(gb + run_start(word, sh)) >> 1];
-      } else {
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-          if ((nib >> k) & 1u) out[k] = G[(gb + run_start(word, sh + k)) >> 1];
+    for (int seg = 0; seg < CT_W / 128; seg++) {
+      const int wc = seg * 4 + (lane >> 3);
+      const uint32_t word = bits[rr][wc];
+      const uint32_t nib = (word >> sh) & 0xFu;
+      int out[4] = {0, 0, 0, 0};
+      if (nib) {
+        const int gb = rr * CT_W + wc * 32;
+        if (nib == 0xFu) {
+          out[0] = out[1] = out[2] = out[3] = G[(gb + run_start(word, sh)) >> 1];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if ((nib >> k) & 1u) out[k] = G[(gb + run_start(word, sh + k)) >> 1];
+        }
       }
-    }
-    const int x = x0 + lane * 4;
-    int* dst = L + (size_t)y * W + x;
-    if (vec_ok && x + 4 <= W) {
-      *(int4*)dst = make_int4(out[0], out[1], out[2], out[3]);
-    } else {
-      for (int k = 0; k < 4; k++)
-        if (x + k < W) dst[k] = out[k];
+      const int x = x0 + seg * 128 + lane * 4;
+      int* dst = L + (size_t)y * W + x;
+      if (vec_ok && x + 4 <= W) {
+        *(int4*)dst = make_int4(out[0], out[1], out[2], out[3]);
+      } else {
+        for (int k = 0; k < 4; k++)
+          if (x + k < W) dst[k] = out[k];
+      }
     }
   }
 }
 
-// seams: blockIdx.y selects (0) horizontal seams y = k*CT_H or (1) vertical seams x = k*CT_W
+// Seams.  Horizontal seams (rows y = k*CT_H, 3.1 % of the image) are handled one 32-pixel WORD per thread: the seam row
+// and the row above it are read as bits, and every (run below, run above) contact is one union between run
+// representatives — all pixels of a run carry the same tile-local root after pass A, so any pixel of it starts the
+// same find.  Vertical seams (columns x = k*CT_W, 0.8 %) stay one pixel per thread.
 template <int CONN>
-__global__ void __launch_bounds__(256) k_ccl_tile_seams(const uint8_t* __restrict__ masks, int* __restrict__ labels, int H,
-                                                        int W) {
+__global__ void __launch_bounds__(128) k_ccl_seams_h(const uint8_t* __restrict__ masks, int* __restrict__ labels, int H, int W,
+                                                      int vec_ok) {
+  const int b = blockIdx.z;
+  const uint8_t* im = masks + (size_t)b * H * W;
+  int* L = labels + (size_t)b * H * W;
+  const int y = (blockIdx.y + 1) * CT_H;
+  const int x0 = (blockIdx.x * 128 + threadIdx.x) * 32;
+  if (y >= H || x0 >= W) return;
+  const uint32_t cur = load_word(im, H, W, y, x0, vec_ok != 0);
+  if (!cur) return;
+  const uint32_t up = load_word(im, H, W, y - 1, x0, vec_ok != 0);
+  const int rowc = y * W + x0, rowu = (y - 1) * W + x0;
+  bool ul = false, ur = false;
+  if (CONN == 8) {
+    ul = x0 > 0 && im[rowu - 1] != 0;
+    ur = x0 + 32 < W && im[rowu + 32] != 0;
+  }
+  if (!up && !ul && !ur) return;
+  uint32_t rest = cur;
+  while (rest) {
+    const int st = __ffs(rest) - 1;
+    const int len = run_len(rest, st);
+    const uint32_t rm = run_mask(st, len);
+    rest &= ~rm;
+    uint32_t aw = rm;
+    if (CONN == 8) aw |= (rm << 1) | (rm >> 1);
+    uint32_t cand = aw & up;
+    while (cand) {
+      const int us = __ffs(cand) - 1;
+      const int ust = run_start(up, us);
+      cand &= ~run_mask(ust, run_len(up, ust));
+      gunion(L, rowc + st, rowu + ust);
+    }
+    if (CONN == 8) {
+      if (st == 0 && ul) gunion(L, rowc, rowu - 1);
+      if (st + len == 32 && ur) gunion(L, rowc + 31, rowu + 32);
+    }
+  }
+}
+
+template <int CONN>
+__global__ void __launch_bounds__(256) k_ccl_seams_v(const uint8_t* __restrict__ masks, int* __restrict__ labels, int H, int W) {
   const int b = blockIdx.z;
   const uint8_t* im = masks + (size_t)b * H * W;
   int* L = labels + (size_t)b * H * W;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (blockIdx.y == 0) {
-    const int n_seams = (H - 1) / CT_H;  // rows CT_H, 2*CT_H, ... < H
-    if (t >= (long long)n_seams * W) return;
-    const int y = (int)(t / W + 1) * CT_H, x = (int)(t % W);
-    const int p = y * W + x;
-    if (!im[p]) return;
-    const bool left = x > 0 && im[p - 1], up = im[p - W] != 0;
-    const bool ul = x > 0 && im[p - W - 1], ur = x + 1 < W && im[p - W + 1];
-    if (up) {
-      if (!(left && ul)) gunion(L, p, p - W);
-    } else if (CONN == 8) {
-      if (ul && !left) gunion(L, p, p - W - 1);
-      if (ur) gunion(L, p, p - W + 1);
-    }
-  } else {
-    const int n_seams = (W - 1) / CT_W;
-    if (t >= (long long)n_seams * H) return;
-    const int x = (int)(t / H + 1) * CT_W, y = (int)(t % H);
-    const int p = y * W + x;
-    if (!im[p]) return;
-    if (im[p - 1]) {
-      gunion(L, p, p - 1);
-    } else if (CONN == 8) {
-      if (y > 0 && im[p - W - 1]) gunion(L, p, p - W - 1);
-      if (y + 1 < H && im[p + W - 1]) gunion(L, p, p + W - 1);
-    }
+  const int n_seams = (W - 1) / CT_W;
+  if (t >= (long long)n_seams * H) return;
+  const int x = (int)(t / H + 1) * CT_W, y = (int)(t % H);
+  const int p = y * W + x;
+  if (!im[p]) return;
+  if (im[p - 1]) {
+    gunion(L, p, p - 1);
+  } else if (CONN == 8) {
+    if (y > 0 && im[p - W - 1]) gunion(L, p, p - W - 1);
+    if (y + 1 < H && im[p + W - 1]) gunion(L, p, p + W - 1);
   }
 }
 
 // pass B2: the seam unions link tile roots to tile roots without compression, so a component that crosses many tiles
-// (a wire network) ends up as a deep tree.  Every seam pixel re-walks its root's path with path halving (each step
-// re-points a node at its grandparent with atomicMin), after which pass C finds global roots in one or two hops.
-__global__ void __launch_bounds__(256) k_ccl_tile_compress(const uint8_t* __restrict__ masks, int* __restrict__ labels, int H,
-                                                           int W) {
-  const int b = blockIdx.z;
-  const uint8_t* im = masks + (size_t)b * H * W;
-  int* L = labels + (size_t)b * H * W;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  int p;
-  if (blockIdx.y == 0) {
-    const int n_seams = (H - 1) / CT_H;
-    if (t >= (long long)n_seams * W) return;
-    p = (int)(t / W + 1) * CT_H * W + (int)(t % W);
-  } else {
-    const int n_seams = (W - 1) / CT_W;
-    if (t >= (long long)n_seams * H) return;
-    p = (int)(t % H) * W + (int)(t / H + 1) * CT_W;
-  }
-  if (!im[p]) return;
+// (a wire network) ends up as a deep tree.  Every run on a horizontal seam row (one walk per run: its pixels share the
+// label) and every pixel on a vertical seam column re-walks its root's path with path halving (each step re-points a
+// node at its grandparent with atomicMin), after which pass C finds global roots in one or two hops.
+__device__ __forceinline__ void halve_path(int* L, int p) {
   int x = __ldcg(L + p) - 1;
   while (true) {
     const int y = __ldcg(L + x) - 1;
@@ -347,6 +365,27 @@ __global__ void __launch_bounds__(256) k_ccl_tile_compress(const uint8_t* __rest
     if (z != y) atomicMin(L + x, z + 1);  // ancestors only ever get smaller indices
     x = z;
   }
+}
+__global__ void __launch_bounds__(128) k_ccl_compress_h(const uint8_t* __restrict__ masks, int* __restrict__ labels, int H, int W,
+                                                         int vec_ok) {
+  const int b = blockIdx.z;
+  const uint8_t* im = masks + (size_t)b * H * W;
+  int* L = labels + (size_t)b * H * W;
+  const int y = (blockIdx.y + 1) * CT_H;
+  const int x0 = (blockIdx.x * 128 + threadIdx.x) * 32;
+  if (y >= H || x0 >= W) return;
+  const uint32_t cur = load_word(im, H, W, y, x0, vec_ok != 0);
+  for (uint32_t st = cur & ~(cur << 1); st; st &= st - 1) halve_path(L, y * W + x0 + __ffs(st) - 1);
+}
+__global__ void __launch_bounds__(256) k_ccl_compress_v(const uint8_t* __restrict__ masks, int* __restrict__ labels, int H, int W) {
+  const int b = blockIdx.z;
+  const uint8_t* im = masks + (size_t)b * H * W;
+  int* L = labels + (size_t)b * H * W;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_seams = (W - 1) / CT_W;
+  if (t >= (long long)n_seams * H) return;
+  const int p = (int)(t % H) * W + (int)(t / H + 1) * CT_W;
+  if (im[p]) halve_path(L, p);
 }
 
 // pass C: same thread <-> word mapping as pass A.  Only words flagged dirty are revisited.  The label pass A wrote at
@@ -376,7 +415,14 @@ __global__ void __launch_bounds__(CT_THREADS) k_ccl_tile_fixup(const uint8_t* __
       const int ref = __ldcg(L + px + len - 1);  // tile-local root + 1 (a run's last pixel is never a root unless len == 1)
       const int f = gfind(L, ref - 1);
       if (ref != f + 1) {
-        for (int k = 0; k < len; k++) L[px + k] = f + 1;
+        // rewrite the run: 16-byte stores over its aligned middle part (a 16-pixel wire crossing is 4 stores, not 16)
+        const int v = f + 1;
+        int k = 0;
+        if (vec_ok) {
+          for (; k < len && ((px + k) & 3); k++) L[px + k] = v;
+          for (; k + 4 <= len; k += 4) *(int4*)(L + px + k) = make_int4(v, v, v, v);
+        }
+        for (; k < len; k++) L[px + k] = v;
       }
       // this run starts at the first pixel of its component (pass A counted the roots of the words it left clean)
       n_roots += (f == px);
@@ -411,16 +457,22 @@ static int ccl_run(const uint8_t* masks, int B, int H, int W, int32_t* labels, i
   cvb_next_work(5.0 * px);
   static std::atomic<unsigned long long> carveout_set{0};
   if (cvb_once_per_device(carveout_set)) {
-    // 12 resident tiles x ~9.7 KB: ask for the large shared-memory split (the default heuristic left room for 6)
+    // 8 resident tiles x ~19 KB: ask for the large shared-memory split (the default heuristic leaves room for fewer)
     CVB_CHECK(cudaFuncSetAttribute(k_ccl_tile_label<CONN>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                    cudaSharedmemCarveoutMaxShared));
   }
   CVB_LAUNCH((k_ccl_tile_label<CONN>), tg, dim3(CT_THREADS), 0, st, masks, labels, H, W, vec_ok, dirty, n_components, partial);
-  const long long seam_px = max((long long)((H - 1) / CT_H) * W, (long long)((W - 1) / CT_W) * H);
-  if (seam_px > 0) {
-    CVB_LAUNCH((k_ccl_tile_seams<CONN>), dim3((unsigned)((seam_px + 255) / 256), 2, B), dim3(256), 0, st, masks, labels, H, W);
-    CVB_LAUNCH(k_ccl_tile_compress, dim3((unsigned)((seam_px + 255) / 256), 2, B), dim3(256), 0, st, masks, labels, H, W);
-  }
+  const int seams_h = (H - 1) / CT_H, seams_v = (W - 1) / CT_W;
+  const int words = (W + 31) / 32;
+  const long long vpx = (long long)seams_v * H;
+  if (seams_h > 0)
+    CVB_LAUNCH((k_ccl_seams_h<CONN>), dim3((words + 127) / 128, seams_h, B), dim3(128), 0, st, masks, labels, H, W, vec_ok);
+  if (vpx > 0)
+    CVB_LAUNCH((k_ccl_seams_v<CONN>), dim3((unsigned)((vpx + 255) / 256), 1, B), dim3(256), 0, st, masks, labels, H, W);
+  if (seams_h > 0)
+    CVB_LAUNCH(k_ccl_compress_h, dim3((words + 127) / 128, seams_h, B), dim3(128), 0, st, masks, labels, H, W, vec_ok);
+  if (vpx > 0)
+    CVB_LAUNCH(k_ccl_compress_v, dim3((unsigned)((vpx + 255) / 256), 1, B), dim3(256), 0, st, masks, labels, H, W);
   CVB_LAUNCH(k_ccl_tile_fixup, tg, dim3(CT_THREADS), 0, st, masks, labels, H, W, vec_ok, dirty, n_components, partial);
   if (n_components && partial) CVB_LAUNCH(k_ccl_count_finish, dim3(B), dim3(32), 0, st, partial, n_components, B);
   return CV_OK;
