@@ -503,7 +503,7 @@ def main():
 
     # ---- CPU baseline on this box's host cores (bounded sample)
     cpu = None
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:  # the CPU leg runs at N = 1 only (rank 0 is the only rank there)
         cores = os.cpu_count() or 1
         n_cpu = 128 if S <= 1024 else 32
         ips_nodes, dt, _ = cpu_nodes_throughput(n_cpu, S, cores, reps=3)
