@@ -362,7 +362,7 @@ __global__ void k_trace_stats(const uint8_t* __restrict__ bin, int h, int w, con
   ContourStats st = trace_outer_simple<uint8_t>(bin + (size_t)b * h * w, w, h, p % w, p / w, nullptr, 0);
   CandStat cs;
   cs.nverts = st.nverts;
-  cs.xmin = st.xmin; cs.ymin = st.ymin; cs.xmax = st.xmax; cs.ymax = st.ymax; cs.pad = 0;
+  cs.xmin = st.xmin; cs.ymin = st.ymin; cs.xmax = st.xmax; cs.ymax = st.ymax; cs.pad = -1;
   cs.a00 = st.a00; cs.a01 = st.a01;
   stats[(size_t)b * max_external + i] = cs;
 }
@@ -401,8 +401,25 @@ __device__ __forceinline__ uint32_t neighbours8(const uint32_t* sm, int w, int h
 __device__ __forceinline__ int chain_dx(int s) { return (int)((0x901Au >> (2 * s)) & 3u) - 1; }  // 1 1 0 -1 -1 -1 0 1
 __device__ __forceinline__ int chain_dy(int s) { return (int)((0xA901u >> (2 * s)) & 3u) - 1; }  // 0 -1 -1 -1 0 1 1 1
 
+// A long border (the wire network of a schematic: tens of thousands of steps) is ONE dependent chain, so the first walk
+// (statistics: vertex count, extents, polygon sums — needed by the area filter) cannot be split.  It drops a CHECKPOINT
+// every TRACE_CK steps, though: the walker's full state.  The second walk, which only has to write the vertices of the
+// contours that passed the filter, then starts one thread per checkpoint and each covers TRACE_CK steps — microseconds
+// instead of another full-length chain.
+constexpr int TRACE_CK = 256;
+struct __align__(16) TraceCk {
+  int32_t cand;     // candidate index within the image
+  int32_t x, y;     // current pixel
+  int32_t s;        // search direction state (-1: isolated pixel, the contour is its single vertex)
+  int32_t prev_s;
+  int32_t nverts;   // vertices emitted before this checkpoint
+  int32_t pad0, pad1;
+};
+
 // trace_outer_fg (node_prims.cuh) on the shared-memory bit plane: same visiting order, same vertex selection, same sums.
-__device__ ContourStats trace_outer_bits(const uint32_t* sm, int w, int h, int x0, int y0, int32_t* out, int cap) {
+// ck / n_ck / ck_cap: checkpoint pool of the image (nullptr: none are recorded); overflow sets *n_ck beyond ck_cap.
+__device__ ContourStats trace_outer_bits(const uint32_t* sm, int w, int h, int x0, int y0, int32_t* out, int cap,
+                                         TraceCk* ck, int* n_ck, int ck_cap, int cand) {
   ContourStats st;
   st.nverts = 0;
   st.xmin = st.xmax = x0;
@@ -423,9 +440,19 @@ __device__ ContourStats trace_outer_bits(const uint32_t* sm, int w, int h, int x
     st.ymin = min(st.ymin, y); st.ymax = max(st.ymax, y);
     st.nverts++;
   };
+  auto checkpoint = [&](int x, int y, int s, int prev_s) {
+    if (!ck) return;
+    const int i = atomicAdd(n_ck, 1);
+    if (i < ck_cap) {
+      TraceCk c;
+      c.cand = cand; c.x = x; c.y = y; c.s = s; c.prev_s = prev_s; c.nverts = st.nverts; c.pad0 = c.pad1 = 0;
+      ck[i] = c;
+    }
+  };
   // first neighbour clockwise, starting just after West: directions 3, 2, 1, 0, 7, 6, 5, 4
   const uint32_t n0 = neighbours8(sm, w, h, x0, y0);
   if (n0 == 0u) {
+    checkpoint(x0, y0, -1, 0);
     emit(x0, y0);  // isolated pixel
   } else {
     // rotate so that direction 3 becomes the top bit of a byte and scan downwards
@@ -434,7 +461,8 @@ __device__ ContourStats trace_outer_bits(const uint32_t* sm, int w, int h, int x
     const int x1 = x0 + chain_dx(s), y1 = y0 + chain_dy(s);
     int x3 = x0, y3 = y0;
     int prev_s = s ^ 4;
-    for (;;) {
+    for (int step = 0;; step++) {
+      if ((step & (TRACE_CK - 1)) == 0) checkpoint(x3, y3, s, prev_s);
       // counter-clockwise search for the next border pixel, starting after the back-pointer
       const uint32_t nb = neighbours8(sm, w, h, x3, y3);
       const uint32_t rot = ((nb | (nb << 8)) >> (s + 1)) & 0xFFu;  // bit j = direction (s + 1 + j) & 7
@@ -456,11 +484,40 @@ __device__ ContourStats trace_outer_bits(const uint32_t* sm, int w, int h, int x
   return st;
 }
 
+// second walk, one checkpoint: up to TRACE_CK steps from the recorded state, vertices written at their final positions
+__device__ void trace_segment_bits(const uint32_t* sm, int w, int h, int x0, int y0, const TraceCk& c, int32_t* out, int cap) {
+  if (c.s < 0) {  // isolated pixel
+    if (cap > 0) { out[0] = x0; out[1] = y0; }
+    return;
+  }
+  // the walk ends when it re-enters the start pixel's first step: (x1, y1) is the first neighbour found from (x0, y0)
+  const uint32_t n0 = neighbours8(sm, w, h, x0, y0);
+  const uint32_t r0 = ((n0 | (n0 << 8)) >> 4) & 0xFFu;
+  const int s0 = (31 - __clz(r0) + 4) & 7;
+  const int x1 = x0 + chain_dx(s0), y1 = y0 + chain_dy(s0);
+  int x3 = c.x, y3 = c.y, s = c.s, prev_s = c.prev_s, nv = c.nverts;
+  for (int step = 0; step < TRACE_CK; step++) {
+    const uint32_t nb = neighbours8(sm, w, h, x3, y3);
+    const uint32_t rot = ((nb | (nb << 8)) >> (s + 1)) & 0xFFu;
+    const int sn = rot ? ((s + 1 + (__ffs(rot) - 1)) & 7) : (s & 7);
+    const int x4 = x3 + chain_dx(sn), y4 = y3 + chain_dy(sn);
+    if (sn != prev_s) {
+      if (nv < cap) { out[2 * nv] = x3; out[2 * nv + 1] = y3; }
+      nv++;
+    }
+    prev_s = sn;
+    if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) break;
+    x3 = x4; y3 = y4;
+    s = (sn + 4) & 7;
+  }
+}
+
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_stats_bits(const uint32_t* __restrict__ bits, int words_per_image,
                                                                     int h, int w, const int* __restrict__ cand,
                                                                     int max_external,
                                                                     const cv_image_result* __restrict__ results,
-                                                                    CandStat* __restrict__ stats) {
+                                                                    CandStat* __restrict__ stats, TraceCk* __restrict__ ck,
+                                                                    int* __restrict__ n_ck, int ck_cap) {
   extern __shared__ __align__(16) uint32_t s_bits[];
   const int b = blockIdx.y;
   const int n = results[b].n_external;
@@ -468,12 +525,38 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_stats_bits(const uint32
   load_bits_to_smem(s_bits, bits + (size_t)b * words_per_image, words_per_image);
   for (int i = blockIdx.x * TRACE_THREADS + threadIdx.x; i < n; i += TRACE_CTAS * TRACE_THREADS) {
     const int p = cand[(size_t)b * max_external + i];
-    const ContourStats st = trace_outer_bits(s_bits, w, h, p % w, p / w, nullptr, 0);
+    const ContourStats st = trace_outer_bits(s_bits, w, h, p % w, p / w, nullptr, 0, ck ? ck + (size_t)b * ck_cap : nullptr,
+                                             n_ck + b, ck_cap, i);
     CandStat cs;
     cs.nverts = st.nverts;
-    cs.xmin = st.xmin; cs.ymin = st.ymin; cs.xmax = st.xmax; cs.ymax = st.ymax; cs.pad = 0;
+    cs.xmin = st.xmin; cs.ymin = st.ymin; cs.xmax = st.xmax; cs.ymax = st.ymax; cs.pad = -1;
     cs.a00 = st.a00; cs.a01 = st.a01;
     stats[(size_t)b * max_external + i] = cs;
+  }
+}
+
+// second walk from the checkpoints (stats[i].pad = id of the kept contour, -1 when the candidate was filtered out).
+// Images whose checkpoint pool overflowed are left to the sequential kernel below (`overflowed` selects which).
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_points_ck(const uint32_t* __restrict__ bits, int words_per_image,
+                                                                   int h, int w, const int* __restrict__ cand,
+                                                                   int max_external, const CandStat* __restrict__ stats,
+                                                                   const cv_contour* __restrict__ contours, int max_contours,
+                                                                   int max_points, const TraceCk* __restrict__ ck,
+                                                                   const int* __restrict__ n_ck, int ck_cap,
+                                                                   int32_t* __restrict__ points) {
+  extern __shared__ __align__(16) uint32_t s_bits[];
+  const int b = blockIdx.y;
+  const int n = n_ck[b];
+  if (n > ck_cap || (int)(blockIdx.x * TRACE_THREADS) >= n) return;
+  load_bits_to_smem(s_bits, bits + (size_t)b * words_per_image, words_per_image);
+  for (int i = blockIdx.x * TRACE_THREADS + threadIdx.x; i < n; i += gridDim.x * TRACE_THREADS) {
+    const TraceCk c = ck[(size_t)b * ck_cap + i];
+    const int id = stats[(size_t)b * max_external + c.cand].pad;
+    if (id < 0) continue;
+    const cv_contour& ct = contours[(size_t)b * max_contours + id];
+    if (ct.offset + ct.nverts > max_points) continue;
+    const int p = cand[(size_t)b * max_external + c.cand];
+    trace_segment_bits(s_bits, w, h, p % w, p / w, c, points + ((size_t)b * max_points + ct.offset) * 2, ct.nverts);
   }
 }
 
@@ -481,21 +564,24 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_points_bits(const uint3
                                                                      int h, int w, const cv_contour* __restrict__ contours,
                                                                      int max_contours, int max_points,
                                                                      const cv_image_result* __restrict__ results,
-                                                                     int32_t* __restrict__ points) {
+                                                                     int32_t* __restrict__ points, const int* __restrict__ n_ck,
+                                                                     int ck_cap) {
   extern __shared__ __align__(16) uint32_t s_bits[];
   const int b = blockIdx.y;
+  if (n_ck && n_ck[b] <= ck_cap) return;  // this image was written from its checkpoints
   const int n = results[b].n_contours;
   if ((int)(blockIdx.x * TRACE_THREADS) >= n) return;
   load_bits_to_smem(s_bits, bits + (size_t)b * words_per_image, words_per_image);
   for (int i = blockIdx.x * TRACE_THREADS + threadIdx.x; i < n; i += TRACE_CTAS * TRACE_THREADS) {
     const cv_contour& ct = contours[(size_t)b * max_contours + i];
     if (ct.offset + ct.nverts > max_points) continue;
-    trace_outer_bits(s_bits, w, h, ct.start_x, ct.start_y, points + ((size_t)b * max_points + ct.offset) * 2, ct.nverts);
+    trace_outer_bits(s_bits, w, h, ct.start_x, ct.start_y, points + ((size_t)b * max_points + ct.offset) * 2, ct.nverts,
+                     nullptr, nullptr, 0, 0);
   }
 }
 
 // area filter (contourArea / (h*w) > 0.0004) + ids + point-pool offsets; one CTA per image
-__global__ void __launch_bounds__(1024) k_filter_contours(const int* __restrict__ cand, const CandStat* __restrict__ stats,
+__global__ void __launch_bounds__(1024) k_filter_contours(const int* __restrict__ cand, CandStat* __restrict__ stats,
                                                           int max_external, int h, int w, double area_thr,
                                                           cv_contour* __restrict__ contours, int max_contours,
                                                           int max_points, cv_image_result* __restrict__ results) {
@@ -549,6 +635,7 @@ __global__ void __launch_bounds__(1024) k_filter_contours(const int* __restrict_
         int cy;
         ct.centroid_y = centroid_y(cs.a00, cs.a01, &cy) ? cy : INT_MIN;
         contours[(size_t)b * max_contours + id] = ct;
+        stats[(size_t)b * max_external + i].pad = id;  // read by the checkpointed second walk
       } else {
         status |= (id >= max_contours) ? CV_STATUS_CONTOUR_OVERFLOW : CV_STATUS_POINT_OVERFLOW;
       }
@@ -740,9 +827,10 @@ __global__ void k_assemble(const cv_box* __restrict__ boxes, const int32_t* __re
   results[b].n_nodes = nxt;
 }
 
-__global__ void k_init_results(cv_image_result* results, unsigned long long* sums, int B) {
+__global__ void k_init_results(cv_image_result* results, unsigned long long* sums, int* n_ck, int B) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  n_ck[b] = 0;
   cv_image_result r;
   r.n_external = r.n_contours = r.n_points = r.n_pairs = r.n_nodes = 0;
   r.ground = -1; r.inverted = 0; r.status = 0;
@@ -891,39 +979,50 @@ extern "C" int cv_nodes_resized_width(int H, int W) {
 struct NodesWs {
   uint8_t* enh_raw; uint8_t* bin; uint8_t* frame; int* labels; int* cand; CandStat* stats; unsigned long long* sums;
   uint32_t* bits; int words;  // bit plane of `bin`, `words` 32-bit words per image (multiple of 4)
+  TraceCk* ck; int* n_ck; int ck_cap;  // checkpoints of the first border walk
   size_t total;
 };
 
 static inline int bit_words(size_t n_pixels) { return (int)((((n_pixels + 31) / 32) + 3) & ~(size_t)3); }
+// one checkpoint per candidate + one per TRACE_CK border steps (a border has at most ~4 steps per pixel; in practice a
+// few per cent of that) — an image that needs more falls back to the sequential second walk
+static inline int trace_ck_cap(int max_external, size_t n_pixels) { return max_external + (int)(n_pixels / 64) + 64; }
 constexpr size_t TRACE_SMEM_MAX = 200 * 1024;  // bit planes up to 1.6 Mpixel stay in shared memory
 
 // the two border walks, from shared memory when the bit plane fits
 static int launch_traces_stats(const uint32_t* bits, int words, const uint8_t* bin, int h, int w, const int* cand,
-                               const cv_nodes_caps& c, int B, const cv_image_result* results, CandStat* stats,
-                               cudaStream_t st) {
+                               const cv_nodes_caps& c, int B, const cv_image_result* results, CandStat* stats, TraceCk* ck,
+                               int* n_ck, int ck_cap, cudaStream_t st) {
   const size_t smem = ((size_t)words + TRACE_PAD_WORDS + 4) * 4;
   if (smem <= TRACE_SMEM_MAX) {
     static std::atomic<unsigned long long> attr{0};
     if (cvb_once_per_device(attr))
       CVB_CHECK(cudaFuncSetAttribute(k_trace_stats_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRACE_SMEM_MAX));
     CVB_LAUNCH(k_trace_stats_bits, dim3(TRACE_CTAS, B), dim3(TRACE_THREADS), smem, st, bits, words, h, w, cand,
-               c.max_external, results, stats);
+               c.max_external, results, stats, ck, n_ck, ck_cap);
   } else {
     CVB_LAUNCH(k_trace_stats, dim3((c.max_external + 63) / 64, B), dim3(64), 0, st, bin, h, w, cand, c.max_external, results,
                stats);
   }
   return CV_OK;
 }
-static int launch_traces_points(const uint32_t* bits, int words, const uint8_t* bin, int h, int w,
-                                const cv_contour* contours, const cv_nodes_caps& c, int B,
-                                const cv_image_result* results, int32_t* points, cudaStream_t st) {
+static int launch_traces_points(const uint32_t* bits, int words, const uint8_t* bin, int h, int w, const int* cand,
+                                const CandStat* stats, const cv_contour* contours, const cv_nodes_caps& c, int B,
+                                const cv_image_result* results, int32_t* points, const TraceCk* ck, const int* n_ck,
+                                int ck_cap, cudaStream_t st) {
   const size_t smem = ((size_t)words + TRACE_PAD_WORDS + 4) * 4;
   if (smem <= TRACE_SMEM_MAX) {
     static std::atomic<unsigned long long> attr{0};
-    if (cvb_once_per_device(attr))
+    if (cvb_once_per_device(attr)) {
       CVB_CHECK(cudaFuncSetAttribute(k_trace_points_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRACE_SMEM_MAX));
+      CVB_CHECK(cudaFuncSetAttribute(k_trace_points_ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRACE_SMEM_MAX));
+    }
+    // every checkpoint is an independent walk of at most TRACE_CK steps ...
+    CVB_LAUNCH(k_trace_points_ck, dim3(2 * TRACE_CTAS, B), dim3(TRACE_THREADS), smem, st, bits, words, h, w, cand,
+               c.max_external, stats, contours, c.max_contours, c.max_points, ck, n_ck, ck_cap, points);
+    // ... and the images whose checkpoint pool overflowed (if any) repeat the full-length walk
     CVB_LAUNCH(k_trace_points_bits, dim3(TRACE_CTAS, B), dim3(TRACE_THREADS), smem, st, bits, words, h, w, contours,
-               c.max_contours, c.max_points, results, points);
+               c.max_contours, c.max_points, results, points, n_ck, ck_cap);
   } else {
     CVB_LAUNCH(k_trace_points, dim3((c.max_contours + 63) / 64, B), dim3(64), 0, st, bin, h, w, contours, c.max_contours,
                c.max_points, results, points);
@@ -944,6 +1043,9 @@ static NodesWs carve_nodes_ws(void* base, int B, int h, int w, const cv_nodes_ca
   ws.sums = (unsigned long long*)(p + off); off += align256((size_t)B * 8);
   ws.words = bit_words((size_t)h * w);
   ws.bits = (uint32_t*)(p + off); off += align256((size_t)B * ws.words * 4);
+  ws.ck_cap = trace_ck_cap(c.max_external, (size_t)h * w);
+  ws.ck = (TraceCk*)(p + off); off += align256((size_t)B * ws.ck_cap * sizeof(TraceCk));
+  ws.n_ck = (int*)(p + off); off += align256((size_t)B * 4);
   ws.total = off;
   return ws;
 }
@@ -975,7 +1077,7 @@ extern "C" int cv_nodes_analyze(const uint8_t* masks, int B, int H, int W, const
   const size_t n_full = (size_t)B * H * W;
   const int n_small = h * w;
 
-  CVB_LAUNCH(k_init_results, dim3((B + 127) / 128), dim3(128), 0, st, results, ws.sums, B);
+  CVB_LAUNCH(k_init_results, dim3((B + 127) / 128), dim3(128), 0, st, results, ws.sums, ws.n_ck, B);
   {  // a12
     bool al = (((uintptr_t)masks | (uintptr_t)emptied) & 15) == 0;
     size_t n16 = al ? n_full / 16 : 0;
@@ -1008,10 +1110,10 @@ extern "C" int cv_nodes_analyze(const uint8_t* masks, int B, int H, int W, const
   CVB_LAUNCH(k_frame_flags, dim3((2 * w + 2 * h + 255) / 256, B), dim3(256), 0, st, ws.bin, ws.labels, ws.frame, h, w);
   CVB_LAUNCH(k_list_external, dim3(B), dim3(1024), (size_t)h * sizeof(int), st, ws.bin, ws.labels, ws.frame, h, w, ws.cand,
              c.max_external, results);
-  if (int rc = launch_traces_stats(ws.bits, ws.words, ws.bin, h, w, ws.cand, c, B, results, ws.stats, st)) return rc;
+  if (int rc = launch_traces_stats(ws.bits, ws.words, ws.bin, h, w, ws.cand, c, B, results, ws.stats, ws.ck, ws.n_ck, ws.ck_cap, st)) return rc;
   CVB_LAUNCH(k_filter_contours, dim3(B), dim3(1024), 0, st, ws.cand, ws.stats, c.max_external, h, w, 0.0004, contours,
              c.max_contours, c.max_points, results);
-  if (int rc = launch_traces_points(ws.bits, ws.words, ws.bin, h, w, contours, c, B, results, points, st)) return rc;
+  if (int rc = launch_traces_points(ws.bits, ws.words, ws.bin, h, w, ws.cand, ws.stats, contours, c, B, results, points, ws.ck, ws.n_ck, ws.ck_cap, st)) return rc;
   // a16, a17
   if (boxes) {
     CVB_LAUNCH(k_contact, dim3(B), dim3(1024), 0, st, boxes, box_offsets, contours, c.max_contours, points, c.max_points,
@@ -1026,6 +1128,7 @@ extern "C" int cv_nodes_analyze(const uint8_t* masks, int B, int H, int W, const
 struct TermWs {
   uint8_t* gray; uint8_t* bin; uint8_t* frame; int* labels; int* cand; CandStat* stats; unsigned long long* sums;
   uint32_t* bits; int words;
+  TraceCk* ck; int* n_ck; int ck_cap;
   size_t total;
 };
 
@@ -1042,6 +1145,9 @@ static TermWs carve_term_ws(void* base, int B, int H, int W, const cv_nodes_caps
   ws.sums = (unsigned long long*)(p + off); off += align256((size_t)B * 8);
   ws.words = bit_words((size_t)H * W);
   ws.bits = (uint32_t*)(p + off); off += align256((size_t)B * ws.words * 4);
+  ws.ck_cap = trace_ck_cap(c.max_external, (size_t)H * W);
+  ws.ck = (TraceCk*)(p + off); off += align256((size_t)B * ws.ck_cap * sizeof(TraceCk));
+  ws.n_ck = (int*)(p + off); off += align256((size_t)B * 4);
   ws.total = off;
   return ws;
 }
@@ -1069,7 +1175,7 @@ extern "C" int cv_terminals_analyze(const uint8_t* pages_rgb, int B, int H, int 
   const int n_img = H * W;
   const size_t n_px = (size_t)B * n_img;
 
-  CVB_LAUNCH(k_init_results, dim3((B + 127) / 128), dim3(128), 0, st, results, ws.sums, B);
+  CVB_LAUNCH(k_init_results, dim3((B + 127) / 128), dim3(128), 0, st, results, ws.sums, ws.n_ck, B);
   // segment_circuit (:313-319 via :2231-2234)
   cvb_next_work(4.0 * (double)n_px);
   CVB_LAUNCH(k_gray_page, dim3((unsigned)((n_px / 4 + 256) / 256)), dim3(256), 0, st, pages_rgb, ws.gray, n_px,
@@ -1095,10 +1201,10 @@ extern "C" int cv_terminals_analyze(const uint8_t* pages_rgb, int B, int H, int 
   CVB_LAUNCH(k_frame_flags, dim3((2 * W + 2 * H + 255) / 256, B), dim3(256), 0, st, ws.bin, ws.labels, ws.frame, H, W);
   CVB_LAUNCH(k_list_external, dim3(B), dim3(1024), (size_t)H * sizeof(int), st, ws.bin, ws.labels, ws.frame, H, W, ws.cand,
              c.max_external, results);
-  if (int rc = launch_traces_stats(ws.bits, ws.words, ws.bin, H, W, ws.cand, c, B, results, ws.stats, st)) return rc;
+  if (int rc = launch_traces_stats(ws.bits, ws.words, ws.bin, H, W, ws.cand, c, B, results, ws.stats, ws.ck, ws.n_ck, ws.ck_cap, st)) return rc;
   CVB_LAUNCH(k_filter_contours, dim3(B), dim3(1024), 0, st, ws.cand, ws.stats, c.max_external, H, W, 0.0001, contours,
              c.max_contours, c.max_points, results);
-  if (int rc = launch_traces_points(ws.bits, ws.words, ws.bin, H, W, contours, c, B, results, points, st)) return rc;
+  if (int rc = launch_traces_points(ws.bits, ws.words, ws.bin, H, W, ws.cand, ws.stats, contours, c, B, results, points, ws.ck, ws.n_ck, ws.ck_cap, st)) return rc;
   // :2270-2287 contacts of the terminals, threshold 10
   if (n_boxes_total > 0)
     CVB_LAUNCH(k_terminal_counts, dim3(B), dim3(1024), 0, st, boxes, box_offsets, contours, c.max_contours, points,
