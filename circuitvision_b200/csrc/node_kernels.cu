@@ -78,6 +78,8 @@ __global__ void __launch_bounds__(256) k_enhance(const uint8_t* __restrict__ src
   __shared__ uint16_t s_h[ENH_T + 12][ENH_T + 8];
   __shared__ uint8_t s_bl[ENH_T + 8][ENH_T + 8];
   __shared__ uint8_t s_di[ENH_T + 4][ENH_T + 4];
+  __shared__ uint8_t s_t1[ENH_T + 8][ENH_T + 4];  // row maxima
+  __shared__ uint8_t s_t2[ENH_T + 4][ENH_T];      // row minima
   __shared__ unsigned int s_sum;
   int b = blockIdx.z;
   const uint8_t* img = src + (size_t)b * h * w;
@@ -103,19 +105,34 @@ __global__ void __launch_bounds__(256) k_enhance(const uint8_t* __restrict__ src
     s_bl[ly][lx] = gauss5_v(s_h[ly][lx], s_h[ly + 1][lx], s_h[ly + 2][lx], s_h[ly + 3][lx], s_h[ly + 4][lx]);
   }
   __syncthreads();
-  // dilate (two 3x3 iterations == 5x5 max over in-image pixels)
+  // Morphology sees in-image pixels only: positions outside the image become 0 for the dilation (a maximum over
+  // non-negative values ignores them) and 255 for the erosion.  Both 5x5 windows are separable: 5 + 5 taps instead of 25.
+  for (int t = tid; t < (ENH_T + 8) * (ENH_T + 8); t += 256) {
+    int ly = t / (ENH_T + 8), lx = t - ly * (ENH_T + 8);
+    int gy = ty0 + ly - 4, gx = tx0 + lx - 4;
+    if (gy < 0 || gy >= h || gx < 0 || gx >= w) s_bl[ly][lx] = 0;
+  }
+  __syncthreads();
+  // dilate (two 3x3 iterations == 5x5 max), rows then columns
+  for (int t = tid; t < (ENH_T + 8) * (ENH_T + 4); t += 256) {
+    int ly = t / (ENH_T + 4), lx = t - ly * (ENH_T + 4);
+    const uint8_t* r = &s_bl[ly][lx];
+    s_t1[ly][lx] = (uint8_t)max(max(max((int)r[0], (int)r[1]), max((int)r[2], (int)r[3])), (int)r[4]);
+  }
+  __syncthreads();
   for (int t = tid; t < (ENH_T + 4) * (ENH_T + 4); t += 256) {
     int ly = t / (ENH_T + 4), lx = t - ly * (ENH_T + 4);
     int gy = ty0 + ly - 2, gx = tx0 + lx - 2;
-    int m = 0;
-#pragma unroll
-    for (int dy = -2; dy <= 2; dy++)
-#pragma unroll
-      for (int dx = -2; dx <= 2; dx++) {
-        int yy = gy + dy, xx = gx + dx;
-        if (yy >= 0 && yy < h && xx >= 0 && xx < w) m = max(m, (int)s_bl[ly + 2 + dy][lx + 2 + dx]);
-      }
-    s_di[ly][lx] = (uint8_t)m;
+    int m = max(max(max((int)s_t1[ly][lx], (int)s_t1[ly + 1][lx]), max((int)s_t1[ly + 2][lx], (int)s_t1[ly + 3][lx])),
+                (int)s_t1[ly + 4][lx]);
+    s_di[ly][lx] = (gy < 0 || gy >= h || gx < 0 || gx >= w) ? (uint8_t)255 : (uint8_t)m;
+  }
+  __syncthreads();
+  // erode (5x5 min), rows then columns
+  for (int t = tid; t < (ENH_T + 4) * ENH_T; t += 256) {
+    int ly = t / ENH_T, lx = t - ly * ENH_T;
+    const uint8_t* r = &s_di[ly][lx];
+    s_t2[ly][lx] = (uint8_t)min(min(min((int)r[0], (int)r[1]), min((int)r[2], (int)r[3])), (int)r[4]);
   }
   __syncthreads();
   unsigned int local = 0;
@@ -123,14 +140,8 @@ __global__ void __launch_bounds__(256) k_enhance(const uint8_t* __restrict__ src
     int ly = t / ENH_T, lx = t - ly * ENH_T;
     int gy = ty0 + ly, gx = tx0 + lx;
     if (gy < h && gx < w) {
-      int m = 255;
-#pragma unroll
-      for (int dy = -2; dy <= 2; dy++)
-#pragma unroll
-        for (int dx = -2; dx <= 2; dx++) {
-          int yy = gy + dy, xx = gx + dx;
-          if (yy >= 0 && yy < h && xx >= 0 && xx < w) m = min(m, (int)s_di[ly + 2 + dy][lx + 2 + dx]);
-        }
+      int m = min(min(min((int)s_t2[ly][lx], (int)s_t2[ly + 1][lx]), min((int)s_t2[ly + 2][lx], (int)s_t2[ly + 3][lx])),
+                  (int)s_t2[ly + 4][lx]);
       dst[(size_t)b * h * w + (size_t)gy * w + gx] = (uint8_t)m;
       local += m;
     }
