@@ -279,6 +279,138 @@ __global__ void __launch_bounds__(256) k_ccl_flatten(const uint8_t* __restrict__
   }
 }
 
+// Word-parallel merge / flatten on the flat bit plane (bit i = pixel i; k_binarize): one thread owns the 32 pixels
+// (y, 32k .. 32k+31) as a register word, so a row pair is compared with a handful of bit operations and every CONTACT
+// between a run of this row and a run of the row above is one union — instead of five byte loads and a chain of
+// predicates per pixel.  k_ccl_init labelled every pixel with the start of its run inside the same 32-pixel segment,
+// so a run's first pixel is its representative.  Foreground merges 8-connected, background 4-connected.
+__device__ __forceinline__ uint32_t row_word(const uint32_t* __restrict__ B, int w, int y, int k, uint32_t* valid) {
+  const int nv = min(32, w - 32 * k);
+  const uint32_t vm = nv >= 32 ? 0xFFFFFFFFu : ((1u << nv) - 1u);
+  const uint32_t f = (uint32_t)y * (uint32_t)w + 32u * (uint32_t)k;
+  const uint32_t lo = __ldg(B + (f >> 5)), hi = __ldg(B + (f >> 5) + 1);  // the plane is padded by >= 1 word
+  *valid = vm;
+  return __funnelshift_r(lo, hi, f & 31) & vm;
+}
+__device__ __forceinline__ bool flat_bit(const uint32_t* __restrict__ B, uint32_t i) { return (__ldg(B + (i >> 5)) >> (i & 31)) & 1u; }
+__device__ __forceinline__ int w_run_len(uint32_t word, int s) {  // consecutive set bits from bit s (set)
+  const uint32_t inv = ~(word >> s);
+  const int l = __ffs(inv) - 1;
+  return (l < 0 || l > 32 - s) ? 32 - s : l;
+}
+__device__ __forceinline__ int w_run_start(uint32_t word, int x) {  // first bit of the run that contains set bit x
+  const uint32_t below = ~word & ((x ? (1u << x) : 1u) - 1u);
+  return below ? 32 - __clz(below) : 0;
+}
+__device__ __forceinline__ uint32_t w_run_mask(int s, int len) { return (len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u)) << s; }
+
+// find with path halving (a visited node is re-pointed at its grandparent with atomicMin: parents only ever become
+// smaller ancestors, so concurrent walkers stay correct).  Without it a tall structure — a vertical wire, the paper
+// background — becomes a chain as long as the image is high and every later find walks all of it.
+__device__ __forceinline__ int uf_find_halve(int* L, int x) {
+  while (true) {
+    const int y = __ldcg(L + x);
+    if (y == x) return x;
+    const int z = __ldcg(L + y);
+    if (z == y) return y;
+    atomicMin(L + x, z);
+    x = z;
+  }
+}
+__device__ __forceinline__ void uf_union_halve(int* L, int a, int b) {
+  bool done;
+  do {
+    a = uf_find_halve(L, a);
+    b = uf_find_halve(L, b);
+    if (a < b) {
+      const int old = atomicMin(L + b, a);
+      done = (old == b);
+      b = old;
+    } else if (b < a) {
+      const int old = atomicMin(L + a, b);
+      done = (old == a);
+      a = old;
+    } else {
+      done = true;
+    }
+  } while (!done);
+}
+
+template <int CONN>
+__device__ __forceinline__ void merge_class(int* L, uint32_t cur, uint32_t up, int pc, int pu) {
+  // every run of `cur` against the runs of `up` it touches (CONN 8: diagonals inside the word included)
+  while (cur) {
+    const int st = __ffs(cur) - 1;
+    const int len = w_run_len(cur, st);
+    const uint32_t rm = w_run_mask(st, len);
+    cur &= ~rm;
+    uint32_t aw = rm;
+    if (CONN == 8) aw |= (rm << 1) | (rm >> 1);
+    uint32_t cand = aw & up;
+    while (cand) {
+      const int us = __ffs(cand) - 1;
+      const int ust = w_run_start(up, us);
+      cand &= ~w_run_mask(ust, w_run_len(up, ust));
+      uf_union_halve(L, pc + st, pu + ust);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_ccl_merge_words(const uint32_t* __restrict__ bits_all, int words_per_image,
+                                                         int* __restrict__ Lall, int h, int w) {
+  const int b = blockIdx.y;
+  const int nwr = (w + 31) >> 5;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= h * nwr) return;
+  const int y = t / nwr, k = t - y * nwr;
+  const uint32_t* B = bits_all + (size_t)b * words_per_image;
+  int* L = Lall + (size_t)b * h * w;
+  uint32_t vm;
+  const uint32_t fg = row_word(B, w, y, k, &vm);
+  const uint32_t bg = ~fg & vm;
+  const int pc = y * w + 32 * k;
+  // runs that continue across the 32-pixel segment boundary (k_ccl_init labels per segment)
+  if (k > 0 && flat_bit(B, (uint32_t)pc - 1u) == (bool)(fg & 1u)) uf_union_halve(L, pc, pc - 1);
+  if (y == 0) return;
+  uint32_t vmu;
+  const uint32_t upf = row_word(B, w, y - 1, k, &vmu);
+  const uint32_t upb = ~upf & vm;
+  const int pu = pc - w;
+  merge_class<8>(L, fg, upf, pc, pu);
+  merge_class<4>(L, bg, upb, pc, pu);
+  // foreground diagonals across the segment boundary
+  if (k > 0 && (fg & 1u) && flat_bit(B, (uint32_t)pu - 1u)) uf_union_halve(L, pc, pu - 1);
+  if (32 * k + 32 < w && (fg >> 31) && flat_bit(B, (uint32_t)pu + 32u)) uf_union_halve(L, pc + 31, pu + 32);
+}
+
+__global__ void __launch_bounds__(256) k_ccl_flatten_words(const uint32_t* __restrict__ bits_all, int words_per_image,
+                                                           int* __restrict__ Lall, int h, int w) {
+  const int b = blockIdx.y;
+  const int nwr = (w + 31) >> 5;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= h * nwr) return;
+  const int y = t / nwr, k = t - y * nwr;
+  const uint32_t* B = bits_all + (size_t)b * words_per_image;
+  int* L = Lall + (size_t)b * h * w;
+  uint32_t vm;
+  const uint32_t fg = row_word(B, w, y, k, &vm);
+  const int pc = y * w + 32 * k;
+#pragma unroll
+  for (int cls = 0; cls < 2; cls++) {
+    uint32_t cur = cls ? (~fg & vm) : fg;
+    while (cur) {
+      const int st = __ffs(cur) - 1;
+      const int len = w_run_len(cur, st);
+      cur &= ~w_run_mask(st, len);
+      const int first = pc + st;
+      const int r = uf_find<0>(L, first);
+      // roots keep pointing at themselves, so concurrent finds stay valid; the run's pixels all named `first`
+      if (r != first)
+        for (int i = 0; i < len; i++) L[first + i] = r;
+    }
+  }
+}
+
 // background regions that touch the image frame (4-connected to cv2's implicit zero border)
 __global__ void k_frame_flags(const uint8_t* __restrict__ bin, const int* __restrict__ Lall, uint8_t* __restrict__ frame,
                               int h, int w) {
@@ -1113,11 +1245,13 @@ extern "C" int cv_nodes_analyze(const uint8_t* masks, int B, int H, int W, const
   dim3 cg((w + 31) / 32, (h + 7) / 8, B), cb(32, 8);
   cvb_next_work(5.0 * (double)B * n_small);  // 1 B/px mask read + 4 B/px label write
   CVB_LAUNCH((k_ccl_init<0, true>), cg, cb, 0, st, ws.bin, ws.labels, h, w);
-  cvb_next_work(5.0 * (double)B * n_small);
-  CVB_LAUNCH((k_ccl_merge<0, true, 8>), cg, cb, 0, st, ws.bin, ws.labels, h, w);
-  cvb_next_work(9.0 * (double)B * n_small);  // mask + label read + label write
-  CVB_LAUNCH((k_ccl_flatten<0, true>), dim3((n_small + 255) / 256, B), dim3(256), 0, st, ws.bin, ws.labels, n_small,
-             (int*)nullptr);
+  {
+    const int n_words = h * ((w + 31) / 32);
+    cvb_next_work(0.25 * (double)B * n_small);  // two rows of bits per word
+    CVB_LAUNCH(k_ccl_merge_words, dim3((n_words + 255) / 256, B), dim3(256), 0, st, ws.bits, ws.words, ws.labels, h, w);
+    cvb_next_work(8.0 * (double)B * n_small);  // label read + write
+    CVB_LAUNCH(k_ccl_flatten_words, dim3((n_words + 255) / 256, B), dim3(256), 0, st, ws.bits, ws.words, ws.labels, h, w);
+  }
   CVB_LAUNCH(k_frame_flags, dim3((2 * w + 2 * h + 255) / 256, B), dim3(256), 0, st, ws.bin, ws.labels, ws.frame, h, w);
   CVB_LAUNCH(k_list_external, dim3(B), dim3(1024), (size_t)h * sizeof(int), st, ws.bin, ws.labels, ws.frame, h, w, ws.cand,
              c.max_external, results);
@@ -1205,10 +1339,13 @@ extern "C" int cv_terminals_analyze(const uint8_t* pages_rgb, int B, int H, int 
   dim3 cg((W + 31) / 32, (H + 7) / 8, B), cb(32, 8);
   cvb_next_work(5.0 * (double)n_px);
   CVB_LAUNCH((k_ccl_init<0, true>), cg, cb, 0, st, ws.bin, ws.labels, H, W);
-  cvb_next_work(5.0 * (double)n_px);
-  CVB_LAUNCH((k_ccl_merge<0, true, 8>), cg, cb, 0, st, ws.bin, ws.labels, H, W);
-  cvb_next_work(9.0 * (double)n_px);
-  CVB_LAUNCH((k_ccl_flatten<0, true>), dim3((n_img + 255) / 256, B), dim3(256), 0, st, ws.bin, ws.labels, n_img, (int*)nullptr);
+  {
+    const int n_words = H * ((W + 31) / 32);
+    cvb_next_work(0.25 * (double)n_px);
+    CVB_LAUNCH(k_ccl_merge_words, dim3((n_words + 255) / 256, B), dim3(256), 0, st, ws.bits, ws.words, ws.labels, H, W);
+    cvb_next_work(8.0 * (double)n_px);
+    CVB_LAUNCH(k_ccl_flatten_words, dim3((n_words + 255) / 256, B), dim3(256), 0, st, ws.bits, ws.words, ws.labels, H, W);
+  }
   CVB_LAUNCH(k_frame_flags, dim3((2 * W + 2 * H + 255) / 256, B), dim3(256), 0, st, ws.bin, ws.labels, ws.frame, H, W);
   CVB_LAUNCH(k_list_external, dim3(B), dim3(1024), (size_t)H * sizeof(int), st, ws.bin, ws.labels, ws.frame, H, W, ws.cand,
              c.max_external, results);
