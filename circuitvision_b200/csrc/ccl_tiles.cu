@@ -12,14 +12,15 @@
 //                              components that stay inside their tile.
 //   pass B  k_ccl_seams_h/_v : only the tile seams (3.5 % of the image; horizontal seams one 32-pixel word per thread, one
 //                              union per run contact) merge components across tiles with the
-//                              global atomicMin union-find on the label image (roots point at roots).
-//   pass B2 k_ccl_compress_h/_v: path halving from the same seam runs / pixels so the trees pass C walks are one or two hops deep.
+//                              global atomicMin union-find on the label image (roots point at roots; the finds halve the
+//                              paths they walk, which replaced a separate compression pass).
 //   pass C  k_ccl_tile_fixup : one thread per 32-pixel word re-reads the mask bits (1 B/px, no full label read), takes
 //                              the tile-local root named at each sub-run's first pixel, looks up its global root and
 //                              rewrites only the runs whose component changed (sparse row segments); counts roots.
 // Total ≈ 6 B/px + seams instead of the 16+ B/px of a per-pixel init / merge / flatten pipeline.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/cv_b200.h"
 #include "common.cuh"
@@ -37,11 +38,27 @@ __device__ __forceinline__ int gfind(const int* L, int x) {
   }
   return x;
 }
+// find with path halving: a visited node is re-pointed at its grandparent (atomicMin: parents only become smaller
+// ancestors, concurrent walkers stay correct), so the seam unions do not build tile-to-tile chains
+__device__ __forceinline__ int gfind_halve(int* L, int x) {
+  while (true) {
+    const int y = __ldcg(L + x) - 1;
+    if (y == x) return x;
+    const int z = __ldcg(L + y) - 1;
+    if (z == y) return y;
+    atomicMin(L + x, z + 1);
+    x = z;
+  }
+}
 __device__ __forceinline__ void gunion(int* L, int a, int b) {
+  // first hop without a write: a and b may be ordinary pixels, and pass C relies on ordinary pixels keeping the
+  // tile-local root pass A gave them — only root entries may be re-pointed
+  a = __ldcg(L + a) - 1;
+  b = __ldcg(L + b) - 1;
   bool done;
   do {
-    a = gfind(L, a);
-    b = gfind(L, b);
+    a = gfind_halve(L, a);
+    b = gfind_halve(L, b);
     if (a < b) {
       int old = atomicMin(L + b, a + 1) - 1;
       done = (old == b);
@@ -352,42 +369,6 @@ __global__ void __launch_bounds__(256) k_ccl_seams_v(const uint8_t* __restrict__
   }
 }
 
-// pass B2: the seam unions link tile roots to tile roots without compression, so a component that crosses many tiles
-// (a wire network) ends up as a deep tree.  Every run on a horizontal seam row (one walk per run: its pixels share the
-// label) and every pixel on a vertical seam column re-walks its root's path with path halving (each step re-points a
-// node at its grandparent with atomicMin), after which pass C finds global roots in one or two hops.
-__device__ __forceinline__ void halve_path(int* L, int p) {
-  int x = __ldcg(L + p) - 1;
-  while (true) {
-    const int y = __ldcg(L + x) - 1;
-    if (y == x) break;
-    const int z = __ldcg(L + y) - 1;
-    if (z != y) atomicMin(L + x, z + 1);  // ancestors only ever get smaller indices
-    x = z;
-  }
-}
-__global__ void __launch_bounds__(128) k_ccl_compress_h(const uint8_t* __restrict__ masks, int* __restrict__ labels, int H, int W,
-                                                         int vec_ok) {
-  const int b = blockIdx.z;
-  const uint8_t* im = masks + (size_t)b * H * W;
-  int* L = labels + (size_t)b * H * W;
-  const int y = (blockIdx.y + 1) * CT_H;
-  const int x0 = (blockIdx.x * 128 + threadIdx.x) * 32;
-  if (y >= H || x0 >= W) return;
-  const uint32_t cur = load_word(im, H, W, y, x0, vec_ok != 0);
-  for (uint32_t st = cur & ~(cur << 1); st; st &= st - 1) halve_path(L, y * W + x0 + __ffs(st) - 1);
-}
-__global__ void __launch_bounds__(256) k_ccl_compress_v(const uint8_t* __restrict__ masks, int* __restrict__ labels, int H, int W) {
-  const int b = blockIdx.z;
-  const uint8_t* im = masks + (size_t)b * H * W;
-  int* L = labels + (size_t)b * H * W;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int n_seams = (W - 1) / CT_W;
-  if (t >= (long long)n_seams * H) return;
-  const int p = (int)(t % H) * W + (int)(t / H + 1) * CT_W;
-  if (im[p]) halve_path(L, p);
-}
-
 // pass C: same thread <-> word mapping as pass A.  Only words flagged dirty are revisited.  The label pass A wrote at
 // the LAST pixel of a sub-run names the run's tile-local root (only root pixels — always the first pixel of a run — are
 // modified by the seam unions); if that root was merged into another component, the whole run is rewritten.
@@ -469,10 +450,6 @@ static int ccl_run(const uint8_t* masks, int B, int H, int W, int32_t* labels, i
     CVB_LAUNCH((k_ccl_seams_h<CONN>), dim3((words + 127) / 128, seams_h, B), dim3(128), 0, st, masks, labels, H, W, vec_ok);
   if (vpx > 0)
     CVB_LAUNCH((k_ccl_seams_v<CONN>), dim3((unsigned)((vpx + 255) / 256), 1, B), dim3(256), 0, st, masks, labels, H, W);
-  if (seams_h > 0)
-    CVB_LAUNCH(k_ccl_compress_h, dim3((words + 127) / 128, seams_h, B), dim3(128), 0, st, masks, labels, H, W, vec_ok);
-  if (vpx > 0)
-    CVB_LAUNCH(k_ccl_compress_v, dim3((unsigned)((vpx + 255) / 256), 1, B), dim3(256), 0, st, masks, labels, H, W);
   CVB_LAUNCH(k_ccl_tile_fixup, tg, dim3(CT_THREADS), 0, st, masks, labels, H, W, vec_ok, dirty, n_components, partial);
   if (n_components && partial) CVB_LAUNCH(k_ccl_count_finish, dim3(B), dim3(32), 0, st, partial, n_components, B);
   return CV_OK;

@@ -151,6 +151,14 @@ def test_native_ccl_matches_cv2(conn):
     d = torch.from_numpy(m[None]).cuda()
     lab, cnt = ccl_label(d, conn)
     assert np.array_equal(lab[0].cpu().numpy(), ccl_labels_min_index(m, conn))
+    # random textures over many tiles: percolating blobs, thin diagonal structures, runs that cross every seam
+    for seed, (hh, ww), p, smooth in [(11, (513, 1030), 0.45, 0), (12, (513, 1030), 0.55, 1), (13, (700, 900), 0.62, 0),
+                                      (14, (1024, 768), 0.5, 2), (15, (333, 2049), 0.58, 0), (16, (2048, 2048), 0.593, 0)]:
+        m = synth.random_blob_mask(seed, hh, ww, p=p, smooth=smooth)
+        lab, cnt = ccl_label(torch.from_numpy(m[None]).cuda(), conn)
+        ref = ccl_labels_min_index(m, conn)
+        assert np.array_equal(lab[0].cpu().numpy(), ref), (seed, conn)
+        assert int(cnt[0]) == len(np.unique(ref)) - 1, (seed, conn)
     # edge cases: all background / all foreground / single row
     for arr in (np.zeros((1, 9, 33), np.uint8), np.full((1, 9, 33), 255, np.uint8), np.full((1, 1, 70), 3, np.uint8)):
         lab, cnt = ccl_label(torch.from_numpy(arr).cuda(), conn)
