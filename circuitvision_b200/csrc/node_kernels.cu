@@ -188,26 +188,6 @@ __device__ __forceinline__ int uf_find(const int* L, int x) {
   return x;
 }
 
-template <int OFF>
-__device__ __forceinline__ void uf_union(int* L, int a, int b) {
-  bool done;
-  do {
-    a = uf_find<OFF>(L, a);
-    b = uf_find<OFF>(L, b);
-    if (a < b) {
-      int old = atomicMin(L + b, a + OFF) - OFF;
-      done = (old == b);
-      b = old;
-    } else if (b < a) {
-      int old = atomicMin(L + a, b + OFF) - OFF;
-      done = (old == a);
-      a = old;
-    } else {
-      done = true;
-    }
-  } while (!done);
-}
-
 // One warp = 32 consecutive pixels of one row.  Initial label = start of the pixel's horizontal run inside
 // the warp segment (ballot + clz), so that only run boundaries need union operations afterwards.
 template <int OFF, bool WITH_BG>
@@ -229,54 +209,6 @@ __global__ void __launch_bounds__(256) k_ccl_init(const uint8_t* __restrict__ bi
   int lbl = p - (int)threadIdx.x + start;
   if (f || WITH_BG) L[base + p] = lbl + OFF;
   else L[base + p] = 0;  // only reachable with OFF == 1: background = 0
-}
-
-template <int OFF, bool WITH_BG, int CONN>
-__global__ void __launch_bounds__(256) k_ccl_merge(const uint8_t* __restrict__ bin, int* __restrict__ Lall, int h,
-                                                   int w) {
-  int b = blockIdx.z;
-  int x = blockIdx.x * 32 + threadIdx.x;
-  int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (y >= h || x >= w) return;
-  const uint8_t* im = bin + (size_t)b * h * w;
-  int* L = Lall + (size_t)b * h * w;
-  int p = y * w + x;
-  bool f = im[p] != 0;
-  if (!f && !WITH_BG) return;
-  bool hasL = x > 0, hasU = y > 0, hasR = x + 1 < w;
-  // "same" = neighbour exists and has the same class (fg/bg) as p
-  bool left = hasL && ((im[p - 1] != 0) == f);
-  bool up = hasU && ((im[p - w] != 0) == f);
-  bool ul = hasU && hasL && ((im[p - w - 1] != 0) == f);
-  if (left && (threadIdx.x == 0)) uf_union<OFF>(L, p, p - 1);  // stitch runs across the warp boundary
-  if (up) {
-    if (!(left && ul)) uf_union<OFF>(L, p, p - w);
-  } else if (f && CONN == 8) {
-    bool ur = hasU && hasR && (im[p - w + 1] != 0);
-    if (ul && !left) uf_union<OFF>(L, p, p - w - 1);
-    if (ur) uf_union<OFF>(L, p, p - w + 1);
-  }
-}
-
-template <int OFF, bool WITH_BG>
-__global__ void __launch_bounds__(256) k_ccl_flatten(const uint8_t* __restrict__ bin, int* __restrict__ Lall,
-                                                     int n_per_image, int* __restrict__ ncomp) {
-  int b = blockIdx.y;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool isroot = false;
-  if (i < n_per_image) {
-    int* L = Lall + (size_t)b * n_per_image;
-    bool f = bin[(size_t)b * n_per_image + i] != 0;
-    if (f || WITH_BG) {
-      int r = uf_find<OFF>(L, i);
-      if (r != i) L[i] = r + OFF;  // roots keep pointing at themselves, so concurrent finds stay valid
-      isroot = f && (r == i);
-    }
-  }
-  if (ncomp) {
-    unsigned m = __ballot_sync(0xffffffffu, isroot);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(ncomp + b, __popc(m));
-  }
 }
 
 // Word-parallel merge / flatten on the flat bit plane (bit i = pixel i; k_binarize): one thread owns the 32 pixels
