@@ -163,3 +163,31 @@ def test_native_ccl_matches_cv2(conn):
     for arr in (np.zeros((1, 9, 33), np.uint8), np.full((1, 9, 33), 255, np.uint8), np.full((1, 1, 70), 3, np.uint8)):
         lab, cnt = ccl_label(torch.from_numpy(arr).cuda(), conn)
         assert np.array_equal(lab[0].cpu().numpy(), ccl_labels_min_index(arr[0], conn))
+
+
+def test_shared_analyzer_from_several_threads(analyzer):
+    """The app shares ONE analyzer across its session threads (app.py:134; SURVEY §8(b) threading): concurrent calls must
+    serialise internally and every caller must get its own, correct result."""
+    import threading
+    from oracle import node_oracle
+    cases = [synth.make_schematic(300 + i, 1024)[:2] for i in range(6)]
+    want = [node_oracle.get_node_connections(m, b) for m, b in cases]
+    got, errors = [None] * len(cases), []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                got[i] = analyzer.get_node_connections(None, cases[i][0], cases[i][1])
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(cases))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for i, (nodes, emptied, enhanced, *_rest) in enumerate(got):
+        rn, remp, renh, _, _ = want[i]
+        assert np.array_equal(emptied, remp) and np.array_equal(enhanced, renh), i
+        _assert_nodes_equal(nodes, rn, f"thread case {i}")
