@@ -5,7 +5,8 @@
 
 Everything numeric runs in libcv_b200.so on the GPU; this file is box bookkeeping plus the UI-only debug
 drawings (cv2 drawing calls on the 600-row canvases, exactly the reference's `drawContours/putText/circle`
-calls fed with device-produced contours — SURVEY §8 row a18, not parity-checked).
+calls fed with device-produced contours — SURVEY §8 row a18; byte-compared with the reference's three images in
+tests/test_nodes_gpu.py).
 """
 from __future__ import annotations
 
@@ -77,6 +78,7 @@ class CircuitAnalyzer:
         from . import terminals as _terminals
         with self._lock:
             r = self._ta().analyze(pages_rgb, boxes_list)
+            r.to_host()  # the analyzer's device buffers are reused by the next call: read them while holding the lock
         for b, boxes in enumerate(boxes_list):
             _terminals.apply_reclassification(boxes, r.counts(b), self.class_names)
         return r
@@ -131,7 +133,9 @@ class CircuitAnalyzer:
         """Batched form used by bench.py / multi-image callers: masks [B,H,W] uint8 (numpy or cuda tensor).
         Returns the device-resident `NodeBatchResult`; `.nodes(b)` gives the reference structure of image b."""
         with self._lock:
-            return self._na().analyze(masks, boxes_list)
+            r = self._na().analyze(masks, boxes_list)
+            r.tables_to_host()  # the analyzer's device tables are reused by the next call: read them under the lock
+            return r
 
     def _render(self, resized, contours, nodes, points):
         """UI-only drawings (:414-458, :1585-1603) on the 600-row canvases."""
@@ -153,9 +157,8 @@ class CircuitAnalyzer:
                 cv2.drawContours(final_viz, [n["contour"]], -1, (0, 255, 0), 2)
                 cv2.putText(final_viz, str(n["id"]), (cx - 10, cy + 10), cv2.FONT_HERSHEY_SIMPLEX, 0.9, (0, 0, 255), 2)
         conn_viz = contour_viz.copy()
-        if nodes:
-            for p in points:
-                cv2.circle(conn_viz, p, radius=5, color=(0, 255, 255), thickness=-1)
+        for p in points:  # without valid nodes there are no points either (:1443 appends only with an attachment)
+            cv2.circle(conn_viz, p, radius=5, color=(0, 255, 255), thickness=-1)
         return contour_viz, final_viz, conn_viz
 
     # ------------------------------------------------------------------ SAM 2 segmentation

@@ -801,7 +801,7 @@ __global__ void __launch_bounds__(1024) k_contact(const cv_box* __restrict__ box
             if (nh < CVB_HITS_PER_BOX) {
               if (lane == 0) { cv_pair pr; pr.contour = k; pr.box = bi; pr.px = hx; pr.py = hy; s_hits[warp][nh] = pr; }
             } else {
-              status |= CV_STATUS_PAIR_OVERFLOW;
+              status |= CV_STATUS_BOX_HITS_OVERFLOW;  // compile-time staging limit: growing max_pairs cannot help
             }
             nh++;
           }
@@ -1198,6 +1198,74 @@ extern "C" int cv_nodes_analyze(const uint8_t* masks, int B, int H, int W, const
     CVB_LAUNCH(k_assemble, dim3((B + 31) / 32), dim3(32), 0, st, boxes, box_offsets, contours, c.max_contours, pairs,
                c.max_pairs, results, B);
   }
+  return CV_OK;
+}
+
+// ------------------------------------------------------------------ result compaction before the device->host copy
+// The result tables are fixed-capacity (max_contours x 64 B + max_pairs x 16 B + max_points x 8 B per image, mostly empty).
+// cv_nodes_pack gathers the used prefixes of all B images into one contiguous blob so that only the bytes that carry
+// information cross PCIe:   header[b] = {byte offset of image b's section, n_contours, n_pairs, n_points} (int64 x 4),
+// header[B].offset = total bytes;  section = contours[nK] | pairs[nP] | points[nPts] (x, y int32 pairs), 16-byte aligned.
+__global__ void __launch_bounds__(1024) k_pack_offsets(const cv_image_result* __restrict__ results, int B,
+                                                       long long* __restrict__ header) {
+  __shared__ long long part[1024];
+  // B <= a few thousand: one block, serial chunks of 1024 with a running base
+  long long base = 0;
+  for (int b0 = 0; b0 < B; b0 += 1024) {
+    const int b = b0 + threadIdx.x;
+    long long sz = 0, nK = 0, nP = 0, nPt = 0;
+    if (b < B) {
+      nK = results[b].n_contours; nP = results[b].n_pairs; nPt = results[b].n_points;
+      sz = (nK * (long long)sizeof(cv_contour) + nP * (long long)sizeof(cv_pair) + nPt * 8 + 15) & ~15ll;
+    }
+    part[threadIdx.x] = sz;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+      long long v = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+      __syncthreads();
+      part[threadIdx.x] += v;
+      __syncthreads();
+    }
+    if (b < B) {
+      header[4 * b + 0] = base + part[threadIdx.x] - sz;
+      header[4 * b + 1] = nK; header[4 * b + 2] = nP; header[4 * b + 3] = nPt;
+    }
+    const long long tot = part[1023];
+    __syncthreads();
+    base += tot;
+  }
+  if (threadIdx.x == 0) { header[4 * B] = base; header[4 * B + 1] = header[4 * B + 2] = header[4 * B + 3] = 0; }
+}
+
+__global__ void __launch_bounds__(256) k_pack_copy(const cv_contour* __restrict__ contours, int max_contours,
+                                                   const int32_t* __restrict__ points, int max_points,
+                                                   const cv_pair* __restrict__ pairs, int max_pairs,
+                                                   const long long* __restrict__ header, uint8_t* __restrict__ blob,
+                                                   long long blob_cap) {
+  const int b = blockIdx.y;
+  const long long off = header[4 * b], nK = header[4 * b + 1], nP = header[4 * b + 2], nPt = header[4 * b + 3];
+  const long long w0 = nK * (long long)(sizeof(cv_contour) / 8), w1 = w0 + nP * (long long)(sizeof(cv_pair) / 8), w2 = w1 + nPt;
+  if (off + w2 * 8 > blob_cap) return;  // caller checks header[B] against the capacity
+  const unsigned long long* sK = (const unsigned long long*)(contours + (size_t)b * max_contours);
+  const unsigned long long* sP = (const unsigned long long*)(pairs + (size_t)b * max_pairs);
+  const unsigned long long* sT = (const unsigned long long*)(points + (size_t)b * max_points * 2);
+  unsigned long long* dst = (unsigned long long*)(blob + off);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < w2; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = i < w0 ? sK[i] : (i < w1 ? sP[i - w0] : sT[i - w1]);
+}
+
+extern "C" int cv_nodes_pack(const cv_contour* contours, const int32_t* points, const cv_pair* pairs,
+                             const cv_image_result* results, int B, const cv_nodes_caps* caps, long long* header,
+                             uint8_t* blob, long long blob_bytes, void* stream) {
+  cvb_reset_launches();
+  if (!contours || !points || !pairs || !results || !header || !blob || B <= 0 || blob_bytes <= 0)
+    return cvb_fail(CV_ERR_INVALID, "cv_nodes_pack: bad argument");
+  cv_nodes_caps c = resolve_caps(caps);
+  cudaStream_t st = (cudaStream_t)stream;
+  CVB_LAUNCH(k_pack_offsets, dim3(1), dim3(1024), 0, st, results, B, header);
+  cvb_next_work(0.0);
+  CVB_LAUNCH(k_pack_copy, dim3(16, B), dim3(256), 0, st, contours, c.max_contours, points, c.max_points, pairs, c.max_pairs,
+             header, blob, (long long)blob_bytes);
   return CV_OK;
 }
 

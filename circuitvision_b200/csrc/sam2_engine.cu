@@ -52,6 +52,7 @@ struct cv_sam2 {
   int D = 96;   // head dim of the attention buffers: hd zero-padded to 64 or 96 by the weight folding
   int launches = 0;
   float refc_b = 0.f;
+  int count_sat = 0;  // debug: count fp16 conversions that saturated (|x| == 65504) in every 16-bit activation buffer
 };
 
 #define TRY(x)               \
@@ -241,6 +242,8 @@ extern "C" int cv_sam2_finalize(cv_sam2* h) {
   TRY(alloc_buf(h, "iou", (size_t)B * 4, 0));
   TRY(alloc_buf(h, "sel", (size_t)B * 4, 0));
   TRY(alloc_buf(h, "high", (size_t)B * 1024 * 1024 * 4, 0));
+  TRY(alloc_buf(h, "satcount", 16, 0));
+  CVB_CHECK(cudaMemset(h->buf["satcount"].p, 0, 16));
   if (h->cfg.use_refinement) CVB_CHECK(cudaMemcpy(&h->refc_b, h->w["refc.b"].p, 4, cudaMemcpyDeviceToHost));
   h->finalized = true;
   return CV_OK;
@@ -251,6 +254,14 @@ extern "C" int cv_sam2_set_max_batch(cv_sam2* h, int max_batch) {
   if (!h || max_batch <= 0) return cvb_fail(CV_ERR_INVALID, "cv_sam2_set_max_batch: bad argument");
   h->cfg.max_batch = max_batch;
   return cv_sam2_finalize(h);
+}
+
+// Debug tap (cv_sam2_set_debug): tc::pack16 converts with cvt.rn.satfinite, so an fp32 value beyond the fp16 range
+// becomes +-65504 silently.  When enabled, every 16-bit activation buffer is scanned right after the kernel that wrote it
+// and the number of +-65504 entries accumulates in the "satcount" buffer (read with cv_sam2_read_buffer).
+static int sat(cv_sam2* h, const void* p, long long n, cudaStream_t st) {
+  if (!h->count_sat || !h->f16 || n <= 0) return CV_OK;
+  return launch_count_sat16((const uint16_t*)p, n, BUF<unsigned int>(h, "satcount"), st);
 }
 
 static int gemm(cv_sam2* h, const bf16* A, long long lda, const bf16* W, int M, int N, int K, GemmEpilogue& e, cudaStream_t st) {
@@ -292,6 +303,8 @@ static int run_block(cv_sam2* h, int i, int B, float* X, float* Xn, cudaStream_t
     e.ld_pool = Cp;
   }
   TRY(gemm(h, A, Cin, WB(h, pre + ".qkv.w"), (int)M, 3 * Cp, Cin, e, st));
+  TRY(sat(h, A, M * Cin, st));
+  TRY(sat(h, QKV, M * 3 * Cp, st));
   float* Xo = X;
   long long To = T;
   int Ho = H, Wo = W, wso = ws;
@@ -326,6 +339,8 @@ static int run_block(cv_sam2* h, int i, int B, float* X, float* Xn, cudaStream_t
                        p.heads, D, scale, AO, Cp, h->f16, st));
   }
   h->launches++;
+  TRY(sat(h, AO, (p.pool ? M / 4 : M) * Cp, st));
+  if (p.pool) TRY(sat(h, BUF<bf16>(h, "Qp"), (M / 4) * Cp, st));
   // proj + window un-partition + residual (in place on the residual stream)
   GemmEpilogue ep;
   ep.bias = WF(h, pre + ".proj.b");
@@ -344,6 +359,8 @@ static int run_block(cv_sam2* h, int i, int B, float* X, float* Xn, cudaStream_t
   e1.act = GEMM_ACT_GELU;
   e1.out_bf16 = Hd; e1.ld_bf16 = 4 * C;
   TRY(gemm(h, A, C, WB(h, pre + ".fc1.w"), (int)To, 4 * C, C, e1, st));
+  TRY(sat(h, A, To * C, st));
+  TRY(sat(h, Hd, To * 4 * C, st));
   GemmEpilogue e2;
   e2.bias = WF(h, pre + ".fc2.b");
   e2.res = Xo; e2.ld_res = C;
@@ -433,6 +450,7 @@ static int decoder_layer(cv_sam2* h, int l, int B, cudaStream_t st) {
   TRY(tok_lin(h, qpe, 256, pre + ".i2t.k", R, 128, 256, 0, nullptr, BUF<float>(h, "t128a"), 128, st));
   TRY(tok_lin(h, q, 256, pre + ".i2t.v", R, 128, 256, 0, nullptr, BUF<float>(h, "t128b"), 128, st));
   TRY(launch_attn_i2t(Qi, 128, BUF<float>(h, "t128a"), BUF<float>(h, "t128b"), B, 4096, T, 8, 16, h->f16, BUF<bf16>(h, "Ai"), st));
+  TRY(sat(h, BUF<bf16>(h, "Ai"), (long long)B * 4096 * 128, st));
   h->launches += 2;
   float* keys32 = BUF<float>(h, "keys32");
   GemmEpilogue eo;
@@ -443,6 +461,7 @@ static int decoder_layer(cv_sam2* h, int l, int B, cudaStream_t st) {
   TRY(launch_ln_rows(keys32, (long long)B * 4096, 256, WF(h, pre + ".n4.g"), WF(h, pre + ".n4.b"), 1e-5f, B, 64, 64, 0,
                      h->f16, BUF<bf16>(h, "keys16"), keys32, st));
   h->launches++;
+  TRY(sat(h, BUF<bf16>(h, "keys16"), (long long)B * 4096 * 256, st));
   return CV_OK;
 }
 
@@ -457,6 +476,7 @@ extern "C" int cv_sam2_forward(cv_sam2* h, const void* images, int input_kind, i
   if ((mask_u8 || out_logits) && (out_h <= 0 || out_w <= 0)) return cvb_fail(CV_ERR_INVALID, "cv_sam2_forward: output size");
   cudaStream_t st = (cudaStream_t)stream;
   h->launches = 0;
+  if (h->count_sat) CVB_CHECK(cudaMemsetAsync(BUF<unsigned int>(h, "satcount"), 0, 16, st));
   const int E = h->cfg.embed_dim;
   static const float mean[3] = {0.485f, 0.456f, 0.406f};
   static const float istd[3] = {1.0f / 0.229f, 1.0f / 0.224f, 1.0f / 0.225f};
@@ -502,6 +522,7 @@ extern "C" int cv_sam2_forward(cv_sam2* h, const void* images, int input_kind, i
     TRY(gemm(h, A, 4 * E, WB(h, "neck2.w"), B * 4096, 256, 4 * E, e2, st));
     TRY(launch_add_nearest2(keys32, BUF<float>(h, "L3"), B, 64, 64, 256, st));
     TRY(launch_ln_rows(keys32, (long long)B * 4096, 256, nullptr, nullptr, 0.f, B, 64, 64, 0, h->f16, BUF<bf16>(h, "keys16"), nullptr, st));
+    TRY(sat(h, BUF<bf16>(h, "keys16"), (long long)B * 4096 * 256, st));
     TRY(launch_ln_rows(X[1], (long long)B * 16384, 2 * E, nullptr, nullptr, 0.f, B, 128, 128, 0, h->f16, A, nullptr, st));
     GemmEpilogue e3;
     e3.bias = WF(h, "s1.b");
@@ -544,6 +565,7 @@ extern "C" int cv_sam2_forward(cv_sam2* h, const void* images, int input_kind, i
     TRY(gemm(h, BUF<bf16>(h, "keys16"), 256, WB(h, "up1.w"), B * 4096, 256, 256, e, st));
     TRY(launch_ln2d_gelu(BUF<float>(h, "U1"), (long long)B * 16384, 64, WF(h, "upln.g"), WF(h, "upln.b"), 1e-6f, h->f16,
                          BUF<bf16>(h, "U1n"), st));
+    TRY(sat(h, BUF<bf16>(h, "U1n"), (long long)B * 16384 * 64, st));
     GemmEpilogue e2;
     e2.bias = WF(h, "up2.b");
     e2.res = BUF<float>(h, "s0"); e2.ld_res = 32;
@@ -597,6 +619,12 @@ extern "C" int cv_sam2_forward(cv_sam2* h, const void* images, int input_kind, i
 }
 
 extern "C" int cv_sam2_last_launches(cv_sam2* h) { return h ? h->launches : 0; }
+
+extern "C" int cv_sam2_set_debug(cv_sam2* h, int count_fp16_saturation) {
+  if (!h) return cvb_fail(CV_ERR_INVALID, "cv_sam2_set_debug: null");
+  h->count_sat = count_fp16_saturation ? 1 : 0;
+  return CV_OK;
+}
 
 // Copies an internal activation buffer (debug / parity taps) into caller memory on the device.
 extern "C" int cv_sam2_read_buffer(cv_sam2* h, const char* name, void* dst_device, long long bytes, void* stream) {

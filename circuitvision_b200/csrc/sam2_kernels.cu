@@ -901,6 +901,28 @@ __global__ void __launch_bounds__(256) k_ln2d_gelu(const float* __restrict__ X, 
   *(uint2*)(out + r * 64 + l * 4) = make_uint2(tc::pack16(fp16, y0, y1), tc::pack16(fp16, y2, y3));
 }
 
+__global__ void __launch_bounds__(256) k_count_sat16(const uint4* __restrict__ p, long long n16, const uint16_t* __restrict__ tail,
+                                                     int n_tail, unsigned int* __restrict__ counter) {
+  unsigned int c = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = p[i];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) c += ((w[j] & 0x7FFFu) == 0x7BFFu) + (((w[j] >> 16) & 0x7FFFu) == 0x7BFFu);
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) c += (tail[threadIdx.x] & 0x7FFFu) == 0x7BFFu;
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(counter, c);
+}
+
+int launch_count_sat16(const uint16_t* p, long long n, unsigned int* counter, cudaStream_t st) {
+  if (((uintptr_t)p & 15) != 0) return cvb_fail(CV_ERR_INVALID, "count_sat16: buffer must be 16-byte aligned");
+  const long long n16 = n / 8;
+  const int grid = (int)std::min<long long>((n16 + 255) / 256 + 1, 148 * 8);
+  CVB_LAUNCH(k_count_sat16, dim3(grid), dim3(256), 0, st, (const uint4*)p, n16, p + n16 * 8, (int)(n - n16 * 8), counter);
+  return CV_OK;
+}
+
 int launch_ln2d_gelu(const float* X, long long rows, int C, const float* g, const float* b, float eps, int fp16,
                      __nv_bfloat16* out, cudaStream_t st) {
   if (C != 64) return cvb_fail(CV_ERR_INVALID, "ln2d_gelu: C must be 64");

@@ -88,4 +88,7 @@ int launch_tail(const float* low_res, int src_full, int B, const RefineWeights& 
 int launch_resize_threshold(const float* high_res, int B, int S, int H, int W, float* out_logits, uint8_t* mask_u8,
                             int* extents, cudaStream_t st);
 
+// ---- debug tap: counter[0] += number of 16-bit entries equal to +-65504 (a saturated cvt.rn.satfinite.f16 result)
+int launch_count_sat16(const uint16_t* p, long long n, unsigned int* counter, cudaStream_t st);
+
 }  // namespace cvb

@@ -52,38 +52,98 @@ def _box_ref(b):
     return u
 
 
+_CLASS_CACHE: dict = {}
+
+
+def _class_flags(cls):
+    """(cv_box flags, contact threshold) of a class name (:1326, :51-52, :1404-1415) — cached per distinct name."""
+    v = _CLASS_CACHE.get(cls)
+    if v is None:
+        flags = 0
+        if cls not in PRESERVE_IN_MASK:
+            flags |= CV_BOX_ZERO_IN_MASK
+        if cls not in NON_COMPONENTS:
+            flags |= CV_BOX_IS_COMPONENT
+        if cls in SOURCE_COMPONENTS:
+            flags |= CV_BOX_IS_SOURCE
+        v = _CLASS_CACHE[cls] = (flags, 20 if cls in SOURCE_COMPONENTS else (8 if cls in THRESH_8 else 6))
+    return v
+
+
+class ResizedBoxes:
+    """The reference's `processing_bboxes_resized` (:807, resize_bboxes :461-477) of one image, materialised lazily: the
+    integer coordinates of every box are computed vectorised at pack time, the dict copy of a box is only built when a
+    node actually references it (a handful per image)."""
+
+    __slots__ = ("boxes", "xyxy", "_cache")
+
+    def __init__(self, boxes, xyxy):
+        self.boxes, self.xyxy, self._cache = boxes, xyxy, {}
+
+    def __len__(self):
+        return len(self.boxes)
+
+    def __getitem__(self, j):
+        r = self._cache.get(j)
+        if r is None:
+            r = self.boxes[j].copy()
+            r["xmin"], r["ymin"], r["xmax"], r["ymax"] = (int(v) for v in self.xyxy[j])
+            self._cache[j] = r
+        return r
+
+    def __iter__(self):
+        return (self[j] for j in range(len(self.boxes)))
+
+
 def pack_boxes(boxes_list, H: int, W: int):
-    """-> (cv_box records [sum n], offsets int32 [B+1], resized dict lists, max boxes per image)."""
+    """-> (cv_box records [sum n], offsets int32 [B+1], per-image ResizedBoxes, max boxes per image).
+    One NumPy pass over all boxes of the batch: `int(v)` (:1339-1340) and `int(v * scale)` (:466-469) are truncations
+    toward zero of the same float64 products the reference forms."""
     new_w = resized_width(H, W)
     sx, sy = new_w / W, RESIZED_HEIGHT / H  # :807
-    total = sum(len(b) for b in boxes_list)
-    rec = np.zeros(max(total, 1), BOX_DTYPE)
+    counts = [len(b) for b in boxes_list]
+    total = sum(counts)
     offs = np.zeros(len(boxes_list) + 1, np.int32)
+    np.cumsum(counts, out=offs[1:])
+    rec = np.zeros(max(total, 1), BOX_DTYPE)
     resized_all = []
-    k = 0
-    for bi, boxes in enumerate(boxes_list):
-        rboxes = resize_bboxes(boxes, sx, sy)
-        resized_all.append(rboxes)
-        first = {}
-        for j, (b, rb) in enumerate(zip(boxes, rboxes)):
-            cls = b["class"]
-            r = rec[k]
-            r["xmin"], r["ymin"], r["xmax"], r["ymax"] = int(b["xmin"]), int(b["ymin"]), int(b["xmax"]), int(b["ymax"])
-            r["rxmin"], r["rymin"], r["rxmax"], r["rymax"] = rb["xmin"], rb["ymin"], rb["xmax"], rb["ymax"]
-            flags = 0
-            if cls not in PRESERVE_IN_MASK:
-                flags |= CV_BOX_ZERO_IN_MASK
-            if cls not in NON_COMPONENTS:
-                flags |= CV_BOX_IS_COMPONENT
-            if cls in SOURCE_COMPONENTS:
-                flags |= CV_BOX_IS_SOURCE
-            r["flags"] = flags
-            r["thresh"] = 20 if cls in SOURCE_COMPONENTS else (8 if cls in THRESH_8 else 6)
-            r["uid_group"] = first.setdefault(_box_ref(rb), j)
-            k += 1
-        offs[bi + 1] = k
-    max_per = max((len(b) for b in boxes_list), default=0)
+    if total:
+        flat = [b for boxes in boxes_list for b in boxes]
+        xy = np.array([(b["xmin"], b["ymin"], b["xmax"], b["ymax"]) for b in flat], dtype=np.float64).reshape(total, 4)
+        ixy = np.trunc(xy).astype(np.int64)
+        rxy = np.trunc(xy * np.array([sx, sy, sx, sy])).astype(np.int64)
+        for k, f in enumerate(("xmin", "ymin", "xmax", "ymax")):
+            rec[f][:total] = ixy[:, k]
+            rec["r" + f][:total] = rxy[:, k]
+        ft = np.array([_class_flags(b["class"]) for b in flat], dtype=np.int32).reshape(total, 2)
+        rec["flags"][:total], rec["thresh"][:total] = ft[:, 0], ft[:, 1]
+        k = 0
+        for boxes, n in zip(boxes_list, counts):
+            r = rxy[k:k + n]
+            first = {}
+            grp = rec["uid_group"][k:k + n]
+            for j, b in enumerate(boxes):
+                u = b.get("persistent_uid")
+                if u is None:  # identity used by the reference's de-duplication (:1424-1436), on RESIZED coordinates
+                    u = (b["class"], int(r[j, 0]), int(r[j, 1]), int(r[j, 2]), int(r[j, 3]))
+                grp[j] = first.setdefault(u, j)
+            resized_all.append(ResizedBoxes(boxes, r))
+            k += n
+    else:
+        resized_all = [ResizedBoxes(b, np.zeros((0, 4), np.int64)) for b in boxes_list]
+    max_per = max(counts, default=0)
     return rec[:total] if total else rec[:0], offs, resized_all, max_per
+
+
+_ATOMIC = (str, int, float, bool, type(None), np.integer, np.floating)
+
+
+def _copy_box(b: dict) -> dict:
+    """deepcopy(bbox) of :1422 for the dicts YOLO post-processing builds (flat scalars); nested values fall back to deepcopy."""
+    for v in b.values():
+        if not isinstance(v, _ATOMIC):
+            return deepcopy(b)
+    return b.copy()
 
 
 class NodeBatchResult:
@@ -113,40 +173,54 @@ class NodeBatchResult:
     def status(self):
         return self.tables_to_host()["results"]["status"]
 
-    def nodes(self, b: int):
-        """new_nodes_list of image b in the reference's format (:1547-1568)."""
+    def _image_tables(self, b: int):
+        """(result row, contours[nK], pairs[nP], points[nPts,2]) of image b from the dense tables or from the packed blob
+        of cv_nodes_pack (pipeline.py)."""
         h = self.tables_to_host()
         res = h["results"][b]
+        if "blob" in h:
+            off, nK, nP, nPt = (int(v) for v in h["header"][b])
+            blob = h["blob"]
+            con = np.frombuffer(blob, CONTOUR_DTYPE, nK, off)
+            off += nK * CONTOUR_DTYPE.itemsize
+            prs = np.frombuffer(blob, PAIR_DTYPE, nP, off)
+            off += nP * PAIR_DTYPE.itemsize
+            pts = np.frombuffer(blob, np.int32, 2 * nPt, off).reshape(-1, 2)
+            return res, con, prs, pts
+        nK, nP = int(res["n_contours"]), int(res["n_pairs"])
+        return res, h["contours"][b, :nK], h["pairs"][b, :nP], h["points"][b]
+
+    def nodes(self, b: int):
+        """new_nodes_list of image b in the reference's format (:1547-1568)."""
+        res, con, prs, pts = self._image_tables(b)
         if res["status"]:
             raise CvError(f"node analysis of image {b} overflowed a capacity (status {int(res['status'])})")
-        nK, nP = int(res["n_contours"]), int(res["n_pairs"])
-        con, prs, pts = h["contours"][b, :nK], h["pairs"][b, :nP], h["points"][b]
         rb = self.resized_boxes[b]
         comps = {}
-        for p in prs:
-            comps.setdefault(int(p["contour"]), []).append(deepcopy(rb[int(p["box"])]))  # :1422
+        for ci, bi in zip(prs["contour"].tolist(), prs["box"].tolist()):
+            comps.setdefault(ci, []).append(_copy_box(rb[bi]))  # :1422
         out = []
-        keep = np.nonzero(con["new_id"] >= 0)[0]
-        for k in keep[np.argsort(con["new_id"][keep], kind="stable")]:
-            c = con[k]
-            poly = np.ascontiguousarray(pts[int(c["offset"]):int(c["offset"]) + int(c["nverts"])]).reshape(-1, 1, 2)
-            out.append({"id": int(c["new_id"]), "components": comps.get(int(k), []), "contour": poly.astype(np.int32)})
+        new_id = con["new_id"]
+        keep = np.nonzero(new_id >= 0)[0]
+        offs, nv = con["offset"], con["nverts"]
+        for k in keep[np.argsort(new_id[keep], kind="stable")].tolist():
+            o = int(offs[k])
+            poly = np.array(pts[o:o + int(nv[k])], dtype=np.int32).reshape(-1, 1, 2)
+            out.append({"id": int(new_id[k]), "components": comps.get(k, []), "contour": poly})
         return out
 
     def connection_points(self, b: int):
-        h = self.tables_to_host()
-        nP = int(h["results"][b]["n_pairs"])
-        return [(int(p["px"]), int(p["py"])) for p in h["pairs"][b, :nP]]
+        _, _, prs, _ = self._image_tables(b)
+        return list(zip(prs["px"].tolist(), prs["py"].tolist()))
 
     def all_contours(self, b: int):
         """Every contour that passed the area filter (get_contours' list, :412), id order."""
-        h = self.tables_to_host()
-        nK = int(h["results"][b]["n_contours"])
+        _, con, _, pts = self._image_tables(b)
         out = []
-        for k in range(nK):
-            c = h["contours"][b, k]
-            poly = np.ascontiguousarray(h["points"][b][int(c["offset"]):int(c["offset"]) + int(c["nverts"])])
-            out.append({"id": k, "contour": poly.reshape(-1, 1, 2).astype(np.int32),
+        for k in range(len(con)):
+            c = con[k]
+            poly = np.array(pts[int(c["offset"]):int(c["offset"]) + int(c["nverts"])], dtype=np.int32)
+            out.append({"id": k, "contour": poly.reshape(-1, 1, 2),
                         "area": abs(int(c["a00"])) * 0.5 / (RESIZED_HEIGHT * self.new_w),
                         "rectangle": (int(c["xmin"]), int(c["ymin"]), int(c["xmax"] - c["xmin"] + 1),
                                       int(c["ymax"] - c["ymin"] + 1))})
@@ -246,6 +320,11 @@ class NodeAnalyzer:
                     self.caps["max_points"] *= 4
                 if st & 8:
                     self.caps["max_pairs"] *= 4
+                if st & 16:
+                    raise CvError("node analysis: one component box touches more than 64 kept contours — beyond the contact "
+                                  "kernel's per-box staging limit (CV_STATUS_BOX_HITS_OVERFLOW); growing the tables cannot help")
+                if self.caps["max_pairs"] > (1 << 20) or self.caps["max_points"] > (1 << 24):
+                    break
             raise CvError("node analysis capacities could not be satisfied")
 
 

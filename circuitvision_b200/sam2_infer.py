@@ -41,6 +41,7 @@ def _declare(lib):
     lib.cv_sam2_set_max_batch.argtypes = [vp, i32]
     lib.cv_sam2_forward.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, i32, vp, vp, vp]
     lib.cv_sam2_last_launches.argtypes = [vp]
+    lib.cv_sam2_set_debug.argtypes = [vp, i32]
     lib.cv_sam2_read_buffer.argtypes = [vp, C.c_char_p, vp, ll, vp]
     lib.cv_sam2_preprocess.argtypes = [vp, i32, i32, i32, vp, vp, vp]
     lib.cv_sam2_resize_logits.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp]
@@ -251,6 +252,14 @@ class _Engine:
                 self.launches += self.lib.cv_sam2_last_launches(self.h)
         return dict(high=high, low=low, iou=iou, mask=mask, logits=logits, extents=ext)
 
+    def set_debug(self, count_saturation: bool):
+        """Debug tap: count fp32 -> fp16 conversions that saturated (+-65504) in the 16-bit activation buffers."""
+        _lib.check(self.lib.cv_sam2_set_debug(self.h, int(bool(count_saturation))), "cv_sam2_set_debug")
+
+    def saturation_count(self) -> int:
+        """Saturated fp16 conversions of the last forward (needs set_debug(True) before it; 0 in bf16 mode)."""
+        return int(self.read_buffer("satcount", (1,), torch.int32).cpu()[0])
+
     def read_buffer(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
         with torch.cuda.device(self.dev):
             t = torch.empty(shape, dtype=dtype, device="cuda")
@@ -430,25 +439,3 @@ def segment_to_mask(model: SAM2ImageWrapper, transforms: SAM2Transforms, image_n
         e = r["extents"][0].cpu().tolist()
     bbox = (e[0], e[1], e[2] + 1, e[3] + 1) if e[2] >= 0 else None
     return mask, bbox
-
-
-def smoke():
-    """One tiny-variant forward on cuda:0 checked against the fp32 oracle (called by __graft_entry__.smoke)."""
-    from oracle import sam2_oracle
-    from . import synth
-    ref = sam2_oracle.build_oracle("tiny", seed=0)
-    model = get_modified_sam2("tiny", None, device="cuda:0", use_refinement_layer=True)
-    model.load_state_dict(ref.state_dict())
-    _, _, rgb = synth.make_schematic(5, IMAGE_SIZE, render_rgb=True)
-    x = sam2_oracle.preprocess_rgb(rgb)[None]
-    with torch.no_grad():
-        rh, rl, ri = ref(x)
-    high, low, iou = model(x.cuda())
-    torch.cuda.synchronize()
-    err = (low.cpu() - rl).abs().max().item() / rl.std().item()
-    a, b = (high.cpu() > 0), (rh > 0)
-    inter, union = (a & b).sum().item(), (a | b).sum().item()
-    miou = inter / union if union else 1.0
-    print(f"smoke: SAM2.1-tiny low-res logits max|err|/std = {err:.4f}, mask IoU vs fp32 oracle = {miou:.4f}, "
-          f"{model.engine().launches} kernel launches")
-    assert miou >= 0.99, miou

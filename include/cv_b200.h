@@ -69,6 +69,7 @@ typedef struct cv_pair {              /* one accepted (node, component) attachme
 #define CV_STATUS_CONTOUR_OVERFLOW 2
 #define CV_STATUS_POINT_OVERFLOW 4
 #define CV_STATUS_PAIR_OVERFLOW 8
+#define CV_STATUS_BOX_HITS_OVERFLOW 16 /* one box touches more than 64 kept contours (fixed staging limit of the contact kernel) */
 
 typedef struct cv_image_result {
   int32_t n_external;  /* external components before the area filter */
@@ -101,6 +102,14 @@ int cv_nodes_analyze(const uint8_t* masks, int B, int H, int W, const cv_box* bo
                      int max_boxes_per_image, uint8_t* emptied, uint8_t* resized, uint8_t* enhanced,
                      cv_contour* contours, int32_t* points, cv_pair* pairs, cv_image_result* results,
                      const cv_nodes_caps* caps, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Compacts the used prefixes of the fixed-capacity result tables of cv_nodes_analyze into one contiguous blob, so that
+ * only bytes that carry information cross PCIe (bench.py e2e; circuitvision_b200/pipeline.py).  All device pointers.
+ * header: int64 [4*(B+1)] = {byte offset of image b's section, n_contours, n_pairs, n_points}, header[4*B] = total bytes;
+ * section b = cv_contour[n_contours] | cv_pair[n_pairs] | int32 (x,y)[n_points], 16-byte aligned.  An image whose
+ * section would end beyond blob_bytes is not copied (the caller compares header[4*B] with the capacity).              */
+int cv_nodes_pack(const cv_contour* contours, const int32_t* points, const cv_pair* pairs, const cv_image_result* results,
+                  int B, const cv_nodes_caps* caps, long long* header, uint8_t* blob, long long blob_bytes, void* stream);
 
 /* ------------------------------------------------------------------ terminal reclassification
  * replaces the numeric part of circuit_analyzer.py:2217-2310 (reclassify_terminals_based_on_connectivity) with its
@@ -181,6 +190,10 @@ int cv_sam2_forward(cv_sam2* h, const void* images, int input_kind, int swap_rb,
                     float* high_res, uint8_t* mask_u8, int out_h, int out_w, float* out_logits, int* extents,
                     void* stream);
 int cv_sam2_last_launches(cv_sam2* h);
+/* Debug tap: with count_fp16_saturation != 0 every 16-bit activation buffer is scanned after the kernel that wrote it and
+ * the number of entries that saturated in the fp32 -> fp16 conversion (+-65504) accumulates in the uint32 buffer
+ * "satcount" (cv_sam2_read_buffer), reset at the start of each cv_sam2_forward.  Off by default (extra launches).  */
+int cv_sam2_set_debug(cv_sam2* h, int count_fp16_saturation);
 /* Parity taps: copy an internal activation buffer (DESIGN.md names them) to caller device memory. */
 int cv_sam2_read_buffer(cv_sam2* h, const char* name, void* dst_device, long long bytes, void* stream);
 /* SAM2Transforms.__call__ for one uint8 HWC image of any size -> float32 CHW [3,1024,1024]; tmp: H*1024*3 floats. */

@@ -71,6 +71,11 @@ def golden_cases():
     # values other than {0,255} in the mask (any non-zero is foreground downstream)
     m2 = (m // 255) * 37
     cases["mask_value_37"] = (m2.astype(np.uint8), b)
+    # the two real schematics the reference ships (hand-drawn photo: noisy mask, many vertices; printed bridge), mask =
+    # segment_circuit(page), hand-written boxes (oracle/real_cases.py; pages travel as tests/golden/real_pages.npz)
+    from oracle import real_cases
+    for name, (rgb, mask, boxes) in real_cases.real_cases().items():
+        cases[f"real_{name}"] = (mask, boxes)
     return cases
 
 
@@ -130,6 +135,9 @@ def terminal_cases():
     col[300:310, 50:450] = (250, 10, 10)
     col[100:310, 240:250] = (10, 250, 10)
     cases["colour_channels"] = (col, [_box("terminal", 230, 190, 262, 222), _box("terminal", 40, 90, 70, 120)])
+    from oracle import real_cases
+    for name, (rgb, mask, boxes) in real_cases.real_cases().items():
+        cases[f"real_{name}"] = (rgb, boxes)
     return cases
 
 
@@ -191,6 +199,10 @@ def main():
     meta = {}
     for name, (mask, boxes) in golden_cases().items():
         nodes, emptied, enhanced, cimg, fviz, cpts, text = ref_loader.reference_node_analysis(mask, boxes)
+        # the connection points themselves (cyan discs of the third drawing): recovered from the oracle restatement,
+        # which the test suite pins to these very fixtures
+        from oracle import node_oracle
+        conn_pts = node_oracle.get_node_connections(mask, boxes)[4]
         meta[name] = {
             "shape": list(mask.shape),
             "n_boxes": len(boxes),
@@ -202,6 +214,9 @@ def main():
             "enhanced_sha256": _sha(enhanced),
             "enhanced_shape": list(enhanced.shape),
             "mask_sha256": _sha(mask),
+            # the three debug drawings the reference returns (:414-458, :1585-1603), byte for byte
+            "contour_viz_sha256": _sha(cimg), "final_viz_sha256": _sha(fviz), "points_viz_sha256": _sha(cpts),
+            "connection_points": [[int(p[0]), int(p[1])] for p in conn_pts],
         }
         for n in nodes:
             store[f"{name}/contour{int(n['id'])}"] = np.asarray(n["contour"], np.int32).reshape(-1, 2)

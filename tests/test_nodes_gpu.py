@@ -47,6 +47,11 @@ def test_golden_fixtures_from_unmodified_reference(analyzer, golden, golden_case
             assert np.array_equal(n["contour"].reshape(-1, 2), z[f"{name}/contour{gn['id']}"]), name
             assert n["contour"].dtype == np.int32 and n["contour"].shape[1:] == (1, 2)
         assert cviz.shape == enhanced.shape + (3,) and fviz.shape == cviz.shape and pviz.shape == cviz.shape
+        # the three debug drawings (circuit_analyzer.py:414-458, :1585-1603): same cv2 calls on device-produced contours /
+        # connection points / resized image => byte-identical to what the unmodified reference returned
+        assert _sha(cviz) == g["contour_viz_sha256"], name
+        assert _sha(fviz) == g["final_viz_sha256"], name
+        assert _sha(pviz) == g["points_viz_sha256"], name
         # netlist connectivity: the drop-in's own generate_netlist_from_nodes / stringify_line on the device-produced
         # node table against the text the unmodified reference printed for this case
         text = "\n".join(analyzer.stringify_line(l) for l in analyzer.generate_netlist_from_nodes(nodes))
