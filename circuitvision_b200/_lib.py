@@ -50,6 +50,7 @@ def _declare(lib):
     lib.cv_nodes_workspace_bytes.restype = sz
     lib.cv_nodes_analyze.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp,
                                      C.POINTER(cv_nodes_caps), vp, sz, vp]
+    lib.cv_nodes_pack.argtypes = [vp, vp, vp, vp, i32, C.POINTER(cv_nodes_caps), vp, vp, C.c_longlong, vp]
     lib.cv_terminals_workspace_bytes.argtypes = [i32, i32, i32, C.POINTER(cv_nodes_caps)]
     lib.cv_terminals_workspace_bytes.restype = sz
     lib.cv_terminals_analyze.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, vp, vp, vp, vp, vp, C.POINTER(cv_nodes_caps),
@@ -59,6 +60,7 @@ def _declare(lib):
     lib.cv_ccl_label.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, sz, vp]
     ll = C.c_longlong
     lib.cv_gemm_bf16.argtypes = [vp, ll, vp, ll, i32, i32, i32, vp, i32, vp, ll, vp, ll, vp, ll, vp]
+    lib.cv_mlp_fused.argtypes = [vp, i32, i32, vp, vp, C.c_float, vp, vp, vp, vp, i32, vp]
     lib.cv_attention_bf16.argtypes = [vp, ll, i32, i32, vp, ll, i32, i32, vp, ll, i32, i32, i32, i32, i32, i32, i32,
                                       i32, C.c_float, vp, ll, vp]
     lib.cv_profile_enable.argtypes = [i32]

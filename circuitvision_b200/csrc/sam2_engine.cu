@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "gemm_tc.cuh"
+#include "mlp_fused.cuh"
 #include "sam2_kernels.cuh"
 
 namespace cvb {
@@ -351,7 +352,20 @@ static int run_block(cv_sam2* h, int i, int B, float* X, float* Xn, cudaStream_t
     ep.ws = wso; ep.nwx = nwx; ep.nwy = nwy; ep.H = Ho; ep.W = Wo;
   }
   TRY(gemm(h, AO, Cp, WB(h, pre + ".proj.w"), (int)(p.pool ? M / 4 : M), C, Cp, ep, st));
-  // norm2 -> MLP (GELU) -> residual
+  // norm2 -> MLP (GELU) -> residual: one fused kernel for the stage-1/2 widths (normalised operand, hidden activation and
+  // fc2 accumulator stay on the SM), LayerNorm + two GEMMs otherwise
+  if (mlp_fused_supported(C)) {
+    MlpFusedArgs m;
+    m.X = Xo; m.M = (int)To; m.C = C;
+    m.gamma = WF(h, pre + ".n2.g"); m.beta = WF(h, pre + ".n2.b"); m.eps = 1e-6f;
+    m.W1 = WB(h, pre + ".fc1.w"); m.b1 = WF(h, pre + ".fc1.b");
+    m.W2 = WB(h, pre + ".fc2.w"); m.b2 = WF(h, pre + ".fc2.b");
+    m.fp16 = h->f16;
+    m.sat_counter = h->count_sat ? BUF<unsigned int>(h, "satcount") : nullptr;
+    TRY(mlp_fused_launch(m, device_sm_count(), st));
+    h->launches++;
+    return CV_OK;
+  }
   TRY(launch_ln_rows(Xo, To, C, WF(h, pre + ".n2.g"), WF(h, pre + ".n2.b"), 1e-6f, B, Ho, Wo, 0, h->f16, A, nullptr, st));
   h->launches++;
   GemmEpilogue e1;

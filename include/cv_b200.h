@@ -145,6 +145,13 @@ int cv_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int
                  int act, const float* residual, long long ld_res, float* out_f32, long long ld_f32, void* out_bf16,
                  long long ld_bf16, void* stream);
 
+/* Fused Hiera MLP half-block (sam2 MultiScaleBlock: x + mlp(norm2(x)), called from sam2_infer.py:226 through the sam2
+ * package):  X[M,C] (fp32, in place)  <-  X + fc2(GELU(fc1(LayerNorm(X; gamma, beta, eps)))).  W1 [4C,C] and W2 [C,4C] are
+ * 16-bit K-major weights in the operand format selected by operand_fp16, b1 [4C] / b2 [C] fp32.  The normalised operand,
+ * the hidden activation and the fc2 accumulator stay on the SM (shared memory / TMEM).  C in {96,112,144,192,224,288}.   */
+int cv_mlp_fused(float* X, int M, int C, const float* gamma, const float* beta, float eps, const void* W1, const float* b1,
+                 const void* W2, const float* b2, int operand_fp16, void* stream);
+
 /* Block-diagonal flash attention on tcgen05 (head_dim 96): tokens are window-major; query row i (window i / Wq)
  * attends the Wkv keys of the same window.  Covers Hiera's windowed, Q-pooled (Wq = Wkv/4) and global
  * (Wq = Wkv = tokens per image) attention (sam2 package, called from sam2_infer.py:226).  q/k/v are bf16 matrices
