@@ -3,21 +3,20 @@
 // Not a reference code path: the oracle is cv2.connectedComponents up to renaming; labels are
 // canonical: labels[p] = 1 + min linear index of p's component, 0 for background.
 //
-// Traffic plan (the kernel is HBM-bound; algorithmic bytes = 1 B/px mask read + 4 B/px label write):
-//   pass A  k_ccl_tile_label : each CTA loads a 256 x 32 tile of the mask as BITS (one 32-pixel word per thread), labels it
-//                              entirely in shared memory (elements = maximal horizontal runs; unions between adjacent
-//                              rows by bit overlap; atomicMin union-find on a 16 KB parent array, one slot per pixel pair) and writes the label
-//                              image once, fully coalesced: 1 + 4 B/px.  It also emits a per-word "dirty" bitmap
-//                              (word holds a run of a component that touches the tile border) and counts the
-//                              components that stay inside their tile.
-//   pass B  k_ccl_seams_h/_v : only the tile seams (3.5 % of the image; horizontal seams one 32-pixel word per thread, one
-//                              union per run contact) merge components across tiles with the
-//                              global atomicMin union-find on the label image (roots point at roots; the finds halve the
-//                              paths they walk, which replaced a separate compression pass).
-//   pass C  k_ccl_tile_fixup : one thread per 32-pixel word re-reads the mask bits (1 B/px, no full label read), takes
-//                              the tile-local root named at each sub-run's first pixel, looks up its global root and
-//                              rewrites only the runs whose component changed (sparse row segments); counts roots.
-// Total ≈ 6 B/px + seams instead of the 16+ B/px of a per-pixel init / merge / flatten pipeline.
+// Traffic plan (the path is HBM-bound; algorithmic bytes = 1 B/px mask read + 4 B/px label write), three passes:
+//   pass A  k_ccl_scan       : one WARP per tile of 1024 x 32 pixels, lane = one 32-pixel word column, rows top to bottom.
+//                              Reads the mask once (1 B/px), writes the bit plane (1 bit/px), the parent entries of the run
+//                              elements (in the label image, at run-start pixels only) and head[word] (first pixel of the
+//                              run that enters a word from the left).  No block barriers, no shared atomics: labels flow
+//                              down the rows through two shared-memory rows of slots per warp, ballot / match / shuffle
+//                              resolve the runs that span several words, and only real merges (two different labels
+//                              meeting) touch the global union-find.
+//   pass B  k_ccl_seam_*     : unions across the tile seams (rows y = 32 k: 3.1 % of the image; columns x = 1024 k).
+//   pass C  k_ccl_write      : the label image is written exactly once (4 B/px): run start from the bit plane, root by
+//                              pointer chasing, 16-byte stores.  It also counts the roots.
+// Total ~ 5.3 B/px.  The algorithm is modelled lane by lane in oracle/ccl_scan_model.py (held to cv2 on the CPU by
+// tests/test_ccl_model_cpu.py); round 1's block-level shared-memory union-find + fix-up pass (6+ B/px, 72 % issue-bound,
+// 35 % of its stalls at __syncthreads) reached 0.32 of the HBM copy peak.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -27,7 +26,6 @@
 
 namespace cvb {
 
-constexpr int CT_W = 256, CT_H = 32, CT_WORDS = CT_W / 32, CT_THREADS = CT_H * CT_WORDS;  // 256 x 32 tile, 256 threads
 
 // ---- global union-find on the label image (parent of x = L[x] - 1; 0 = background)
 __device__ __forceinline__ int gfind(const int* L, int x) {
@@ -73,35 +71,8 @@ __device__ __forceinline__ void gunion(int* L, int a, int b) {
   } while (!done);
 }
 
-// ---- shared-memory union-find on sub-run start positions (tile-local pixel index)
-// Slot of element x = x >> 1: two horizontally adjacent pixels are never both the first pixel of a (sub-)run, so the
-// parent array needs one slot per pixel PAIR (8 KB per tile instead of 16 KB: twice the resident tiles per SM).
-__device__ __forceinline__ int sfind(const volatile int* P, int x) {
-  int y = P[x >> 1];
-  while (y != x) {
-    x = y;
-    y = P[x >> 1];
-  }
-  return x;
-}
-__device__ __forceinline__ void sunion(int* P, int a, int b) {
-  bool done;
-  do {
-    a = sfind(P, a);
-    b = sfind(P, b);
-    if (a < b) {
-      int old = atomicMin(P + (b >> 1), a);
-      done = (old == b);
-      b = old;
-    } else if (b < a) {
-      int old = atomicMin(P + (a >> 1), b);
-      done = (old == a);
-      a = old;
-    } else {
-      done = true;
-    }
-  } while (!done);
-}
+// union of two ELEMENTS (run-start pixels with a parent entry)
+__device__ __forceinline__ void gunion_roots(int* L, int a, int b) { gunion(L, a, b); }
 
 // start of the sub-run of `word` that contains set bit x
 __device__ __forceinline__ int run_start(uint32_t word, int x) {
@@ -139,280 +110,341 @@ __device__ __forceinline__ uint32_t load_word(const uint8_t* __restrict__ im, in
   return w;
 }
 
-// Element of the union-find = a maximal horizontal run of the tile row (it may span several 32-pixel words), identified
-// by the tile-local index of its first pixel.  fid[r][c] = element of the run that ENTERS word c of row r from the left
-// (valid when the word's bit 0 is set and the previous word's bit 31 is set).
-__device__ __forceinline__ bool carries_in(const uint32_t (*bits)[CT_WORDS], int r, int c) {
-  return c > 0 && (bits[r][c] & 1u) && (bits[r][c - 1] >> 31);
-}
-__device__ __forceinline__ int elem_of(const uint32_t (*bits)[CT_WORDS], const int (*fid)[CT_WORDS], int r, int c, int st) {
-  return (st == 0 && carries_in(bits, r, c)) ? fid[r][c] : r * CT_W + c * 32 + st;
-}
-
-// Thread <-> word mapping: lane = row, warp = word column (r = t % 32, c = t / 32).  A vertical wire then keeps whole
-// warps busy instead of one lane in every warp, which matters because the union-find code is divergent.
+// ================================================================================================
+// pass A: warp-sequential scan.  One warp per tile of 1024 x CS_TH pixels, lane = one 32-pixel word column, rows top to
+// bottom.  Model: oracle/ccl_scan_model.py (pass_a_tile) — same names, same order.
 //
-// Builds the tile's union-find in shared memory.  On return (after the trailing __syncthreads) the forest is complete:
-// sfind(P, e) gives the ROOT (tile-local pixel index of the component's first pixel in raster order) of run element e.
-template <int CONN>
-__device__ __forceinline__ uint32_t tile_label(const uint8_t* __restrict__ im, int H, int W, int x0, int y0, bool vec_ok,
-                                               uint32_t (*bits)[CT_WORDS], int (*fid)[CT_WORDS], int* P) {
-  const int r = threadIdx.x % CT_H, c = threadIdx.x / CT_H;
-  const uint32_t w = load_word(im, H, W, y0 + r, x0 + c * 32, vec_ok);
-  const int base = r * CT_W + c * 32;
-  bits[r][c] = w;
-  __syncthreads();
-  // the run that enters my word from the left starts in the nearest word to the left that is not completely set
-  bool cin = false;
-  int first = base;
-  if (c > 0 && (w & 1u) && (bits[r][c - 1] >> 31)) {
-    cin = true;
-    for (int k = c - 1; k >= 0; k--) {
-      const uint32_t lw = bits[r][k];
-      const int ls = run_start(lw, 31);
-      first = r * CT_W + k * 32 + ls;
-      if (ls > 0 || k == 0 || !(bits[r][k - 1] >> 31)) break;
-    }
+// Element of the union-find = a maximal horizontal run inside the tile row, identified by the linear index of its first
+// pixel; its parent entry lives in the label image AT that pixel (L[start] = parent + 1), nowhere else.  A run takes the
+// label (ancestor index) of a run it touches in the row above, so vertical structures never build chains; a run that
+// touches nothing becomes a root; touching two different labels is a (rare) union with global atomics.
+// lab[parity][lane][start bit >> 1] = label of the word-local sub-run starting at that bit (two runs cannot start at
+// adjacent bits), for the previous and the current row.
+// ================================================================================================
+constexpr int CS_TH = 32;        // rows per tile
+constexpr int CS_WARPS = 8;      // tiles (stacked vertically) per CTA
+constexpr int CS_LSTRIDE = 17;   // 16 slots + 1: lane stride coprime with the 32 banks
+constexpr int CS_INF = 0x7FFFFFFF;
+
+__device__ __forceinline__ void cs_combine(int* L, int& cd, int t) {
+  if (cd == CS_INF) {
+    cd = t;
+  } else if (t != cd) {
+    gunion_roots(L, cd, t);
+    cd = min(cd, t);
   }
-  fid[r][c] = first;
-  uint32_t starts = w & ~(w << 1);
-  if (cin) starts &= ~1u;  // a continued run is not an element of its own
-  for (uint32_t s = starts; s; s &= s - 1) {
-    int i = __ffs(s) - 1;
-    P[(base + i) >> 1] = base + i;
-  }
-  __syncthreads();
-  if (w && r > 0) {
-    const uint32_t up = bits[r - 1][c];
-    const uint32_t upl = (c > 0) ? bits[r - 1][c - 1] : 0u, upr = (c + 1 < CT_WORDS) ? bits[r - 1][c + 1] : 0u;
-    const bool up_cin = (c > 0) && (up & 1u) && (upl >> 31);
-    uint32_t cur = w;
-    while (cur) {
-      const int s = __ffs(cur) - 1;
-      const int len = run_len(cur, s);
-      const uint32_t rm = run_mask(s, len);
-      cur &= ~rm;
-      const int me = (s == 0 && cin) ? first : base + s;
-      uint32_t aw = rm;
-      if (CONN == 8) aw |= (rm << 1) | (rm >> 1);
-      uint32_t cand = aw & up;
-      while (cand) {
-        const int us = __ffs(cand) - 1;
-        const int st = run_start(up, us);
-        cand &= ~run_mask(st, run_len(up, st));
-        // both runs continue from the previous word and already touch there: that thread made the union
-        if (s == 0 && cin && st == 0 && up_cin) continue;
-        sunion(P, me, elem_of(bits, fid, r - 1, c, st));
-      }
-      if (CONN == 8) {
-        if (s == 0 && !cin && (upl >> 31)) sunion(P, me, elem_of(bits, fid, r - 1, c - 1, run_start(upl, 31)));
-        if (s + len == 32 && !(up >> 31) && (upr & 1u)) sunion(P, me, elem_of(bits, fid, r - 1, c + 1, 0));
-      }
-    }
-  }
-  __syncthreads();
-  return w;
 }
 
-// dirty[(b*n_tiles + tile)*4 + warp] bit l: the word owned by thread 32*warp + l holds a sub-run of a component that
-// touches the tile border — only such components can be merged by the seam pass, so only those words are revisited by
-// pass C.  Components that stay inside their tile are final after pass A and are counted here.
 template <int CONN>
-__global__ void __launch_bounds__(CT_THREADS, 8) k_ccl_tile_label(const uint8_t* __restrict__ masks, int* __restrict__ labels,
-                                                                int H, int W, int vec_ok, uint32_t* __restrict__ dirty,
-                                                                int* __restrict__ ncomp, int* __restrict__ partial) {
-  __shared__ uint32_t bits[CT_H][CT_WORDS];
-  __shared__ int fid[CT_H][CT_WORDS];
-  __shared__ int P[CT_H * CT_W / 2];
-  __shared__ uint32_t touch[CT_H * CT_W / 32];  // bit per tile-local pixel: root of a border-touching component
-  __shared__ int closed_roots;
-  const int b = blockIdx.z, x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
+__global__ void __launch_bounds__(CS_WARPS * 32) k_ccl_scan(const uint8_t* __restrict__ masks, int* __restrict__ labels,
+                                                           uint32_t* __restrict__ bits_all, int* __restrict__ head_all, int H,
+                                                           int W, int wpr, int vec_ok) {
+  __shared__ int lab_s[CS_WARPS][2][32 * CS_LSTRIDE];
+  const int warp = threadIdx.x >> 5, c = threadIdx.x & 31;
+  const int b = blockIdx.z, x0 = blockIdx.x * 1024, y0 = (blockIdx.y * CS_WARPS + warp) * CS_TH;
+  if (y0 >= H) return;
   const uint8_t* im = masks + (size_t)b * H * W;
   int* L = labels + (size_t)b * H * W;
-  if (threadIdx.x < CT_H * CT_W / 32) touch[threadIdx.x] = 0u;
-  if (threadIdx.x == 0) closed_roots = 0;
-  const uint32_t w = tile_label<CONN>(im, H, W, x0, y0, vec_ok != 0, bits, fid, P);
-  int* G = P;  // after the second sync below the slots hold the GLOBAL label of the sub-run starting there
-  const int r = threadIdx.x % CT_H, c = threadIdx.x / CT_H;
-  const int base = r * CT_W + c * 32;
-  const bool cin = carries_in(bits, r, c);
-  const uint32_t sub = w & ~(w << 1);  // every sub-run of my word, continued or not
-  // root and global label of every sub-run; roots of components that touch the tile border are marked.  The root is
-  // parked in the slot of base + i: for a run element that is path compression, for a continued sub-run the slot is unused.
-  for (uint32_t s = sub; s; s &= s - 1) {
-    const int i = __ffs(s) - 1;
-    const int root = sfind(P, (i == 0 && cin) ? fid[r][c] : base + i);
-    const bool edge = r == 0 || r == CT_H - 1 || (c == 0 && i == 0) || (c == CT_WORDS - 1 && i + run_len(w, i) == 32);
-    if (edge) atomicOr(&touch[root >> 5], 1u << (root & 31));
-    if (root != base + i) P[(base + i) >> 1] = root;
+  uint32_t* bits = bits_all + (size_t)b * H * wpr;
+  int* head = head_all + (size_t)b * H * wpr;
+  const int wc = blockIdx.x * 32 + c;
+  const bool valid = wc < wpr;
+  int(*lab)[32 * CS_LSTRIDE] = lab_s[warp];
+  uint32_t up = 0, upl = 0, upr = 0;
+  const int rows = min(CS_TH, H - y0);
+  // the rows of the tile are walked one after the other (each depends on the labels of the one above): pull the whole tile
+  // towards L2 first, then keep two rows in flight in registers, so that a row costs an L2 hit, not a DRAM round trip
+  if (valid) {
+    const uint8_t* pf = im + (size_t)y0 * W + x0 + c * 32;
+    for (int r = 0; r < rows; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (size_t)r * W));
   }
-  __syncthreads();
-  bool my_dirty = false;
-  int n_closed = 0;
-  for (uint32_t s = sub; s; s &= s - 1) {
-    const int i = __ffs(s) - 1;
-    const int root = P[(base + i) >> 1];
-    const bool t = (touch[root >> 5] >> (root & 31)) & 1u;
-    my_dirty |= t;
-    n_closed += (!t && root == base + i);  // first pixel of a component that cannot change any more
-    G[(base + i) >> 1] = (y0 + root / CT_W) * W + x0 + (root % CT_W) + 1;  // nobody else reads my slots any more
-  }
-  if (my_dirty) n_closed = 0;  // pass C revisits this word and counts every root in it
-  const uint32_t dmask = __ballot_sync(0xffffffffu, my_dirty);
-  if (dirty && (threadIdx.x & 31) == 0)
-    dirty[(((size_t)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (CT_THREADS / 32) + (threadIdx.x >> 5)] = dmask;
-  if (ncomp) {
-    for (int o = 16; o; o >>= 1) n_closed += __shfl_xor_sync(0xffffffffu, n_closed, o);
-    if ((threadIdx.x & 31) == 0 && n_closed) atomicAdd(&closed_roots, n_closed);
-  }
-  __syncthreads();
-  if (ncomp && dirty && threadIdx.x == 0 && closed_roots) {
-    if (partial) atomicAdd(partial + ((size_t)b * 32 + ((blockIdx.x + blockIdx.y) & 31)) * 32, closed_roots);
-    else atomicAdd(ncomp + b, closed_roots);
-  }
-  // coalesced label write: each warp takes rows warp, warp + n_warps, ...; per 128-pixel segment of the row lane l owns
-  // pixels 4l..4l+3
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int sh = (lane & 7) * 4;
-  for (int rr = warp; rr < CT_H; rr += CT_THREADS / 32) {
-    const int y = y0 + rr;
-    if (y >= H) break;
-#pragma unroll
-    for (int seg = 0; seg < CT_W / 128; seg++) {
-      const int wc = seg * 4 + (lane >> 3);
-      const uint32_t word = bits[rr][wc];
-      const uint32_t nib = (word >> sh) & 0xFu;
-      int out[4] = {0, 0, 0, 0};
-      if (nib) {
-        const int gb = rr * CT_W + wc * 32;
-        if (nib == 0xFu) {
-          out[0] = out[1] = out[2] = out[3] = G[(gb + run_start(word, sh)) >> 1];
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; k++)
-            if ((nib >> k) & 1u) out[k] = G[(gb + run_start(word, sh + k)) >> 1];
+  uint32_t w_next = valid ? load_word(im, H, W, y0, x0 + c * 32, vec_ok != 0) : 0u;
+  uint32_t w_next2 = (valid && rows > 1) ? load_word(im, H, W, y0 + 1, x0 + c * 32, vec_ok != 0) : 0u;
+  for (int r = 0; r < rows; r++) {
+    const int y = y0 + r, par = r & 1;
+    const uint32_t w = w_next;
+    w_next = w_next2;
+    if (r + 2 < rows) w_next2 = valid ? load_word(im, H, W, y + 2, x0 + c * 32, vec_ok != 0) : 0u;  // two rows in flight
+    if (valid) bits[(size_t)y * wpr + wc] = w;
+    uint32_t wl = __shfl_up_sync(0xffffffffu, w, 1), wr = __shfl_down_sync(0xffffffffu, w, 1);
+    if (c == 0) wl = 0u;
+    if (c == 31) wr = 0u;
+    const bool cin = (w & 1u) && (wl >> 31), cout = (w >> 31) && (wr & 1u);
+    const bool full = w == 0xFFFFFFFFu, brk = !(full && cin);
+    const uint32_t Bm = __ballot_sync(0xffffffffu, brk);
+    const int origin = cin ? 31 - __clz(Bm & ((1u << c) - 1u)) : c;  // lane 0 never has cin, so the mask is non-empty
+    const int rowbase = y * W + x0 + c * 32;
+    int* lp = lab[par ^ 1];  // previous row
+    int* lc = lab[par];
+    int ch = CS_INF, ct = CS_INF, tail_st = 0;
+    for (uint32_t s = w & ~(w << 1); s; s &= s - 1) {
+      const int st = __ffs(s) - 1;
+      const int len = run_len(w, st);
+      const uint32_t rm = run_mask(st, len);
+      int cd = CS_INF;
+      if (r > 0) {
+        uint32_t aw = rm;
+        if (CONN == 8) aw |= (rm << 1) | (rm >> 1);
+        uint32_t ov = aw & up;
+        while (ov) {
+          const int u = __ffs(ov) - 1;
+          const int us = run_start(up, u);
+          ov &= ~run_mask(us, run_len(up, us));
+          cs_combine(L, cd, lp[c * CS_LSTRIDE + (us >> 1)]);
+        }
+        if (CONN == 8) {
+          if ((rm & 1u) && (upl >> 31)) cs_combine(L, cd, lp[(c - 1) * CS_LSTRIDE + (run_start(upl, 31) >> 1)]);
+          if ((rm >> 31) && (upr & 1u)) cs_combine(L, cd, lp[(c + 1) * CS_LSTRIDE]);
         }
       }
-      const int x = x0 + seg * 128 + lane * 4;
-      int* dst = L + (size_t)y * W + x;
-      if (vec_ok && x + 4 <= W) {
-        *(int4*)dst = make_int4(out[0], out[1], out[2], out[3]);
+      const bool is_head = st == 0 && cin, is_tail = (rm >> 31) && cout;
+      if (is_head) {
+        ch = cd;  // joins the run that started in lane `origin`
+      } else if (is_tail) {
+        ct = cd;
+        tail_st = st;
       } else {
-        for (int k = 0; k < 4; k++)
-          if (x + k < W) dst[k] = out[k];
+        const int m = cd == CS_INF ? rowbase + st : cd;  // nothing touched: a root, named by its first pixel
+        L[rowbase + st] = m + 1;
+        lc[c * CS_LSTRIDE + (st >> 1)] = m;
       }
     }
+    // runs that span words: minimum over the portions, unions between portions that disagree
+    // (segmented backward min-scan over the followers of each origin: the groups are contiguous lane ranges, so five
+    //  shuffle steps do it; __match_any + __reduce_min on sub-masks compiled to a loop over ~30 singleton groups per row)
+    const int key = cin ? origin : 32 + c;
+    int gmin = cin ? ch : CS_INF;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v2 = __shfl_down_sync(0xffffffffu, gmin, d), k2 = __shfl_down_sync(0xffffffffu, key, d);
+      if (c + d < 32 && k2 == key) gmin = min(gmin, v2);
+    }
+    const int from_right = __shfl_down_sync(0xffffffffu, gmin, 1);  // first follower: minimum over the whole group
+    const bool tail_org = cout && brk;  // my tail run starts in my word and continues to the right
+    int my_m = 0;
+    const int my_start = rowbase + tail_st;
+    if (tail_org) {
+      const int tot = min(ct, from_right);
+      my_m = tot == CS_INF ? my_start : tot;
+      if (ct != CS_INF && ct != my_m) gunion_roots(L, ct, my_m);
+      L[my_start] = my_m + 1;
+      lc[c * CS_LSTRIDE + (tail_st >> 1)] = my_m;
+    }
+    const int mo = __shfl_sync(0xffffffffu, my_m, origin), so = __shfl_sync(0xffffffffu, my_start, origin);
+    if (cin) {
+      if (ch != CS_INF && ch != mo) gunion_roots(L, ch, mo);
+      lc[c * CS_LSTRIDE] = mo;
+      head[(size_t)y * wpr + wc] = so;
+    }
+    __syncwarp();  // label slots and parent entries of this row are visible to every lane before the next row reads them
+    up = w; upl = wl; upr = wr;
   }
 }
 
-// Seams.  Horizontal seams (rows y = k*CT_H, 3.1 % of the image) are handled one 32-pixel WORD per thread: the seam row
-// and the row above it are read as bits, and every (run below, run above) contact is one union between run
-// representatives — all pixels of a run carry the same tile-local root after pass A, so any pixel of it starts the
-// same find.  Vertical seams (columns x = k*CT_W, 0.8 %) stay one pixel per thread.
+// first pixel (linear index) of the tile-row run that contains pixel (y, 32 wc + bit); bit is set in bits[y][wc]
+__device__ __forceinline__ int cs_start_of(const uint32_t* __restrict__ bits, const int* __restrict__ head, int W, int wpr, int y,
+                                           int wc, int bit) {
+  const uint32_t wv = bits[(size_t)y * wpr + wc];
+  const int st = run_start(wv, bit);
+  if (st == 0 && (wc & 31) && (bits[(size_t)y * wpr + wc - 1] >> 31)) return head[(size_t)y * wpr + wc];
+  return y * W + wc * 32 + st;
+}
+
+// pass B, horizontal seams: rows y = k CS_TH against the row above, one 32-pixel word per thread
 template <int CONN>
-__global__ void __launch_bounds__(128) k_ccl_seams_h(const uint8_t* __restrict__ masks, int* __restrict__ labels, int H, int W,
-                                                      int vec_ok) {
-  const int b = blockIdx.z;
-  const uint8_t* im = masks + (size_t)b * H * W;
+__global__ void __launch_bounds__(128) k_ccl_seam_rows(int* __restrict__ labels, const uint32_t* __restrict__ bits_all,
+                                                        const int* __restrict__ head_all, int H, int W, int wpr) {
+  const int b = blockIdx.z, y = (blockIdx.y + 1) * CS_TH, wc = blockIdx.x * 128 + threadIdx.x;
+  if (y >= H || wc >= wpr) return;
   int* L = labels + (size_t)b * H * W;
-  const int y = (blockIdx.y + 1) * CT_H;
-  const int x0 = (blockIdx.x * 128 + threadIdx.x) * 32;
-  if (y >= H || x0 >= W) return;
-  const uint32_t cur = load_word(im, H, W, y, x0, vec_ok != 0);
-  if (!cur) return;
-  const uint32_t up = load_word(im, H, W, y - 1, x0, vec_ok != 0);
-  const int rowc = y * W + x0, rowu = (y - 1) * W + x0;
+  const uint32_t* bits = bits_all + (size_t)b * H * wpr;
+  const int* head = head_all + (size_t)b * H * wpr;
+  const uint32_t wv = bits[(size_t)y * wpr + wc];
+  if (!wv) return;
+  const uint32_t uv = bits[(size_t)(y - 1) * wpr + wc];
   bool ul = false, ur = false;
   if (CONN == 8) {
-    ul = x0 > 0 && im[rowu - 1] != 0;
-    ur = x0 + 32 < W && im[rowu + 32] != 0;
+    ul = wc > 0 && (bits[(size_t)(y - 1) * wpr + wc - 1] >> 31);
+    ur = wc + 1 < wpr && (bits[(size_t)(y - 1) * wpr + wc + 1] & 1u);
   }
-  if (!up && !ul && !ur) return;
-  uint32_t rest = cur;
-  while (rest) {
-    const int st = __ffs(rest) - 1;
-    const int len = run_len(rest, st);
+  if (!uv && !ul && !ur) return;
+  for (uint32_t s = wv & ~(wv << 1); s; s &= s - 1) {
+    const int st = __ffs(s) - 1;
+    const int len = run_len(wv, st);
     const uint32_t rm = run_mask(st, len);
-    rest &= ~rm;
     uint32_t aw = rm;
     if (CONN == 8) aw |= (rm << 1) | (rm >> 1);
-    uint32_t cand = aw & up;
-    while (cand) {
-      const int us = __ffs(cand) - 1;
-      const int ust = run_start(up, us);
-      cand &= ~run_mask(ust, run_len(up, ust));
-      gunion(L, rowc + st, rowu + ust);
+    uint32_t ov = aw & uv;
+    const bool dl = CONN == 8 && (rm & 1u) && ul, dr = CONN == 8 && (rm >> 31) && ur;
+    if (!ov && !dl && !dr) continue;
+    const int me = cs_start_of(bits, head, W, wpr, y, wc, st);
+    while (ov) {
+      const int u = __ffs(ov) - 1;
+      const int us = run_start(uv, u);
+      ov &= ~run_mask(us, run_len(uv, us));
+      gunion_roots(L, me, cs_start_of(bits, head, W, wpr, y - 1, wc, us));
     }
-    if (CONN == 8) {
-      if (st == 0 && ul) gunion(L, rowc, rowu - 1);
-      if (st + len == 32 && ur) gunion(L, rowc + 31, rowu + 32);
-    }
+    if (dl) gunion_roots(L, me, cs_start_of(bits, head, W, wpr, y - 1, wc - 1, 31));
+    if (dr) gunion_roots(L, me, cs_start_of(bits, head, W, wpr, y - 1, wc + 1, 0));
   }
 }
 
+// pass B, vertical seams: columns x = k 1024 against column x - 1, one row per thread
 template <int CONN>
-__global__ void __launch_bounds__(256) k_ccl_seams_v(const uint8_t* __restrict__ masks, int* __restrict__ labels, int H, int W) {
+__global__ void __launch_bounds__(256) k_ccl_seam_cols(int* __restrict__ labels, const uint32_t* __restrict__ bits_all,
+                                                        const int* __restrict__ head_all, int H, int W, int wpr) {
   const int b = blockIdx.z;
-  const uint8_t* im = masks + (size_t)b * H * W;
-  int* L = labels + (size_t)b * H * W;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int n_seams = (W - 1) / CT_W;
+  const int n_seams = (W - 1) / 1024;
   if (t >= (long long)n_seams * H) return;
-  const int x = (int)(t / H + 1) * CT_W, y = (int)(t % H);
-  const int p = y * W + x;
-  if (!im[p]) return;
-  if (im[p - 1]) {
-    gunion(L, p, p - 1);
-  } else if (CONN == 8) {
-    if (y > 0 && im[p - W - 1]) gunion(L, p, p - W - 1);
-    if (y + 1 < H && im[p + W - 1]) gunion(L, p, p + W - 1);
+  const int wc = (int)(t / H + 1) * 32, y = (int)(t % H);
+  int* L = labels + (size_t)b * H * W;
+  const uint32_t* bits = bits_all + (size_t)b * H * wpr;
+  const int* head = head_all + (size_t)b * H * wpr;
+  const bool cur = bits[(size_t)y * wpr + wc] & 1u, left = bits[(size_t)y * wpr + wc - 1] >> 31;
+  if (cur && left) {
+    gunion_roots(L, cs_start_of(bits, head, W, wpr, y, wc, 0), cs_start_of(bits, head, W, wpr, y, wc - 1, 31));
+  } else if (CONN == 8 && cur) {
+    const int me = cs_start_of(bits, head, W, wpr, y, wc, 0);
+    if (y > 0 && (bits[(size_t)(y - 1) * wpr + wc - 1] >> 31)) gunion_roots(L, me, cs_start_of(bits, head, W, wpr, y - 1, wc - 1, 31));
+    if (y + 1 < H && (bits[(size_t)(y + 1) * wpr + wc - 1] >> 31)) gunion_roots(L, me, cs_start_of(bits, head, W, wpr, y + 1, wc - 1, 31));
+  } else if (CONN == 8 && left) {
+    const int me = cs_start_of(bits, head, W, wpr, y, wc - 1, 31);
+    if (y > 0 && (bits[(size_t)(y - 1) * wpr + wc] & 1u)) gunion_roots(L, me, cs_start_of(bits, head, W, wpr, y - 1, wc, 0));
+    if (y + 1 < H && (bits[(size_t)(y + 1) * wpr + wc] & 1u)) gunion_roots(L, me, cs_start_of(bits, head, W, wpr, y + 1, wc, 0));
   }
 }
 
-// pass C: same thread <-> word mapping as pass A.  Only words flagged dirty are revisited.  The label pass A wrote at
-// the LAST pixel of a sub-run names the run's tile-local root (only root pixels — always the first pixel of a run — are
-// modified by the seam unions); if that root was merged into another component, the whole run is rewritten.
-// With dirty == nullptr every word is visited (and every root is counted here).
-__global__ void __launch_bounds__(CT_THREADS) k_ccl_tile_fixup(const uint8_t* __restrict__ masks, int* __restrict__ labels, int H,
-                                                                int W, int vec_ok, const uint32_t* __restrict__ dirty,
-                                                                int* __restrict__ ncomp, int* __restrict__ partial) {
-  const int b = blockIdx.z, x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
-  const int lane = threadIdx.x & 31;
-  uint32_t dmask = 0xffffffffu;
-  if (dirty)
-    dmask = __ldg(dirty + (((size_t)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (CT_THREADS / 32) + (threadIdx.x >> 5));
-  if (dmask == 0u) return;  // whole warp: nothing in its 8 rows can have changed
-  const uint8_t* im = masks + (size_t)b * H * W;
+// pass B', flatten: a vertical structure that crosses k tile seams leaves a chain root_k -> root_k-1 -> ... -> root_0 (union by
+// minimum index links every tile's root under the one above it), and pass C would walk it from every pixel.  All those
+// roots are runs of the FIRST row of a tile, so re-pointing the run starts of the seam rows at their final root (3 % of the
+// rows, path-halving finds) bounds every later chase by a few hops.
+__global__ void __launch_bounds__(128) k_ccl_flatten_rows(int* __restrict__ labels, const uint32_t* __restrict__ bits_all, int H, int W,
+                                                          int wpr) {
+  const int b = blockIdx.z, y = (blockIdx.y + 1) * CS_TH, wc = blockIdx.x * 128 + threadIdx.x;
+  if (y >= H || wc >= wpr) return;
   int* L = labels + (size_t)b * H * W;
-  const int r = threadIdx.x % CT_H, c = threadIdx.x / CT_H;
-  const int y = y0 + r, x = x0 + c * 32;
+  const uint32_t* bits = bits_all + (size_t)b * H * wpr;
+  const uint32_t wv = bits[(size_t)y * wpr + wc];
+  uint32_t starts = wv & ~(wv << 1);
+  if ((wv & 1u) && (wc & 31) && (bits[(size_t)y * wpr + wc - 1] >> 31)) starts &= ~1u;  // continued run: no entry of its own
+  for (; starts; starts &= starts - 1) {
+    const int s = y * W + wc * 32 + __ffs(starts) - 1;
+    const int r = gfind_halve(L, s);
+    if (r != s) atomicMin(L + s, r + 1);
+  }
+}
+
+// pass C: the label image is written ONCE.  One warp per row segment of 1024 pixels (= one tile row), lane = one 32-pixel word:
+// the lane resolves the label of its word's run (run start from the bit plane, or head[] when the run entered from the left;
+// root by pointer chasing), then the warp writes the 4 KB of labels cooperatively — per 16-byte store a lane fetches the word
+// and the label of the word it is writing by shuffle, so a store instruction covers 512 contiguous bytes.  Words that hold
+// more than one run (noise, text: ~1 % of the words) are written by their own lane afterwards.  (A thread-per-4-pixels
+// version needed 1.1 instructions per pixel and was bound by them: 0.70 ms for 16 x 4096^2; this one needs ~0.15.)
+// The parent entries sit at run-start pixels and this pass overwrites them with root + 1 — still a valid parent pointer for
+// any thread that chases through them concurrently.
+constexpr int CW_WARPS = 8;  // warps per CTA
+constexpr int CW_R = 4;      // rows per warp: their pointer chases are independent and run side by side
+
+// rare path of pass C: this lane's word holds several runs — resolve each and write the lane's own 32 pixels
+__device__ __noinline__ int ccl_write_multi(int* L, int* dst, uint32_t word, int base, int x, int W, int first_lab, int vec_ok) {
   int n_roots = 0;
-  if ((dmask >> lane) & 1u) {
-    const uint32_t w = load_word(im, H, W, y, x, vec_ok != 0);
-    for (uint32_t s = w & ~(w << 1); s; s &= s - 1) {
-      const int i = __ffs(s) - 1;
-      const int len = run_len(w, i);
-      const int px = y * W + x + i;
-      const int ref = __ldcg(L + px + len - 1);  // tile-local root + 1 (a run's last pixel is never a root unless len == 1)
-      const int f = gfind(L, ref - 1);
-      if (ref != f + 1) {
-        // rewrite the run: 16-byte stores over its aligned middle part (a 16-pixel wire crossing is 4 stores, not 16)
-        const int v = f + 1;
-        int k = 0;
-        if (vec_ok) {
-          for (; k < len && ((px + k) & 3); k++) L[px + k] = v;
-          for (; k + 4 <= len; k += 4) *(int4*)(L + px + k) = make_int4(v, v, v, v);
-        }
-        for (; k < len; k++) L[px + k] = v;
-      }
-      // this run starts at the first pixel of its component (pass A counted the roots of the words it left clean)
-      n_roots += (f == px);
+  bool first = true;
+  for (uint32_t s = word & ~(word << 1); s; s &= s - 1) {
+    const int st = __ffs(s) - 1;
+    int l2 = first_lab;
+    if (!first) {  // a further run always starts inside the word: it has its own parent entry
+      const int root = gfind(L, base + st);
+      l2 = root + 1;
+      n_roots += (root == base + st);
     }
+    first = false;
+    const int len = run_len(word, st);
+    for (int k = st; k < st + len; k++)
+      if (x + k < W) dst[k] = l2;
+  }
+  // zeros between the runs
+  for (uint32_t z = ~word; z; z &= z - 1) {
+    const int k = __ffs(z) - 1;
+    if (x + k < W) dst[k] = 0;
+  }
+  (void)vec_ok;
+  return n_roots;
+}
+
+__global__ void __launch_bounds__(CW_WARPS * 32) k_ccl_write(int* __restrict__ labels, const uint32_t* __restrict__ bits_all,
+                                                           const int* __restrict__ head_all, int H, int W, int wpr, int vec_ok,
+                                                           int* __restrict__ ncomp, int* __restrict__ partial) {
+  const int b = blockIdx.z, y0 = (blockIdx.y * CW_WARPS + (threadIdx.x >> 5)) * CW_R, c = threadIdx.x & 31;
+  if (y0 >= H) return;
+  int* L = labels + (size_t)b * H * W;
+  const uint32_t* bits = bits_all + (size_t)b * H * wpr;
+  const int* head = head_all + (size_t)b * H * wpr;
+  const int wc = blockIdx.x * 32 + c;
+  uint32_t word[CW_R];
+  int cur[CW_R], par[CW_R], start[CW_R];
+  bool cont[CW_R];
+#pragma unroll
+  for (int i = 0; i < CW_R; i++) word[i] = (wc < wpr && y0 + i < H) ? bits[(size_t)(y0 + i) * wpr + wc] : 0u;
+#pragma unroll
+  for (int i = 0; i < CW_R; i++) {
+    uint32_t wl = __shfl_up_sync(0xffffffffu, word[i], 1);
+    if (c == 0) wl = 0u;
+    cont[i] = (word[i] & 1u) && (wl >> 31);  // the first run of my word entered from the left
+    start[i] = -1;
+    if (word[i]) start[i] = cont[i] ? head[(size_t)(y0 + i) * wpr + wc] : (y0 + i) * W + wc * 32 + __ffs(word[i]) - 1;
+  }
+#pragma unroll
+  for (int i = 0; i < CW_R; i++) {
+    cur[i] = start[i];
+    par[i] = start[i] >= 0 ? __ldcg(L + start[i]) - 1 : -1;
+  }
+  for (bool moving = true; moving;) {  // all chains advance together
+    moving = false;
+#pragma unroll
+    for (int i = 0; i < CW_R; i++)
+      if (par[i] != cur[i]) {
+        cur[i] = par[i];
+        par[i] = __ldcg(L + cur[i]) - 1;
+        moving = true;
+      }
+  }
+  int n_roots = 0;
+  const int sub = c >> 3, sh = (c & 7) * 4;
+#pragma unroll
+  for (int i = 0; i < CW_R; i++) {
+    const int y = y0 + i;
+    if (y >= H) break;
+    const int lab = cur[i] + 1;  // 0 for an empty word
+    if (word[i] && !cont[i]) n_roots += (cur[i] == start[i]);
+    const uint32_t starts = word[i] & ~(word[i] << 1);
+    const bool multi = (starts & (starts - 1)) != 0u;
+    const uint32_t mm = __ballot_sync(0xffffffffu, multi);
+    int* row = L + (size_t)y * W + blockIdx.x * 1024;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int src = 4 * q + sub;
+      const uint32_t wsrc = __shfl_sync(0xffffffffu, word[i], src);
+      const int lsrc = __shfl_sync(0xffffffffu, lab, src);
+      const uint32_t nib = (wsrc >> sh) & 0xFu;
+      const int x = blockIdx.x * 1024 + src * 32 + sh;
+      if (((mm >> src) & 1u) || x >= W) continue;
+      const int4 o = make_int4((nib & 1u) ? lsrc : 0, (nib & 2u) ? lsrc : 0, (nib & 4u) ? lsrc : 0, (nib & 8u) ? lsrc : 0);
+      int* dst = row + src * 32 + sh;
+      if (vec_ok && x + 4 <= W) {
+        *(int4*)dst = o;
+      } else {
+        const int v[4] = {o.x, o.y, o.z, o.w};
+        for (int k = 0; k < 4; k++)
+          if (x + k < W) dst[k] = v[k];
+      }
+    }
+    if (multi) n_roots += ccl_write_multi(L, row + c * 32, word[i], y * W + wc * 32, wc * 32, W, lab, vec_ok);
   }
   if (ncomp) {
     for (int o = 16; o; o >>= 1) n_roots += __shfl_xor_sync(0xffffffffu, n_roots, o);
-    if (lane == 0 && n_roots) {
-      if (partial) atomicAdd(partial + ((size_t)b * 32 + ((blockIdx.x + blockIdx.y + 7) & 31)) * 32, n_roots);
+    if (c == 0 && n_roots) {
+      if (partial) atomicAdd(partial + ((size_t)b * 32 + ((blockIdx.x + blockIdx.y) & 31)) * 32, n_roots);
       else atomicAdd(ncomp + b, n_roots);
     }
   }
@@ -429,41 +461,36 @@ __global__ void k_ccl_count_finish(const int* __restrict__ partial, int* __restr
 
 using namespace cvb;
 
+static size_t ccl_partial_bytes(int B) { return (size_t)(B > 0 ? B : 1) * 32 * 32 * sizeof(int); }
+static size_t ccl_plane_bytes(int B, int H, int W) { return (((size_t)B * H * ((W + 31) / 32) * 4) + 255) & ~(size_t)255; }
+
 template <int CONN>
 static int ccl_run(const uint8_t* masks, int B, int H, int W, int32_t* labels, int32_t* n_components, int* partial,
-                   uint32_t* dirty, cudaStream_t st) {
+                   uint32_t* bits, int* head, cudaStream_t st) {
   const int vec_ok = (W % 16 == 0) && (((uintptr_t)masks & 15) == 0) && (((uintptr_t)labels & 15) == 0);
-  dim3 tg((W + CT_W - 1) / CT_W, (H + CT_H - 1) / CT_H, B);
+  const int wpr = (W + 31) / 32;
   const double px = (double)B * H * W;
-  cvb_next_work(5.0 * px);
-  static std::atomic<unsigned long long> carveout_set{0};
-  if (cvb_once_per_device(carveout_set)) {
-    // 8 resident tiles x ~19 KB: ask for the large shared-memory split (the default heuristic leaves room for fewer)
-    CVB_CHECK(cudaFuncSetAttribute(k_ccl_tile_label<CONN>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                   cudaSharedmemCarveoutMaxShared));
-  }
-  CVB_LAUNCH((k_ccl_tile_label<CONN>), tg, dim3(CT_THREADS), 0, st, masks, labels, H, W, vec_ok, dirty, n_components, partial);
-  const int seams_h = (H - 1) / CT_H, seams_v = (W - 1) / CT_W;
-  const int words = (W + 31) / 32;
-  const long long vpx = (long long)seams_v * H;
+  cvb_next_work(1.0 * px);
+  CVB_LAUNCH((k_ccl_scan<CONN>), dim3((W + 1023) / 1024, (H + CS_TH * CS_WARPS - 1) / (CS_TH * CS_WARPS), B), dim3(CS_WARPS * 32), 0,
+             st, masks, labels, bits, head, H, W, wpr, vec_ok);
+  const int seams_h = (H - 1) / CS_TH;
+  const long long vpx = (long long)((W - 1) / 1024) * H;
   if (seams_h > 0)
-    CVB_LAUNCH((k_ccl_seams_h<CONN>), dim3((words + 127) / 128, seams_h, B), dim3(128), 0, st, masks, labels, H, W, vec_ok);
+    CVB_LAUNCH((k_ccl_seam_rows<CONN>), dim3((wpr + 127) / 128, seams_h, B), dim3(128), 0, st, labels, bits, head, H, W, wpr);
   if (vpx > 0)
-    CVB_LAUNCH((k_ccl_seams_v<CONN>), dim3((unsigned)((vpx + 255) / 256), 1, B), dim3(256), 0, st, masks, labels, H, W);
-  CVB_LAUNCH(k_ccl_tile_fixup, tg, dim3(CT_THREADS), 0, st, masks, labels, H, W, vec_ok, dirty, n_components, partial);
+    CVB_LAUNCH((k_ccl_seam_cols<CONN>), dim3((unsigned)((vpx + 255) / 256), 1, B), dim3(256), 0, st, labels, bits, head, H, W, wpr);
+  if (seams_h > 0)
+    CVB_LAUNCH(k_ccl_flatten_rows, dim3((wpr + 127) / 128, seams_h, B), dim3(128), 0, st, labels, bits, H, W, wpr);
+  cvb_next_work(4.0 * px);
+  CVB_LAUNCH(k_ccl_write, dim3((W + 1023) / 1024, (H + CW_WARPS * CW_R - 1) / (CW_WARPS * CW_R), B), dim3(CW_WARPS * 32), 0, st, labels, bits, head, H, W, wpr, vec_ok, n_components,
+             partial);
   if (n_components && partial) CVB_LAUNCH(k_ccl_count_finish, dim3(B), dim3(32), 0, st, partial, n_components, B);
   return CV_OK;
 }
 
-static size_t ccl_dirty_bytes(int B, int H, int W) {
-  return (size_t)B * ((W + CT_W - 1) / CT_W) * ((H + CT_H - 1) / CT_H) * (CT_THREADS / 32) * sizeof(uint32_t);
-}
-static size_t ccl_partial_bytes(int B) { return (size_t)(B > 0 ? B : 1) * 32 * 32 * sizeof(int); }
-
 extern "C" size_t cv_ccl_workspace_bytes(int B, int H, int W) {
-  // labels are resolved in place in the caller's label image; the workspace holds the spread component counters and
-  // the per-tile dirty bitmap
-  return ccl_partial_bytes(B) + ccl_dirty_bytes(B, H, W);
+  // spread component counters | bit plane (1 bit / pixel) | head[] (one int per 32-pixel word)
+  return ccl_partial_bytes(B) + 2 * ccl_plane_bytes(B, H, W);
 }
 
 extern "C" int cv_ccl_label(const uint8_t* masks, int B, int H, int W, int connectivity, int32_t* labels,
@@ -473,16 +500,17 @@ extern "C" int cv_ccl_label(const uint8_t* masks, int B, int H, int W, int conne
     return cvb_fail(CV_ERR_INVALID, "cv_ccl_label: null pointer or non-positive size");
   if (connectivity != 4 && connectivity != 8) return cvb_fail(CV_ERR_INVALID, "cv_ccl_label: connectivity must be 4 or 8");
   if ((long long)H * W >= (1ll << 31) - 2) return cvb_fail(CV_ERR_INVALID, "cv_ccl_label: image too large for int32 labels");
-  if (B > 65535) return cvb_fail(CV_ERR_INVALID, "cv_ccl_label: batch too large");
+  if (B > 65535 || H > 65535) return cvb_fail(CV_ERR_INVALID, "cv_ccl_label: batch or height too large");
+  if (!workspace || workspace_bytes < cv_ccl_workspace_bytes(B, H, W))
+    return cvb_fail(CV_ERR_INVALID, "cv_ccl_label: workspace of cv_ccl_workspace_bytes(B, H, W) bytes required");
   cudaStream_t st = (cudaStream_t)stream_;
-  int* partial = nullptr;
-  uint32_t* dirty = nullptr;
-  if (workspace && workspace_bytes >= cv_ccl_workspace_bytes(B, H, W)) {
-    partial = (int*)workspace;
-    dirty = (uint32_t*)((uint8_t*)workspace + ccl_partial_bytes(B));
-    if (n_components) CVB_CHECK(cudaMemsetAsync(partial, 0, ccl_partial_bytes(B), st));
+  int* partial = (int*)workspace;
+  uint32_t* bits = (uint32_t*)((uint8_t*)workspace + ccl_partial_bytes(B));
+  int* head = (int*)((uint8_t*)bits + ccl_plane_bytes(B, H, W));
+  if (n_components) {
+    CVB_CHECK(cudaMemsetAsync(partial, 0, ccl_partial_bytes(B), st));
+    CVB_CHECK(cudaMemsetAsync(n_components, 0, (size_t)B * 4, st));
   }
-  if (n_components) CVB_CHECK(cudaMemsetAsync(n_components, 0, (size_t)B * 4, st));
-  return connectivity == 8 ? ccl_run<8>(masks, B, H, W, labels, n_components, partial, dirty, st)
-                           : ccl_run<4>(masks, B, H, W, labels, n_components, partial, dirty, st);
+  return connectivity == 8 ? ccl_run<8>(masks, B, H, W, labels, n_components, partial, bits, head, st)
+                           : ccl_run<4>(masks, B, H, W, labels, n_components, partial, bits, head, st);
 }

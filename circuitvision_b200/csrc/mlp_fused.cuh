@@ -23,6 +23,7 @@ struct MlpFusedArgs {
   const float* b2 = nullptr;           // [C]
   int fp16 = 0;                        // operand format: 0 bf16, 1 IEEE half
   unsigned int* sat_counter = nullptr; // debug: counts hidden activations that saturated in the fp16 conversion
+  unsigned long long* trace = nullptr; // debug: CTA 0 appends (event id << 48 | %globaltimer ns) records, trace[0] = count
 };
 
 // true when a fused instantiation exists for this width (the caller falls back to LN + fc1 + fc2 GEMMs otherwise)

@@ -9,7 +9,9 @@ every entry point raises `CvError`.
 from __future__ import annotations
 
 import ctypes as C
+from collections import defaultdict
 from copy import deepcopy
+from operator import itemgetter
 
 import numpy as np
 import torch
@@ -70,15 +72,19 @@ def _class_flags(cls):
     return v
 
 
+_ATOMIC = (str, int, float, bool, type(None), np.integer, np.floating)
+_XYXY = itemgetter("xmin", "ymin", "xmax", "ymax")
+
+
 class ResizedBoxes:
     """The reference's `processing_bboxes_resized` (:807, resize_bboxes :461-477) of one image, materialised lazily: the
     integer coordinates of every box are computed vectorised at pack time, the dict copy of a box is only built when a
     node actually references it (a handful per image)."""
 
-    __slots__ = ("boxes", "xyxy", "_cache")
+    __slots__ = ("boxes", "xyxy", "_cache", "_flat")
 
     def __init__(self, boxes, xyxy):
-        self.boxes, self.xyxy, self._cache = boxes, xyxy, {}
+        self.boxes, self.xyxy, self._cache, self._flat = boxes, xyxy, {}, {}
 
     def __len__(self):
         return len(self.boxes)
@@ -87,9 +93,16 @@ class ResizedBoxes:
         r = self._cache.get(j)
         if r is None:
             r = self.boxes[j].copy()
-            r["xmin"], r["ymin"], r["xmax"], r["ymax"] = (int(v) for v in self.xyxy[j])
+            r["xmin"], r["ymin"], r["xmax"], r["ymax"] = self.xyxy[j].tolist()
             self._cache[j] = r
+            # deepcopy(bbox) of :1422 degenerates to dict.copy() for the flat scalar dicts YOLO post-processing builds
+            self._flat[j] = all(isinstance(v, _ATOMIC) for v in r.values())
         return r
+
+    def copy_of(self, j):
+        """An independent copy of resized box j (the reference attaches deepcopy(bbox) per (node, uid), :1422)."""
+        r = self[j]
+        return r.copy() if self._flat[j] else deepcopy(r)
 
     def __iter__(self):
         return (self[j] for j in range(len(self.boxes)))
@@ -109,41 +122,36 @@ def pack_boxes(boxes_list, H: int, W: int):
     resized_all = []
     if total:
         flat = [b for boxes in boxes_list for b in boxes]
-        xy = np.array([(b["xmin"], b["ymin"], b["xmax"], b["ymax"]) for b in flat], dtype=np.float64).reshape(total, 4)
+        xy = np.array([_XYXY(b) for b in flat], dtype=np.float64).reshape(total, 4)
         ixy = np.trunc(xy).astype(np.int64)
         rxy = np.trunc(xy * np.array([sx, sy, sx, sy])).astype(np.int64)
         for k, f in enumerate(("xmin", "ymin", "xmax", "ymax")):
             rec[f][:total] = ixy[:, k]
             rec["r" + f][:total] = rxy[:, k]
-        ft = np.array([_class_flags(b["class"]) for b in flat], dtype=np.int32).reshape(total, 2)
+        cache = _CLASS_CACHE
+        try:
+            ft = [cache[b["class"]] for b in flat]
+        except KeyError:
+            ft = [_class_flags(b["class"]) for b in flat]
+        ft = np.array(ft, dtype=np.int32).reshape(total, 2)
         rec["flags"][:total], rec["thresh"][:total] = ft[:, 0], ft[:, 1]
+        groups = []
         k = 0
         for boxes, n in zip(boxes_list, counts):
             r = rxy[k:k + n]
             first = {}
-            grp = rec["uid_group"][k:k + n]
-            for j, b in enumerate(boxes):
-                u = b.get("persistent_uid")
-                if u is None:  # identity used by the reference's de-duplication (:1424-1436), on RESIZED coordinates
-                    u = (b["class"], int(r[j, 0]), int(r[j, 1]), int(r[j, 2]), int(r[j, 3]))
-                grp[j] = first.setdefault(u, j)
+            sd = first.setdefault
+            uids = [b.get("persistent_uid") for b in boxes]
+            if None in uids:  # identity used by the reference's de-duplication (:1424-1436), on RESIZED coordinates
+                uids = [u if u is not None else (b["class"],) + tuple(r[j].tolist()) for j, (u, b) in enumerate(zip(uids, boxes))]
+            groups.extend([sd(u, j) for j, u in enumerate(uids)])
             resized_all.append(ResizedBoxes(boxes, r))
             k += n
+        rec["uid_group"][:total] = groups
     else:
         resized_all = [ResizedBoxes(b, np.zeros((0, 4), np.int64)) for b in boxes_list]
     max_per = max(counts, default=0)
     return rec[:total] if total else rec[:0], offs, resized_all, max_per
-
-
-_ATOMIC = (str, int, float, bool, type(None), np.integer, np.floating)
-
-
-def _copy_box(b: dict) -> dict:
-    """deepcopy(bbox) of :1422 for the dicts YOLO post-processing builds (flat scalars); nested values fall back to deepcopy."""
-    for v in b.values():
-        if not isinstance(v, _ATOMIC):
-            return deepcopy(b)
-    return b.copy()
 
 
 class NodeBatchResult:
@@ -196,17 +204,21 @@ class NodeBatchResult:
         if res["status"]:
             raise CvError(f"node analysis of image {b} overflowed a capacity (status {int(res['status'])})")
         rb = self.resized_boxes[b]
-        comps = {}
+        comps = defaultdict(list)
+        cache, flat = rb._cache, rb._flat
         for ci, bi in zip(prs["contour"].tolist(), prs["box"].tolist()):
-            comps.setdefault(ci, []).append(_copy_box(rb[bi]))  # :1422
+            r = cache.get(bi)
+            if r is None:
+                r = rb[bi]
+            comps[ci].append(r.copy() if flat[bi] else deepcopy(r))  # :1422
         out = []
         new_id = con["new_id"]
         keep = np.nonzero(new_id >= 0)[0]
-        offs, nv = con["offset"], con["nverts"]
-        for k in keep[np.argsort(new_id[keep], kind="stable")].tolist():
-            o = int(offs[k])
-            poly = np.array(pts[o:o + int(nv[k])], dtype=np.int32).reshape(-1, 1, 2)
-            out.append({"id": int(new_id[k]), "components": comps.get(k, []), "contour": poly})
+        order = keep[np.argsort(new_id[keep], kind="stable")]
+        offs, nv = con["offset"][order].tolist(), con["nverts"][order].tolist()
+        pts3 = pts.reshape(-1, 1, 2)
+        for k, nid, o, n in zip(order.tolist(), new_id[order].tolist(), offs, nv):
+            out.append({"id": nid, "components": comps.get(k, []), "contour": pts3[o:o + n].astype(np.int32, copy=True)})
         return out
 
     def connection_points(self, b: int):
@@ -263,11 +275,24 @@ class NodeAnalyzer:
             self._ws = torch.empty(need, dtype=u8, device=dev)
         return self._bufs
 
-    def upload_boxes(self, boxes_list, H, W):
+    def upload_boxes(self, boxes_list, H, W, pinned=None):
+        """Pack + upload the box records on torch's current stream.  `pinned` = (uint8 [cap,48], int32 [B+1]) pinned staging
+        tensors makes the copy asynchronous (pipelines); without it the pageable copy blocks the host until it is done."""
         rec, offs, rboxes, max_per = pack_boxes(boxes_list, H, W)
         dev = self.device
+        raw = rec.view(np.uint8).reshape(-1, BOX_DTYPE.itemsize)
+        if pinned is not None and len(rec) <= pinned[0].shape[0] and len(offs) <= pinned[1].shape[0]:
+            h_rec, h_off = pinned
+            n = max(len(rec), 1)
+            h_rec[:len(rec)].numpy()[...] = raw
+            h_off[:len(offs)].numpy()[...] = offs
+            d_rec = torch.empty((n, BOX_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+            d_rec.copy_(h_rec[:n], non_blocking=True)
+            d_off = torch.empty((len(offs),), dtype=torch.int32, device=dev)
+            d_off.copy_(h_off[:len(offs)], non_blocking=True)
+            return d_rec, d_off, rboxes, max_per
         if len(rec):
-            d_rec = torch.from_numpy(rec.view(np.uint8).reshape(-1, BOX_DTYPE.itemsize).copy()).to(dev)
+            d_rec = torch.from_numpy(raw.copy()).to(dev)
         else:
             d_rec = torch.zeros((1, BOX_DTYPE.itemsize), dtype=torch.uint8, device=dev)
         d_off = torch.from_numpy(offs).to(dev)

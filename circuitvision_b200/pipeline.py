@@ -44,6 +44,9 @@ class _TableStager:
         self.h_blob = torch.empty(self.cap, dtype=torch.uint8, pin_memory=True)
         self.h_results = torch.empty((B, RESULT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
         self.ev_header = torch.cuda.Event()
+        # the blob is fetched on a stream of its own: the copy-out stream already holds the NEXT batch's image copies, which
+        # wait for that batch's compute — synchronising on it would serialise the pipeline
+        self.s_fetch = torch.cuda.Stream(dev)
         self.lib = _lib.load()
 
     def pack(self, r: NodeBatchResult, stream):
@@ -56,8 +59,9 @@ class _TableStager:
         self.h_results.copy_(r.results, non_blocking=True)
         self.ev_header.record(stream)
 
-    def fetch(self, r: NodeBatchResult, stream):
+    def fetch(self, r: NodeBatchResult, stream=None):
         """Host side: wait for the header, copy exactly the used bytes of the blob; returns the host-table dict."""
+        stream = self.s_fetch
         self.ev_header.synchronize()
         total = int(self.h_header[self.B, 0])
         res = self.h_results.numpy().view(RESULT_DTYPE).reshape(self.B)
@@ -80,6 +84,7 @@ class _Slot:
         pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
         self.tables = _TableStager(dev, B, self.na.caps)
         self.h_extents = pin((B, 4), torch.int32)
+        self.h_boxes = (pin((B * 256, 48), torch.uint8), pin((B + 1,), torch.int32))  # async box upload staging
         self.h_masks = pin((B, S, S), torch.uint8) if want_images else None
         self.h_emptied = pin((B, S, S), torch.uint8) if want_images else None
         self.h_enhanced = None  # allocated on first use (width depends on the aspect ratio)
@@ -152,6 +157,7 @@ class CropPipeline:
         with torch.cuda.device(self.dev):
             with torch.cuda.stream(self.s_in):
                 s.d_rgb.copy_(host_crops, non_blocking=True)
+                d_rec, d_off, rboxes, max_per = s.na.upload_boxes(boxes_list, self.S, self.S, pinned=s.h_boxes)
                 s.ev_in.record(self.s_in)
             with torch.cuda.stream(self.s_compute):
                 self.s_compute.wait_event(s.ev_in)
@@ -159,10 +165,11 @@ class CropPipeline:
                 ext = self.model.last_extents
                 s.ev_mask.record(self.s_compute)
             with torch.cuda.stream(self.s_nodes):
-                d_rec, d_off, rboxes, max_per = s.na.upload_boxes(boxes_list, self.S, self.S)
-                self.s_nodes.wait_event(s.ev_mask)
+                self.s_nodes.wait_event(s.ev_mask)  # (follows ev_in on the compute stream: the boxes have landed too)
                 r = s.na.run(masks, d_rec, d_off, max_per, rboxes)
                 masks.record_stream(self.s_nodes)
+                d_rec.record_stream(self.s_nodes)
+                d_off.record_stream(self.s_nodes)
                 s.tables.pack(r, self.s_nodes)
                 s.launches = self.model.last_launches + r.launches + 2
                 s.ev_done.record(self.s_nodes)
@@ -213,6 +220,7 @@ class _MaskSlot:
         self.d_masks = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
         self.tables = _TableStager(dev, B, self.na.caps)
         pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
+        self.h_boxes = (pin((B * 1024, 48), torch.uint8), pin((B + 1,), torch.int32))  # async box upload staging
         self.h_emptied = pin((B, H, W), torch.uint8) if want_images else None
         self.h_enhanced = pin((B, RESIZED_HEIGHT, resized_width(H, W)), torch.uint8) if want_images else None
         self.ev_in, self.ev_done, self.ev_out = (torch.cuda.Event() for _ in range(3))
@@ -260,7 +268,7 @@ class MaskPipeline:
         with torch.cuda.device(self.dev):
             with torch.cuda.stream(self.s_in):
                 s.d_masks.copy_(host_masks, non_blocking=True)
-                d_rec, d_off, rboxes, max_per = s.na.upload_boxes(boxes_list, self.H, self.W)
+                d_rec, d_off, rboxes, max_per = s.na.upload_boxes(boxes_list, self.H, self.W, pinned=s.h_boxes)
                 s.ev_in.record(self.s_in)
             with torch.cuda.stream(self.s_compute):
                 self.s_compute.wait_event(s.ev_in)

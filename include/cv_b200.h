@@ -152,6 +152,10 @@ int cv_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int
 int cv_mlp_fused(float* X, int M, int C, const float* gamma, const float* beta, float eps, const void* W1, const float* b1,
                  const void* W2, const float* b2, int operand_fp16, void* stream);
 
+/* Debug: a zeroed device buffer of >= 4001 uint64 that the following cv_mlp_fused calls fill with the pipeline timeline of
+ * CTA 0 (record = (event * 4096 + index) << 44 | globaltimer ns; buffer[0] = number of records); NULL switches it off. */
+int cv_mlp_fused_set_trace(void* device_buffer);
+
 /* Block-diagonal flash attention on tcgen05 (head_dim 96): tokens are window-major; query row i (window i / Wq)
  * attends the Wkv keys of the same window.  Covers Hiera's windowed, Q-pooled (Wq = Wkv/4) and global
  * (Wq = Wkv = tokens per image) attention (sam2 package, called from sam2_infer.py:226).  q/k/v are bf16 matrices
