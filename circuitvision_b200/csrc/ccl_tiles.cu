@@ -123,8 +123,11 @@ __device__ __forceinline__ uint32_t load_word(const uint8_t* __restrict__ im, in
 // ================================================================================================
 constexpr int CS_TH = 32;        // rows per tile
 constexpr int CS_WARPS = 8;      // tiles (stacked vertically) per CTA
-constexpr int CS_LSTRIDE = 17;   // 16 slots + 1: lane stride coprime with the 32 banks
+constexpr int CS_LSTRIDE = 16;   // 16 slots per lane; the slot index is XOR-swizzled with the lane so that the 32 lanes hit 32 banks
+                                 // (4 KB per warp: 7 CTAs = 56 warps per SM, the whole 16 x 4096^2 problem in one wave)
 constexpr int CS_INF = 0x7FFFFFFF;
+
+__device__ __forceinline__ int cs_slot(int lane, int slot) { return lane * CS_LSTRIDE + (slot ^ ((lane >> 1) & 15)); }
 
 __device__ __forceinline__ void cs_combine(int* L, int& cd, int t) {
   if (cd == CS_INF) {
@@ -190,11 +193,11 @@ __global__ void __launch_bounds__(CS_WARPS * 32) k_ccl_scan(const uint8_t* __res
           const int u = __ffs(ov) - 1;
           const int us = run_start(up, u);
           ov &= ~run_mask(us, run_len(up, us));
-          cs_combine(L, cd, lp[c * CS_LSTRIDE + (us >> 1)]);
+          cs_combine(L, cd, lp[cs_slot(c, us >> 1)]);
         }
         if (CONN == 8) {
-          if ((rm & 1u) && (upl >> 31)) cs_combine(L, cd, lp[(c - 1) * CS_LSTRIDE + (run_start(upl, 31) >> 1)]);
-          if ((rm >> 31) && (upr & 1u)) cs_combine(L, cd, lp[(c + 1) * CS_LSTRIDE]);
+          if ((rm & 1u) && (upl >> 31)) cs_combine(L, cd, lp[cs_slot(c - 1, run_start(upl, 31) >> 1)]);
+          if ((rm >> 31) && (upr & 1u)) cs_combine(L, cd, lp[cs_slot(c + 1, 0)]);
         }
       }
       const bool is_head = st == 0 && cin, is_tail = (rm >> 31) && cout;
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(CS_WARPS * 32) k_ccl_scan(const uint8_t* __res
       } else {
         const int m = cd == CS_INF ? rowbase + st : cd;  // nothing touched: a root, named by its first pixel
         L[rowbase + st] = m + 1;
-        lc[c * CS_LSTRIDE + (st >> 1)] = m;
+        lc[cs_slot(c, st >> 1)] = m;
       }
     }
     // runs that span words: minimum over the portions, unions between portions that disagree
@@ -228,12 +231,12 @@ __global__ void __launch_bounds__(CS_WARPS * 32) k_ccl_scan(const uint8_t* __res
       my_m = tot == CS_INF ? my_start : tot;
       if (ct != CS_INF && ct != my_m) gunion_roots(L, ct, my_m);
       L[my_start] = my_m + 1;
-      lc[c * CS_LSTRIDE + (tail_st >> 1)] = my_m;
+      lc[cs_slot(c, tail_st >> 1)] = my_m;
     }
     const int mo = __shfl_sync(0xffffffffu, my_m, origin), so = __shfl_sync(0xffffffffu, my_start, origin);
     if (cin) {
       if (ch != CS_INF && ch != mo) gunion_roots(L, ch, mo);
-      lc[c * CS_LSTRIDE] = mo;
+      lc[cs_slot(c, 0)] = mo;
       head[(size_t)y * wpr + wc] = so;
     }
     __syncwarp();  // label slots and parent entries of this row are visible to every lane before the next row reads them
@@ -471,6 +474,9 @@ static int ccl_run(const uint8_t* masks, int B, int H, int W, int32_t* labels, i
   const int wpr = (W + 31) / 32;
   const double px = (double)B * H * W;
   cvb_next_work(1.0 * px);
+  static std::atomic<unsigned long long> carveout_set{0};
+  if (cvb_once_per_device(carveout_set))  // 7 CTAs x 32 KB of label slots per SM: ask for the large shared-memory split
+    CVB_CHECK(cudaFuncSetAttribute(k_ccl_scan<CONN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CVB_LAUNCH((k_ccl_scan<CONN>), dim3((W + 1023) / 1024, (H + CS_TH * CS_WARPS - 1) / (CS_TH * CS_WARPS), B), dim3(CS_WARPS * 32), 0,
              st, masks, labels, bits, head, H, W, wpr, vec_ok);
   const int seams_h = (H - 1) / CS_TH;
