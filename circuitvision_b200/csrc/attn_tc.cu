@@ -133,55 +133,58 @@ k_attn_global(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issuer: the whole warp runs the control flow (converged), one elected lane issues — inside an `if (lane == 0)`
+    // region every tcgen05.mma was wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~25 dependent instructions)
+    {
       const uint32_t idesc_qk = tc::idesc_bf16(ATT_BM, ATT_BN, false, false, p.fp16 != 0);
       const uint32_t idesc_pv = tc::idesc_bf16(ATT_BM, ATT_D, false, true, p.fp16 != 0);  // A = P (TMEM, K-major), B = V MN-major
-      auto issue_qk = [&](int g, int j) {
-        const uint32_t q_addr = tc::smem_u32(sQ + g * ATT_TILE_BYTES);
-        const uint32_t k_addr = tc::smem_u32(sK + (j & 1) * ATT_TILE_BYTES);
+      auto issue_qk = [&](int g, int j, uint64_t* also) {
+        const uint64_t dq = tc::desc_kmajor(tc::smem_u32(sQ + g * ATT_TILE_BYTES));
+        const uint64_t dk = tc::desc_kmajor(tc::smem_u32(sK + (j & 1) * ATT_TILE_BYTES));
+        if (tc::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < ATT_D / 16; k++) {
-          uint32_t off = (k >> 2) * (ATT_BM * 128) + (k & 3) * 32;
-          tc::mma_f16_ss(tmem_base + g * 128, tc::desc_kmajor(q_addr + off), tc::desc_kmajor(k_addr + off), idesc_qk,
-                         k > 0 ? 1u : 0u);
+          for (int k = 0; k < ATT_D / 16; k++) {
+            const uint32_t off = ((k >> 2) * (ATT_BM * 128) + (k & 3) * 32) >> 4;  // descriptor address units of 16 bytes
+            tc::mma_f16_ss(tmem_base + g * 128, dq + off, dk + off, idesc_qk, k > 0 ? 1u : 0u);
+          }
+          tc::mma_commit(&s_full[g]);
+          if (also) tc::mma_commit(also);
         }
-        tc::mma_commit(&s_full[g]);
+        __syncwarp();
       };
-      auto issue_pv = [&](int g, int j) {
-        const uint32_t v_addr = tc::smem_u32(sV + (j & 1) * ATT_TILE_BYTES);
+      auto issue_pv = [&](int g, int j, uint64_t* also) {
+        const uint64_t dv = tc::smem_desc_sw128(tc::smem_u32(sV + (j & 1) * ATT_TILE_BYTES), ATT_BN * 128, 1024);
+        if (tc::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < ATT_BN / 16; k++) {
-          // A: 16 keys = 8 packed columns of the P region; B: 16 key rows (2048 B) per k-step of the MN-major V tile
-          uint64_t b = tc::smem_desc_sw128(v_addr + k * 2048, ATT_BN * 128, 1024);
-          tc::mma_f16_ts(tmem_base + 256 + g * ATT_D, tmem_base + g * 128 + k * 8, b, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < ATT_BN / 16; k++)
+            // A: 16 keys = 8 packed columns of the P region; B: 16 key rows (2048 B) per k-step of the MN-major V tile
+            tc::mma_f16_ts(tmem_base + 256 + g * ATT_D, tmem_base + g * 128 + k * 8, dv + (k * 2048 >> 4), idesc_pv,
+                           (j > 0 || k > 0) ? 1u : 0u);
+          tc::mma_commit(&o_full[g]);
+          if (also) tc::mma_commit(also);
         }
-        tc::mma_commit(&o_full[g]);
+        __syncwarp();
       };
       tc::mbar_wait(q_full, 0);
       tc::mbar_wait(&k_full[0], 0);
       tc::tc_fence_after();
-      issue_qk(0, 0);
-      issue_qk(1, 0);
-      tc::mma_commit(&k_empty[0]);
+      issue_qk(0, 0, nullptr);
+      issue_qk(1, 0, &k_empty[0]);
       for (int j = 0; j < n_tiles; j++) {
         const bool more = j + 1 < n_tiles;
         tc::mbar_wait(&v_full[j & 1], (j >> 1) & 1);
         tc::mbar_wait(&p_full[0], j & 1);
         tc::tc_fence_after();
-        issue_pv(0, j);
+        issue_pv(0, j, nullptr);
         if (more) {
           tc::mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
           tc::tc_fence_after();
-          issue_qk(0, j + 1);
+          issue_qk(0, j + 1, nullptr);
         }
         tc::mbar_wait(&p_full[1], j & 1);
         tc::tc_fence_after();
-        issue_pv(1, j);
-        tc::mma_commit(&v_empty[j & 1]);
-        if (more) {
-          issue_qk(1, j + 1);
-          tc::mma_commit(&k_empty[(j + 1) & 1]);
-        }
+        issue_pv(1, j, &v_empty[j & 1]);
+        if (more) issue_qk(1, j + 1, &k_empty[(j + 1) & 1]);
       }
     }
   } else if (warp >= 4) {
@@ -432,8 +435,8 @@ k_attn_win(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUten
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer
-    if (lane == 0) {
+    // ===================== MMA issuer (converged warp, one elected lane issues: see k_attn_global)
+    {
       const uint32_t idesc_qk = tc::idesc_bf16(ATT_BM, ATT_BN, false, false, p.fp16 != 0);
       const uint32_t idesc_pv = tc::idesc_bf16(ATT_BM, ATT_D, false, true, p.fp16 != 0);
       uint32_t ring = 0, ring_uses = 0;
@@ -443,23 +446,25 @@ k_attn_win(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUten
         tc::tc_fence_after();
         return tc::smem_u32(sR + ring * ATT_TILE_BYTES);
       };
-      auto ring_release = [&]() {
-        tc::mma_commit(&r_empty[ring]);
+      auto ring_advance = [&]() {
         ring = (ring + 1) % AW_RING;
         ring_uses++;
       };
       auto issue_qk = [&](int g, bool last) {
-        const uint32_t k_addr = ring_wait();
-        const uint32_t q_addr = tc::smem_u32(sQ + g * ATT_TILE_BYTES);
+        const uint64_t dk = tc::desc_kmajor(ring_wait());
+        const uint64_t dq = tc::desc_kmajor(tc::smem_u32(sQ + g * ATT_TILE_BYTES));
+        if (tc::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < ATT_D / 16; k++) {
-          uint32_t off = (k >> 2) * (ATT_BM * 128) + (k & 3) * 32;
-          tc::mma_f16_ss(tmem_base + g * 128, tc::desc_kmajor(q_addr + off), tc::desc_kmajor(k_addr + off), idesc_qk,
-                         k > 0 ? 1u : 0u);
+          for (int k = 0; k < ATT_D / 16; k++) {
+            const uint32_t off = ((k >> 2) * (ATT_BM * 128) + (k & 3) * 32) >> 4;
+            tc::mma_f16_ss(tmem_base + g * 128, dq + off, dk + off, idesc_qk, k > 0 ? 1u : 0u);
+          }
+          tc::mma_commit(&s_full[g]);
+          tc::mma_commit(&r_empty[ring]);
+          if (last) tc::mma_commit(&q_empty[g]);
         }
-        tc::mma_commit(&s_full[g]);
-        ring_release();
-        if (last) tc::mma_commit(&q_empty[g]);
+        __syncwarp();
+        ring_advance();
       };
       for (int pp = blockIdx.x; pp < n_pairs; pp += gridDim.x) {
         WinItem it[2] = {win_item(p, n_items, 2 * pp), win_item(p, n_items, 2 * pp + 1)};
@@ -481,14 +486,17 @@ k_attn_win(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUten
                 item_uses[g]++;
               }
               tc::tc_fence_after();
-              const uint32_t v_addr = ring_wait();
+              const uint64_t dv = tc::smem_desc_sw128(ring_wait(), ATT_BN * 128, 1024);
+              if (tc::elect_one()) {
 #pragma unroll
-              for (int k = 0; k < ATT_BN / 16; k++) {
-                uint64_t b = tc::smem_desc_sw128(v_addr + k * 2048, ATT_BN * 128, 1024);
-                tc::mma_f16_ts(tmem_base + 256 + g * ATT_D, tmem_base + g * 128 + k * 8, b, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < ATT_BN / 16; k++)
+                  tc::mma_f16_ts(tmem_base + 256 + g * ATT_D, tmem_base + g * 128 + k * 8, dv + (k * 2048 >> 4), idesc_pv,
+                                 (j > 0 || k > 0) ? 1u : 0u);
+                tc::mma_commit(&o_full[g]);
+                tc::mma_commit(&r_empty[ring]);
               }
-              tc::mma_commit(&o_full[g]);
-              ring_release();
+              __syncwarp();
+              ring_advance();
               if (j + 1 < it[g].n_kt) issue_qk(g, j + 2 == it[g].n_kt);
             }
       }

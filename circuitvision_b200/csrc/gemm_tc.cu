@@ -198,8 +198,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread)
-    if (lane == 0 && rank == 0) {
+    // ===================== MMA issuer.  The whole warp runs the control flow (converged, so descriptors and barrier addresses
+    // stay in uniform registers) and one elected lane issues.  Inside an `if (lane == 0)` region ptxas wrapped every
+    // tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop: 28 dependent instructions per MMA, as long as the 128
+    // tensor-pipe cycles of a 256-wide MMA itself — the K >= 384 shapes sat at 0.55-0.60 of the sustained peak behind it.
+    if (rank == 0) {
       const uint32_t idesc = tc::idesc_bf16(GEMM_BM * CG, BN, false, false, e.fp16 != 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -208,26 +211,31 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
       for (int t = tile0; t < n_tiles; t += tile_stride) {
         tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc::tc_fence_after();
-        uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < n_kb; kb++) {
           tc::mbar_wait(&full[stage], phase);
           tc::tc_fence_after();
-          uint32_t a0 = tc::smem_u32(sA + stage * A_BYTES), b0 = tc::smem_u32(sB + stage * B_BYTES);
-          int ksteps = min(GEMM_BK / 16, (p.K - kb * GEMM_BK + 15) / 16);
-          for (int k = 0; k < ksteps; k++) {
-            if (CG == 2)
-              tc::mma_f16_ss2(d_tmem, tc::desc_kmajor(a0 + k * 32), tc::desc_kmajor(b0 + k * 32), idesc,
-                              (kb > 0 || k > 0) ? 1u : 0u);
-            else
-              tc::mma_f16_ss(d_tmem, tc::desc_kmajor(a0 + k * 32), tc::desc_kmajor(b0 + k * 32), idesc,
-                             (kb > 0 || k > 0) ? 1u : 0u);
+          const uint64_t da = tc::desc_kmajor(tc::smem_u32(sA + stage * A_BYTES));
+          const uint64_t db = tc::desc_kmajor(tc::smem_u32(sB + stage * B_BYTES));
+          const int ksteps = min(GEMM_BK / 16, (p.K - kb * GEMM_BK + 15) / 16);
+          if (tc::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 16; k++)
+              if (k < ksteps) {  // + 32 bytes per k-step: 2 units of the descriptor's 16-byte address field
+                if (CG == 2) tc::mma_f16_ss2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                else tc::mma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              }
+            if (CG == 2) tc::mma_commit2(&empty[stage]);
+            else tc::mma_commit(&empty[stage]);
           }
-          if (CG == 2) tc::mma_commit2(&empty[stage]);
-          else tc::mma_commit(&empty[stage]);
+          __syncwarp();
           if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
         }
-        if (CG == 2) tc::mma_commit2(&tfull[acc]);
-        else tc::mma_commit(&tfull[acc]);
+        if (tc::elect_one()) {
+          if (CG == 2) tc::mma_commit2(&tfull[acc]);
+          else tc::mma_commit(&tfull[acc]);
+        }
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

@@ -1,9 +1,9 @@
 // Fused LayerNorm -> fc1 -> GELU -> fc2 -> +residual for one Hiera MLP half-block (interface: mlp_fused.cuh).
 //
-// Persistent CTA of 24 warps per SM; a work item is a 128-row tile of the fp32 residual stream X [M, C]:
+// Persistent CTA of 28 warps per SM; a work item is a 128-row tile of the fp32 residual stream X [M, C]:
 //
 //   warp 3       TMA producer of the fp32 rows: slices of the tile through a small shared-memory ring (deep prefetch)
-//   warps 20-23  LayerNorm producers: read the fp32 rows from that ring, normalise, write the 16-bit A operand [128, C] into
+//   warps 24-27  LayerNorm producers: read the fp32 rows from that ring, normalise, write the 16-bit A operand [128, C] into
 //                shared memory in the K-major 128-byte-swizzled layout tcgen05 reads (double-buffered across tiles when it fits)
 //   warp 0       TMA producer: streams W1 / W2 boxes ([rows, 64] 16-bit, 128B swizzle) from L2 through a ring
 //   warp 1       MMA issuer (one lane).  The hidden dimension 4C is cut into chunks of HC columns; per chunk g
@@ -11,11 +11,10 @@
 //                    fc2(g):  Y      += H[g&1] * W2[:, chunk g]^T     (TS MMA: A operand = H read from TMEM)
 //                issued as fc1(g), fc2(g-1), fc1(g+1), ... across tile boundaries, so the tensor pipe works on the next chunk
 //                while the epilogue warps turn S into H
-//   warps 4-19   epilogue (four warps per TMEM lane quadrant, each owning a quarter of the columns — the epilogue is a chain of
-//                TMEM / shared / global latencies, and four warps per scheduler hide what two could not: ncu showed 73 % of
-//                the issue slots idle on long-scoreboard stalls with eight): per chunk  tcgen05.ld S -> +b1 -> GELU -> 16-bit
-//                -> tcgen05.st H over the head of the same TMEM columns (a warp only overwrites columns it has already
-//                loaded); per tile  tcgen05.ld Y -> +b2 -> + fp32 residual -> swizzled staging -> TMA store (in place)
+//   warps 4-19   chunk epilogue (four warps per TMEM lane quadrant, each owning a quarter of the chunk's columns): tcgen05.ld S -> +b1
+//                -> GELU -> 16-bit -> tcgen05.st H over the head of the same TMEM columns (a warp only overwrites columns it has
+//                already loaded)
+//   warps 20-23  store warps, per tile: tcgen05.ld Y -> +b2 -> + fp32 residual -> swizzled staging -> TMA store (in place)
 //
 // TMEM: Y at column 0 (two buffers for C = 96), S/H double buffer above it; 512 columns allocated.
 // The hidden activation and the normalised operand never reach HBM; HBM sees X once in, once out.
@@ -30,14 +29,21 @@
 namespace cvb {
 
 constexpr int MLP_SMEM_MAX = 232448;
-constexpr int MLP_THREADS = 768;
-constexpr int MLP_EW = 16;  // epilogue warps
 
 template <int C_>
 struct MlpCfg {
   static constexpr int C = C_;
-  static constexpr int HC = (C == 96 || C == 192) ? 128 : 64;      // hidden columns per chunk (= N of fc1, K of fc2)
-  static constexpr int NY = (C == 96) ? 2 : 1;                      // Y accumulator buffers
+  // warp roles: 0 weight TMA, 1 MMA, 2 TMEM alloc, 3 X TMA, then EW chunk-epilogue warps (S -> GELU -> H), SW store warps
+  // (Y + b2 + residual -> X, off the chunk pipeline's critical path) and 4 LayerNorm producers.  With two Y buffers the
+  // store phase overlaps a whole tile, so one store warp per quadrant is enough and the epilogue gets four; with one Y buffer
+  // the store phase gates the next tile's first fc2 and gets two per quadrant.
+  static constexpr int EW = (C <= 192) ? 16 : 8;
+  static constexpr int SW = (C <= 192) ? 4 : 8;
+  static constexpr int THREADS = (4 + EW + SW + 4) * 32;
+  static constexpr int HC = (C == 96) ? 128 : 64;                   // hidden columns per chunk (= N of fc1, K of fc2)
+  // Y accumulator buffers: two whenever 2 C + 2 HC columns fit the 512 of TMEM — with one, the first fc2 of a tile waits for the
+  // store warps to drain the previous tile (6 us at C = 192, hidden behind only two chunks of fc1)
+  static constexpr int NY = (C <= 192) ? 2 : 1;
   static constexpr int NCH = 4 * C / HC;                            // chunks per tile
   static constexpr int NKB1 = (C + 63) / 64;                        // 64-wide K-blocks of fc1
   static constexpr int KS1_LAST = (C - (NKB1 - 1) * 64) / 16;       // 16-wide k-steps in the last K-block
@@ -47,9 +53,9 @@ struct MlpCfg {
   static constexpr int UNIT_ROWS = HC > N2 ? HC : N2;               // rows of the largest weight box
   static constexpr int STAGE_BYTES = UNIT_ROWS * 128;
   static constexpr int A_BYTES = NKB1 * 128 * 128;
-  static constexpr int OUT_BYTES = MLP_EW * 2048;                   // one 32 x 16 fp32 staging box per epilogue warp
+  static constexpr int OUT_BYTES = SW * 2048;                   // one 32 x 16 fp32 staging box per store warp
   static constexpr int BIAS_BYTES = ((5 * C * 4 + 1023) / 1024) * 1024;  // b1 [4C] | b2 [C] copied to shared memory once
-  static constexpr int PC = HC / 4;                                 // hidden columns per epilogue warp and chunk
+  static constexpr int PC = HC / (EW / 4);                      // hidden columns per epilogue warp and chunk
   // LayerNorm producers: LN_L lanes per row, LN_V float4 per lane (C = 4 * LN_L * LN_V)
   static constexpr int LN_L = (C == 96 || C == 224 || C == 288) ? 8 : (C == 192) ? 16 : (C == 384) ? 32 : 4;
   static constexpr int LN_V = C / (4 * LN_L);
@@ -61,7 +67,7 @@ struct MlpCfg {
   static constexpr int NXB = C > 256 ? 2 : 1;                       // column boxes per slice (TMA box dims are <= 256)
   static constexpr int XBC = C / NXB;
   static constexpr int X_BYTES = XR * C * 4;
-  static constexpr int XSLOTS = X_BYTES > 16384 ? (C > 256 ? 2 : 3) : 4;
+  static constexpr int XSLOTS = 2;
   static constexpr int FIXED = 1024 + 512 + OUT_BYTES + BIAS_BYTES + XSLOTS * X_BYTES;
   // A operand buffers: two (LayerNorm of tile t+1 under the MMAs of tile t) when four weight stages still fit beside them
   static constexpr int NA = ((MLP_SMEM_MAX - FIXED - 2 * A_BYTES) / STAGE_BYTES >= 4) ? 2 : 1;
@@ -96,7 +102,7 @@ __device__ __forceinline__ bool fc2_first(int j) { return K::NA == 1 && j == 0; 
 // ILV: issue the MMAs of a k-step alternately on two independent accumulator halves (fc1: two N = HC/2 MMAs; fc2 with
 // NSPLIT = 2: the two column halves of Y) instead of running one dependent accumulation chain after the other.
 template <int C_, int ILV>
-__global__ void __launch_bounds__(MLP_THREADS, 1)
+__global__ void __launch_bounds__(MlpCfg<C_>::THREADS, 1)
 k_mlp_fused(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2,
             const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_x, MlpFusedArgs p) {
   using K = MlpCfg<C_>;
@@ -142,9 +148,9 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__
       tc::mbar_init(&a_full[i], 4);
       tc::mbar_init(&a_empty[i], 1);
       tc::mbar_init(&s_full[i], 1);
-      tc::mbar_init(&h_full[i], MLP_EW);
+      tc::mbar_init(&h_full[i], K::EW);
       tc::mbar_init(&y_full[i], 1);
-      tc::mbar_init(&y_empty[i], MLP_EW);
+      tc::mbar_init(&y_empty[i], K::SW);
     }
     for (int i = 0; i < K::XSLOTS; i++) {
       tc::mbar_init(&x_full[i], 1);
@@ -153,7 +159,7 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__
     tc::fence_barrier_init();
   }
   if (warp == 2) tc::tmem_alloc<512>(tmem_slot);
-  for (int i = threadIdx.x; i < 5 * C; i += MLP_THREADS) sB1[i] = i < 4 * C ? p.b1[i] : p.b2[i - 4 * C];
+  for (int i = threadIdx.x; i < 5 * C; i += K::THREADS) sB1[i] = i < 4 * C ? p.b1[i] : p.b2[i - 4 * C];
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -320,10 +326,10 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__
         if (!swap && g >= 1) fc2(g - 1);
       }
     }
-  } else if (warp >= 4 + MLP_EW) {
+  } else if (warp >= 4 + K::EW + K::SW) {
     // ===================== LayerNorm producers: fp32 rows -> normalised 16-bit A operand (swizzled K-major)
     constexpr int L = K::LN_L, V = K::LN_V, RPW = 32 / L, RPP = 4 * RPW, SL = 128 / K::XR, PPS = K::XR / RPP;
-    const int pw = warp - 4 - MLP_EW, sub = lane % L, rsub = lane / L;
+    const int pw = warp - 4 - K::EW - K::SW, sub = lane % L, rsub = lane / L;
     constexpr bool HOIST = V <= 3;  // this lane's columns are the same in every pass: keep their gamma / beta in registers
     float4 gam[HOIST ? V : 1], bet[HOIST ? V : 1];
     if (HOIST) {
@@ -390,52 +396,17 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__
       if (lane == 0) tc::mbar_arrive(&a_full[ab]);
       if (pw == 0 && lane == 0) mlp_trace(p, 11, it);  // LN: A operand written
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue warps: quadrant = warp % 4 (TMEM lanes), column quarter = (warp - 4) / 4
-    constexpr int PC = K::PC;
-    const int quad = warp & 3, part = (warp - 4) >> 2;
+  } else if (warp >= 4 + K::EW) {
+    // ===================== store warps: quadrant = warp % 4 (TMEM lanes), unit parity = (warp - 12) / 4.
+    // Y + b2 + residual -> fp32 rows, in place, in units of 16 columns.  They only ever wait for y_full, so the chunk
+    // epilogue warps run straight on into the next tile (with the same warps doing both, the 4-5 us of this epilogue
+    // stalled the chunk pipeline at every tile boundary: timeline in profiles/r2_mlp_fused_notes.md).
+    const int quad = warp & 3, uh = (warp - 4 - K::EW) >> 2;
+    constexpr int USTEP = K::SW / 4;  // store warps per quadrant
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    uint8_t* buf = sOut + (warp - 4) * 2048;
-    unsigned int nsat = 0;
+    uint8_t* buf = sOut + (warp - 4 - K::EW) * 2048;
     for (int it = 0; it < my_tiles; it++) {
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-      for (int j = 0; j < K::NCH; j++) {
-        const int g = it * K::NCH + j;
-        tc::mbar_wait(&s_full[g & 1], (uint32_t)(g >> 1) & 1u);
-        tc::tc_fence_after();
-        if (warp == 4 && lane == 0) mlp_trace(p, 5, g);  // epilogue: S(g) is there
-        const uint32_t sbase = lane_addr + K::SBASE + (g & 1) * HC + part * PC;
-        uint32_t v[PC];
-        if (PC == 32) tc::tmem_ld_32x32(sbase, *(uint32_t(*)[32])v);
-        else tc::tmem_ld_32x16(sbase, *(uint32_t(*)[16])v);
-        const float4* bp = (const float4*)(sB1 + j * HC + part * PC);  // same address for every lane: broadcast reads
-        tc::tmem_ld_wait();
-        uint32_t pk[PC / 2];
-#pragma unroll
-        for (int q = 0; q < PC / 4; q++) {
-          const float4 bv = bp[q];
-          float f0, f1, f2, f3;
-          up2(add2(pk2(__uint_as_float(v[4 * q + 0]), __uint_as_float(v[4 * q + 1])), pk2(bv.x, bv.y)), f0, f1);
-          up2(add2(pk2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])), pk2(bv.z, bv.w)), f2, f3);
-          gelu_tanh2(f0, f1);
-          gelu_tanh2(f2, f3);
-          if (p.fp16) { pk[2 * q] = tc::pack16(1, f0, f1); pk[2 * q + 1] = tc::pack16(1, f2, f3); }
-          else { pk[2 * q] = tc::pack16(0, f0, f1); pk[2 * q + 1] = tc::pack16(0, f2, f3); }
-        }
-        if (p.sat_counter && p.fp16) {
-#pragma unroll
-          for (int q = 0; q < PC / 2; q++) nsat += ((pk[q] & 0x7FFFu) == 0x7BFFu) + (((pk[q] >> 16) & 0x7FFFu) == 0x7BFFu);
-        }
-        // H over columns this warp has already consumed
-        if (PC == 32) tc::tmem_st_32x16(sbase, *(uint32_t(*)[16])pk);
-        else tc::tmem_st_32x8(sbase, *(uint32_t(*)[8])pk);
-        tc::tmem_st_wait();
-        tc::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&h_full[g & 1]);
-        if (warp == 4 && lane == 0) mlp_trace(p, 6, g);  // epilogue: H(g) written
-      }
-      // ---- tile epilogue: Y + b2 + residual -> fp32 rows, in place; units of 16 columns, unit u belongs to quarter u % 4
       const int yb = it % K::NY;
       const long long row0 = (long long)tile * 128 + quad * 32, myrow = row0 + lane;
       const bool live = myrow < p.M;
@@ -445,11 +416,11 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__
 #pragma unroll
         for (int q = 0; q < 4; q++) rv[q] = live ? rp[q] : make_float4(0.f, 0.f, 0.f, 0.f);
       };
-      if (part < C / 16) load_res(part);
+      if (uh < C / 16) load_res(uh);
       tc::mbar_wait(&y_full[yb], (uint32_t)(it / K::NY) & 1u);
       tc::tc_fence_after();
-      if (warp == 4 && lane == 0) mlp_trace(p, 7, it);  // epilogue: Y of the tile is there
-      for (int u = part; u < C / 16; u += 4) {
+      if (warp == 4 + K::EW && lane == 0) mlp_trace(p, 7, it);  // store: Y of the tile is there
+      for (int u = uh; u < C / 16; u += USTEP) {
         const int col0 = u * 16;
         uint32_t v[16];
         tc::tmem_ld_32x16(lane_addr + yb * C + col0, v);
@@ -468,7 +439,7 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__
           // 32 x 16 fp32 box, 64-byte rows, 64B swizzle: 16-byte chunk q of row r lives at chunk q ^ ((r >> 1) & 3)
           *(float4*)(buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = o;
         }
-        if (u + 4 < C / 16) load_res(u + 4);
+        if (u + USTEP < C / 16) load_res(u + USTEP);
         tc::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0 && row0 < p.M) {
@@ -479,9 +450,55 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&y_empty[yb]);
-      if (warp == 4 && lane == 0) mlp_trace(p, 8, it);  // epilogue: tile stored
+      if (warp == 4 + K::EW && lane == 0) mlp_trace(p, 8, it);  // store: tile stored
     }
     if (lane == 0) tc::tma_store_wait<0>();
+  } else if (warp >= 4) {
+    // ===================== chunk-epilogue warps: quadrant = warp % 4 (TMEM lanes), column half = (warp - 4) / 4
+    constexpr int PC = K::PC;
+    const int quad = warp & 3, part = (warp - 4) >> 2;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    unsigned int nsat = 0;
+    for (int g = 0; g < n_chunks; g++) {
+      const int j = g % K::NCH;
+      tc::mbar_wait(&s_full[g & 1], (uint32_t)(g >> 1) & 1u);
+      tc::tc_fence_after();
+      if (warp == 4 && lane == 0) mlp_trace(p, 5, g);  // epilogue: S(g) is there
+      const uint32_t sbase = lane_addr + K::SBASE + (g & 1) * HC + part * PC;
+      constexpr int SUBW = PC >= 32 ? 32 : 16;  // columns per TMEM load
+#pragma unroll
+      for (int i = 0; i < PC / SUBW; i++) {
+        uint32_t v[SUBW];
+        if (SUBW == 32) tc::tmem_ld_32x32(sbase + 32 * i, *(uint32_t(*)[32])v);
+        else tc::tmem_ld_32x16(sbase + 16 * i, *(uint32_t(*)[16])v);
+        const float4* bp = (const float4*)(sB1 + j * HC + part * PC + SUBW * i);  // same address for every lane: broadcast reads
+        tc::tmem_ld_wait();
+        uint32_t pk[SUBW / 2];
+#pragma unroll
+        for (int q = 0; q < SUBW / 4; q++) {
+          const float4 bv = bp[q];
+          float f0, f1, f2, f3;
+          up2(add2(pk2(__uint_as_float(v[4 * q + 0]), __uint_as_float(v[4 * q + 1])), pk2(bv.x, bv.y)), f0, f1);
+          up2(add2(pk2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])), pk2(bv.z, bv.w)), f2, f3);
+          gelu_tanh2(f0, f1);
+          gelu_tanh2(f2, f3);
+          if (p.fp16) { pk[2 * q] = tc::pack16(1, f0, f1); pk[2 * q + 1] = tc::pack16(1, f2, f3); }
+          else { pk[2 * q] = tc::pack16(0, f0, f1); pk[2 * q + 1] = tc::pack16(0, f2, f3); }
+        }
+        if (p.sat_counter && p.fp16) {
+#pragma unroll
+          for (int q = 0; q < SUBW / 2; q++) nsat += ((pk[q] & 0x7FFFu) == 0x7BFFu) + (((pk[q] >> 16) & 0x7FFFu) == 0x7BFFu);
+        }
+        // H over columns this warp has already consumed
+        if (SUBW == 32) tc::tmem_st_32x16(sbase + 16 * i, *(uint32_t(*)[16])pk);
+        else tc::tmem_st_32x8(sbase + 8 * i, *(uint32_t(*)[8])pk);
+      }
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&h_full[g & 1]);
+      if (warp == 4 && lane == 0) mlp_trace(p, 6, g);  // epilogue: H(g) written
+    }
     if (p.sat_counter) {
       nsat = __reduce_add_sync(0xffffffffu, nsat);
       if (lane == 0 && nsat) atomicAdd(p.sat_counter, nsat);
@@ -522,7 +539,7 @@ static int launch_mlp_v(const MlpFusedArgs& a, int num_sms, cudaStream_t st) {
     snprintf(nm, sizeof(nm), "mlp M%d C%d hc%d fused LN+fc1+GELU+fc2+res", a.M, C_, K::HC);
     cvb_next_name(nm);
   }
-  CVB_LAUNCH(kern, dim3(grid), dim3(MLP_THREADS), K::SMEM, st, t1, t2, to, tx, a);
+  CVB_LAUNCH(kern, dim3(grid), dim3(K::THREADS), K::SMEM, st, t1, t2, to, tx, a);
   return CV_OK;
 }
 
