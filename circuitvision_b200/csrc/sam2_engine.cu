@@ -660,6 +660,16 @@ extern "C" int cv_sam2_preprocess(const uint8_t* img_hwc, int H, int W, int swap
   return launch_preprocess_aa(img_hwc, H, W, 1024, mean, istd, swap_rb, tmp, out_chw, (cudaStream_t)stream);
 }
 
+extern "C" int cv_sam2_preprocess_pages(const uint8_t* pages, const void* geom, int B, int max_crop_h, int swap_rb, float* tmp,
+                                        float* out_chw, void* stream) {
+  cvb_reset_launches();
+  if (!pages || !geom || !tmp || !out_chw || B <= 0 || max_crop_h <= 0)
+    return cvb_fail(CV_ERR_INVALID, "cv_sam2_preprocess_pages: bad argument");
+  static const float mean[3] = {0.485f, 0.456f, 0.406f};
+  static const float istd[3] = {1.0f / 0.229f, 1.0f / 0.224f, 1.0f / 0.225f};
+  return launch_preprocess_pages(pages, geom, B, max_crop_h, 1024, mean, istd, swap_rb, tmp, out_chw, (cudaStream_t)stream);
+}
+
 extern "C" int cv_sam2_resize_logits(const float* logits, int B, int S, int H, int W, float* out_logits, uint8_t* mask_u8,
                                      int* extents, void* stream) {
   cvb_reset_launches();

@@ -216,6 +216,67 @@ int launch_preprocess_aa(const uint8_t* img, int H, int W, int S, const float* m
   return CV_OK;
 }
 
+// Batched form for whole pages (analysis_pipeline.py:177-208): image b is the crop window
+// [x0, x1) x [y0, y1) of page b (uint8 HWC at pages + off[b], page width pw[b]) — the array the reference obtains by slicing
+// (circuit_analyzer.py:1246) and hands to SAM2Transforms.  Same arithmetic as the single-image kernels above, one grid
+// z-slice per image; tmp is [B][max_hc][S][3] floats.
+struct PageGeom { long long off; int pw, x0, y0, x1, y1, pad; };
+
+__global__ void __launch_bounds__(256) k_aa_width_pages(const uint8_t* __restrict__ pages, const PageGeom* __restrict__ geom, int S,
+                                                        int swap_rb, int max_hc, float* __restrict__ tmp) {
+  const PageGeom g = geom[blockIdx.z];
+  const int Hc = g.y1 - g.y0, Wc = g.x1 - g.x0;
+  int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (x >= S || y >= Hc) return;
+  const float scale = (float)Wc / (float)S;
+  AATap t = aa_tap(x, scale, Wc);
+  float tot = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int j = 0; j < t.n; j++) tot += aa_w(t, j);
+  const uint8_t* rowp = pages + g.off + ((long long)(g.y0 + y) * g.pw + g.x0) * 3;
+  for (int j = 0; j < t.n; j++) {
+    float w = aa_w(t, j) / tot;
+    const uint8_t* p = rowp + (long long)(t.lo + j) * 3;
+    a0 += w * ((float)p[swap_rb ? 2 : 0] / 255.0f);
+    a1 += w * ((float)p[1] / 255.0f);
+    a2 += w * ((float)p[swap_rb ? 0 : 2] / 255.0f);
+  }
+  float* o = tmp + (((long long)blockIdx.z * max_hc + y) * S + x) * 3;
+  o[0] = a0; o[1] = a1; o[2] = a2;
+}
+
+__global__ void __launch_bounds__(256) k_aa_height_pages(const float* __restrict__ tmp, const PageGeom* __restrict__ geom, int S,
+                                                         int max_hc, float m0, float m1, float m2, float s0, float s1, float s2,
+                                                         float* __restrict__ out) {
+  const PageGeom g = geom[blockIdx.z];
+  const int Hc = g.y1 - g.y0;
+  int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (x >= S || y >= S) return;
+  const float scale = (float)Hc / (float)S;
+  AATap t = aa_tap(y, scale, Hc);
+  float tot = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int j = 0; j < t.n; j++) tot += aa_w(t, j);
+  const float* base = tmp + (long long)blockIdx.z * max_hc * S * 3;
+  for (int j = 0; j < t.n; j++) {
+    float w = aa_w(t, j) / tot;
+    const float* p = base + ((long long)(t.lo + j) * S + x) * 3;
+    a0 += w * p[0]; a1 += w * p[1]; a2 += w * p[2];
+  }
+  long long pl = (long long)S * S, o = (long long)y * S + x;
+  float* ob = out + (long long)blockIdx.z * 3 * pl;
+  ob[o] = (a0 - m0) * s0;
+  ob[pl + o] = (a1 - m1) * s1;
+  ob[2 * pl + o] = (a2 - m2) * s2;
+}
+
+int launch_preprocess_pages(const uint8_t* pages, const void* geom, int B, int max_hc, int S, const float* mean,
+                            const float* inv_std, int swap_rb, float* tmp, float* out, cudaStream_t st) {
+  CVB_LAUNCH(k_aa_width_pages, dim3((S + 63) / 64, (max_hc + 3) / 4, B), dim3(256), 0, st, pages, (const PageGeom*)geom, S, swap_rb,
+             max_hc, tmp);
+  CVB_LAUNCH(k_aa_height_pages, dim3((S + 63) / 64, (S + 3) / 4, B), dim3(256), 0, st, tmp, (const PageGeom*)geom, S, max_hc, mean[0],
+             mean[1], mean[2], inv_std[0], inv_std[1], inv_std[2], out);
+  return CV_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ LayerNorm rows
 // One warp per destination row.  C % 4 == 0, C <= 1536.
 __global__ void __launch_bounds__(256) k_ln_rows(const float* __restrict__ X, int C, const float* __restrict__ gamma,

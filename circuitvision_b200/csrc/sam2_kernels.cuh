@@ -27,6 +27,11 @@ int launch_im2col_f32(const float* img_chw, int B, int S, int fp16, __nv_bfloat1
 int launch_preprocess_aa(const uint8_t* img_hwc, int H, int W, int S, const float* mean, const float* inv_std, int swap_rb,
                          float* tmp, float* out_chw, cudaStream_t st);
 
+// batched page form: geom = B records {int64 byte offset of the page, int page width, x0, y0, x1, y1, pad} (32 bytes each, device);
+// image b = crop window of page b; tmp: float [B, max_hc, S, 3]; out: float [B, 3, S, S]
+int launch_preprocess_pages(const uint8_t* pages, const void* geom, int B, int max_hc, int S, const float* mean,
+                            const float* inv_std, int swap_rb, float* tmp, float* out, cudaStream_t st);
+
 // ---- LayerNorm over the channel dim with optional window partition (zero rows for window padding).
 // ws == 0: identity row order.  gamma == nullptr: plain fp32 -> bf16 cast.  out_f32 optional (normalised, fp32).
 int launch_ln_rows(const float* X, long long n_src_rows, int C, const float* gamma, const float* beta, float eps,

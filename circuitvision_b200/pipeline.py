@@ -308,3 +308,80 @@ class MaskPipeline:
     def run(self, host_masks: torch.Tensor, boxes_list: List[list]) -> BatchResult:
         self.submit(host_masks, boxes_list)
         return self.collect()
+
+
+class PagePipeline:
+    """The reference's per-page sequence (`/root/reference/src/analysis_pipeline.py:177-246`: crop_image_and_adjust_bboxes ->
+    segment_with_sam2 on the crop -> get_node_connections on the crop's mask) for a BATCH of whole pages of any size.
+
+    Only the raw uint8 pages cross PCIe (<= 3 bytes per page pixel instead of 12 MB of fp32 per crop): the crop window comes
+    from the host box geometry (crop.py, the reference's rule), the crop + ToTensor + antialiased Resize((1024,1024)) +
+    Normalize run in one batched device kernel pair (cv_sam2_preprocess_pages), SAM 2.1 runs on the whole batch, the logits go
+    back to each crop's own resolution (postprocess_masks), and the node analysis runs per crop (their sizes differ)."""
+
+    def __init__(self, model, padding: int = 80):
+        from . import sam2_infer as _s
+        self._s = _s
+        self.model = model
+        self.eng = model.engine()
+        self.dev = torch.device("cuda", self.eng.dev)
+        self.padding = padding
+        self.na = NodeAnalyzer(self.dev)
+        self.lib = _lib.load()
+        self.lib.cv_sam2_preprocess_pages.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                      C.c_void_p]
+        self.h2d_bytes = 0
+
+    def run(self, pages: List[np.ndarray], boxes_list: List[list]):
+        """pages: (H,W,3) uint8 arrays in the channel order the reference's pipeline passes to segment_with_sam2.
+        -> list of dicts: mask [Hc,Wc] u8, extent, nodes, emptied, enhanced, boxes (moved into the crop), crop_info."""
+        from . import crop as _crop
+        from .nodes import NON_COMPONENTS
+        B = len(pages)
+        if B == 0 or B != len(boxes_list):
+            raise CvError("one box list per page is required")
+        geom = np.zeros(B, np.dtype([("off", "<i8"), ("pw", "<i4"), ("x0", "<i4"), ("y0", "<i4"), ("x1", "<i4"), ("y1", "<i4"),
+                                     ("pad", "<i4")]))
+        moved, infos, off = [], [], 0
+        for b, (pg, boxes) in enumerate(zip(pages, boxes_list)):
+            if pg.ndim != 3 or pg.shape[2] != 3 or pg.dtype != np.uint8:
+                raise CvError("pages must be (H,W,3) uint8 arrays")
+            _, mv, info = _crop.crop_image_and_adjust_bboxes(pg, boxes, self.padding, NON_COMPONENTS)  # host box geometry only
+            win = info["final_crop_window_abs"] if info.get("crop_applied") else (0, 0, pg.shape[1], pg.shape[0])
+            geom[b] = (off, pg.shape[1], win[0], win[1], win[2], win[3], 0)
+            off += pg.size
+            moved.append(mv)
+            infos.append(info)
+        host = torch.empty(off, dtype=torch.uint8, pin_memory=True)
+        hv = host.numpy()
+        for b, pg in enumerate(pages):
+            hv[int(geom["off"][b]):int(geom["off"][b]) + pg.size] = np.ascontiguousarray(pg).reshape(-1)
+        self.h2d_bytes = off + geom.nbytes
+        hc = (geom["y1"] - geom["y0"]).astype(int)
+        wc = (geom["x1"] - geom["x0"]).astype(int)
+        max_hc = int(hc.max())
+        out = []
+        with torch.cuda.device(self.dev):
+            st = torch.cuda.current_stream().cuda_stream
+            d_pages = host.to(self.dev, non_blocking=True)
+            d_geom = torch.from_numpy(geom.view(np.uint8).reshape(B, 32).copy()).to(self.dev)
+            x = torch.empty((B, 3, 1024, 1024), dtype=torch.float32, device=self.dev)
+            tmp = torch.empty((B, max_hc, 1024, 3), dtype=torch.float32, device=self.dev)
+            _lib.check(self.lib.cv_sam2_preprocess_pages(d_pages.data_ptr(), d_geom.data_ptr(), B, max_hc, 1, tmp.data_ptr(),
+                                                         x.data_ptr(), st), "cv_sam2_preprocess_pages")
+            self.last_input = x
+            r = self.eng.forward(x, 1, False, want_high=True, want_low=False)
+            high = r["high"]
+            libs = self._s._libsam()
+            for b in range(B):
+                H, W = int(hc[b]), int(wc[b])
+                mask = torch.empty((H, W), dtype=torch.uint8, device=self.dev)
+                ext = torch.empty((4,), dtype=torch.int32, device=self.dev)
+                _lib.check(libs.cv_sam2_resize_logits(high[b].data_ptr(), 1, 1024, H, W, None, mask.data_ptr(), ext.data_ptr(), st),
+                           "cv_sam2_resize_logits")
+                nr = self.na.analyze(mask[None], [moved[b]])
+                e = ext.cpu().tolist()
+                out.append(dict(mask=mask.cpu().numpy(), extent=(e[0], e[1], e[2] + 1, e[3] + 1) if e[2] >= 0 else None,
+                                nodes=nr.nodes(0), emptied=nr.emptied[0].cpu().numpy(), enhanced=nr.enhanced[0].cpu().numpy(),
+                                boxes=moved[b], crop_info=infos[b]))
+        return out

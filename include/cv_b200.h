@@ -209,6 +209,12 @@ int cv_sam2_set_debug(cv_sam2* h, int count_fp16_saturation);
 int cv_sam2_read_buffer(cv_sam2* h, const char* name, void* dst_device, long long bytes, void* stream);
 /* SAM2Transforms.__call__ for one uint8 HWC image of any size -> float32 CHW [3,1024,1024]; tmp: H*1024*3 floats. */
 int cv_sam2_preprocess(const uint8_t* img_hwc, int H, int W, int swap_rb, float* tmp, float* out_chw, void* stream);
+/* Batched SAM2Transforms.__call__ on crop windows of whole pages (analysis_pipeline.py:177-208: crop_image_and_adjust_bboxes,
+ * then segment_with_sam2 on the crop): image b = window [x0,x1) x [y0,y1) of page b, a uint8 HWC page of width pw at
+ * pages + off.  geom: B device records of 32 bytes {int64 off; int32 pw, x0, y0, x1, y1, pad}.  tmp: B*max_crop_h*1024*3 floats.
+ * out_chw: [B,3,1024,1024] f32, what cv_sam2_forward(input_kind 1) consumes.  Only the raw uint8 pages cross PCIe.          */
+int cv_sam2_preprocess_pages(const uint8_t* pages, const void* geom, int B, int max_crop_h, int swap_rb, float* tmp,
+                             float* out_chw, void* stream);
 /* SAM2Transforms.postprocess_masks with hole/sprinkle filters off: bilinear (align_corners=False) resize of
  * [B,1,S,S] f32 logits to [B,1,H,W]; optional threshold mask + extents as in cv_sam2_forward.                 */
 int cv_sam2_resize_logits(const float* logits, int B, int S, int H, int W, float* out_logits, uint8_t* mask_u8,
