@@ -58,7 +58,28 @@ constexpr int AG_THREADS = 384;
 template <int D>
 constexpr int ag_smem() { return 1024 + att_tile_bytes<D>() * (2 /*Q0,Q1*/ + 2 /*K*/ + 2 /*V*/) + 256; }
 
-template <int D>
+// 2^x for a PAIR of scores on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, relative error 7.7e-5 — a sixth of
+// an fp16 ulp of P): x = n + f with n = round(x) taken from the low mantissa bits of x + 1.5 * 2^23, 2^f on [-0.5, 0.5] by
+// Horner, 2^n by an integer add into the exponent field.  The softmax warps of the global kernel are bound by the XU pipe
+// (one MUFU.EX2 per score: 56 % busy in ncu while the tensor pipe sat at 40 %), so a third of the scores go through here.
+__device__ __forceinline__ void ex2_poly2(float x0, float x1, float& e0, float& e1) {
+  x0 = fmaxf(x0, -125.f);
+  x1 = fmaxf(x1, -125.f);
+  const uint64_t x = pk2(x0, x1);
+  const uint64_t xf = add2(x, pk2(12582912.f, 12582912.f));
+  const uint64_t r = add2(xf, pk2(-12582912.f, -12582912.f));
+  const uint64_t f = fma2(r, pk2(-1.f, -1.f), x);
+  uint64_t q = fma2(f, pk2(0.05508868f, 0.05508868f), pk2(0.24260405f, 0.24260405f));
+  q = fma2(q, f, pk2(0.69327624f, 0.69327624f));
+  q = fma2(q, f, pk2(0.99992894f, 0.99992894f));
+  float q0, q1, n0, n1;
+  up2(q, q0, q1);
+  up2(xf, n0, n1);
+  e0 = __int_as_float(__float_as_int(q0) + (__float_as_int(n0) << 23));
+  e1 = __int_as_float(__float_as_int(q1) + (__float_as_int(n1) << 23));
+}
+
+template <int D, bool EXP_FMA>
 __global__ void __launch_bounds__(AG_THREADS, 1)
 k_attn_global(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
               const __grid_constant__ CUtensorMap tv, AttnParams p) {
@@ -231,8 +252,12 @@ k_attn_global(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
           asm("max.f32 %0, %0, %1, %2;" : "+f"(tmax) : "f"(s0), "f"(s1));
           float x0, x1;
           up2(fma2(pk2(s0, s1), sc2, mr2), x0, x1);
-          pe[i] = ex2(x0);
-          pe[i + 1] = ex2(x1);
+          if (EXP_FMA && ((i >> 1) % 3) == 2) {  // every third pair: exponentials on the FMA pipe
+            ex2_poly2(x0, x1, pe[i], pe[i + 1]);
+          } else {
+            pe[i] = ex2(x0);
+            pe[i + 1] = ex2(x1);
+          }
           const uint64_t pp = pk2(pe[i], pe[i + 1]);
           asm("add.rn.f32x2 %0, %0, %1;" : "+l"(rs2) : "l"(pp));
         }
@@ -640,10 +665,17 @@ static int attn_launch_d(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
   if (glob) {
     static std::atomic<unsigned long long> attr_set_g{0};
     if (cvb_once_per_device(attr_set_g)) {
-      cudaError_t e = cudaFuncSetAttribute(k_attn_global<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, ag_smem<D>());
+      cudaError_t e = cudaFuncSetAttribute(k_attn_global<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ag_smem<D>());
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_global<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ag_smem<D>());
       if (e != cudaSuccess) return cvb_fail_cuda(e, "cudaFuncSetAttribute(k_attn_global)");
     }
-    CVB_LAUNCH((k_attn_global<D>), dim3(p.Mq / (2 * ATT_BM), p.heads), dim3(AG_THREADS), ag_smem<D>(), st, tq, tk, tv, p);
+    // CVB_ATTN_EXPFMA=0: every exponential on the XU pipe (A/B switch)
+    static const bool exp_fma = getenv("CVB_ATTN_EXPFMA") ? atoi(getenv("CVB_ATTN_EXPFMA")) != 0 : true;
+    if (exp_fma) {
+      CVB_LAUNCH((k_attn_global<D, true>), dim3(p.Mq / (2 * ATT_BM), p.heads), dim3(AG_THREADS), ag_smem<D>(), st, tq, tk, tv, p);
+    } else {
+      CVB_LAUNCH((k_attn_global<D, false>), dim3(p.Mq / (2 * ATT_BM), p.heads), dim3(AG_THREADS), ag_smem<D>(), st, tq, tk, tv, p);
+    }
     return CV_OK;
   }
   static std::atomic<unsigned long long> attr_set_w{0};

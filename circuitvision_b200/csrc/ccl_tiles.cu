@@ -212,32 +212,35 @@ __global__ void __launch_bounds__(CS_WARPS * 32) k_ccl_scan(const uint8_t* __res
         lc[cs_slot(c, st >> 1)] = m;
       }
     }
-    // runs that span words: minimum over the portions, unions between portions that disagree
-    // (segmented backward min-scan over the followers of each origin: the groups are contiguous lane ranges, so five
-    //  shuffle steps do it; __match_any + __reduce_min on sub-masks compiled to a loop over ~30 singleton groups per row)
-    const int key = cin ? origin : 32 + c;
-    int gmin = cin ? ch : CS_INF;
+    // runs that span words: minimum over the portions, unions between portions that disagree.  Most rows have none (only
+    // horizontal structures cross word boundaries): one ballot skips the whole step.
+    if (__ballot_sync(0xffffffffu, cin) != 0u) {
+      // segmented backward min-scan over the followers of each origin: the groups are contiguous lane ranges, so five shuffle
+      // steps do it (__match_any + __reduce_min on sub-masks compiled to a loop over ~30 singleton groups per row)
+      const int key = cin ? origin : 32 + c;
+      int gmin = cin ? ch : CS_INF;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int v2 = __shfl_down_sync(0xffffffffu, gmin, d), k2 = __shfl_down_sync(0xffffffffu, key, d);
-      if (c + d < 32 && k2 == key) gmin = min(gmin, v2);
-    }
-    const int from_right = __shfl_down_sync(0xffffffffu, gmin, 1);  // first follower: minimum over the whole group
-    const bool tail_org = cout && brk;  // my tail run starts in my word and continues to the right
-    int my_m = 0;
-    const int my_start = rowbase + tail_st;
-    if (tail_org) {
-      const int tot = min(ct, from_right);
-      my_m = tot == CS_INF ? my_start : tot;
-      if (ct != CS_INF && ct != my_m) gunion_roots(L, ct, my_m);
-      L[my_start] = my_m + 1;
-      lc[cs_slot(c, tail_st >> 1)] = my_m;
-    }
-    const int mo = __shfl_sync(0xffffffffu, my_m, origin), so = __shfl_sync(0xffffffffu, my_start, origin);
-    if (cin) {
-      if (ch != CS_INF && ch != mo) gunion_roots(L, ch, mo);
-      lc[cs_slot(c, 0)] = mo;
-      head[(size_t)y * wpr + wc] = so;
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v2 = __shfl_down_sync(0xffffffffu, gmin, d), k2 = __shfl_down_sync(0xffffffffu, key, d);
+        if (c + d < 32 && k2 == key) gmin = min(gmin, v2);
+      }
+      const int from_right = __shfl_down_sync(0xffffffffu, gmin, 1);  // first follower: minimum over the whole group
+      const bool tail_org = cout && brk;  // my tail run starts in my word and continues to the right
+      int my_m = 0;
+      const int my_start = rowbase + tail_st;
+      if (tail_org) {
+        const int tot = min(ct, from_right);
+        my_m = tot == CS_INF ? my_start : tot;
+        if (ct != CS_INF && ct != my_m) gunion_roots(L, ct, my_m);
+        L[my_start] = my_m + 1;
+        lc[cs_slot(c, tail_st >> 1)] = my_m;
+      }
+      const int mo = __shfl_sync(0xffffffffu, my_m, origin), so = __shfl_sync(0xffffffffu, my_start, origin);
+      if (cin) {
+        if (ch != CS_INF && ch != mo) gunion_roots(L, ch, mo);
+        lc[cs_slot(c, 0)] = mo;
+        head[(size_t)y * wpr + wc] = so;
+      }
     }
     __syncwarp();  // label slots and parent entries of this row are visible to every lane before the next row reads them
     up = w; upl = wl; upr = wr;

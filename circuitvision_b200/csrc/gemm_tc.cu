@@ -551,6 +551,10 @@ static int launch_bn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16*
     const bool gelu_sig = gelu_form == 1, gelu_tanh = gelu_form == 2;
     if (pairs_on && BN >= 128 && BN >= pair_min_bn && K >= 256 && M >= 1024) {
       if (b16 && !res && e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 0, 1, 0, 0, 2>(CVB_GEMM_ARGS);
+      // 16 epilogue warps for the GELU epilogue of the CTA-pair shapes (fc1 of stages 3-4, epilogue-bound): 844 -> 880 TFLOP/s on
+      // M262144 N1536 K384 once the MMA issue no longer co-limited (CVB_GELU_EW16=0 restores 8)
+      static const int gelu_ew16 = getenv("CVB_GELU_EW16") ? atoi(getenv("CVB_GELU_EW16")) : 1;
+      if (b16 && !res && e.act == GEMM_ACT_GELU && gelu_tanh && gelu_ew16) return launch_cfg<BN, 4, 0, 1, 0, 0, 2, 16>(CVB_GEMM_ARGS);
       if (b16 && !res && e.act == GEMM_ACT_GELU && gelu_tanh) return launch_cfg<BN, 4, 0, 1, 0, 0, 2>(CVB_GEMM_ARGS);
       if (b16 && !res && e.act == GEMM_ACT_GELU && gelu_sig) return launch_cfg<BN, 3, 0, 1, 0, 0, 2>(CVB_GEMM_ARGS);
       if (b16 && !res && e.act == GEMM_ACT_GELU) return launch_cfg<BN, 1, 0, 1, 0, 0, 2>(CVB_GEMM_ARGS);
