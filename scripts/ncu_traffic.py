@@ -1,6 +1,6 @@
 """Folds an `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv` launch list of
 `bench.py --steps 1 --warmup 3 --no-profile` into per-kernel time / DRAM traffic of the timed step
-(-> profiles/r1_ncu_traffic_pipeline_b64.json, read by bench.py for roofline.traffic).
+(-> profiles/r2_ncu_traffic_pipeline_b64.json, read by bench.py for roofline.traffic).
 usage: ncu_traffic.py launches.csv launches_per_step out.json"""
 import collections, csv, json, re, sys
 
@@ -31,6 +31,6 @@ for nm, a in sorted(agg.items(), key=lambda x: -x[1][1]):
                               "dram_GBps": (a[2] + a[3]) / a[1] / 1e9}
     print(f"{nm:26s} n={a[0]:3d} {a[1]*1e3:8.3f} ms share {a[1]/tot:.3f} dram {(a[2]+a[3])/1e9:7.3f} GB -> {(a[2]+a[3])/a[1]/1e9:6.0f} GB/s")
 json.dump({"source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
-                     "on `bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile` (cfg2 pipeline, tiny, B=64); the timed step",
+                     "on `bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile --no-extras` (cfg2 pipeline, tiny, B=64); the timed step",
            "first_kernel": step[0]["name"][:60], "last_kernel": step[-1]["name"][:60],
            "launches_per_step": per_step, "total_ms": tot * 1e3, "kernels": out}, open(dst, "w"), indent=1)
