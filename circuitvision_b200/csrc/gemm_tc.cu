@@ -255,6 +255,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
     uint32_t acc_phase = 0;
     uint32_t nbuf = 0;
     const int sub_row = lane >> 3, sub_c = lane & 7;
+    int cg_rot = cgroup;
     for (int t = tile0; t < n_tiles; t += tile_stride) {
       int tm = t / p.n_tiles_n, nb = t - tm * p.n_tiles_n;
       const int mb = tm * CG + rank;
@@ -283,7 +284,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
       tc::mbar_wait(&tfull[acc], acc_phase);
       tc::tc_fence_after();
 #pragma unroll 1
-      for (int c = cgroup; c < BN / 32; c += EW / 4) {
+      // BN / 32 chunks over EW / 4 warp groups: with 3 chunks and 2 groups one group would take two chunks of EVERY tile;
+      // rotating the start group evens that out over consecutive tiles (the accumulators are double-buffered, so a group
+      // that finishes early moves on to the next tile)
+      const int c_first = cg_rot;
+      if ((BN / 32) % (EW / 4) != 0 && p.rotate) cg_rot = (cg_rot + (EW / 4) - ((BN / 32) % (EW / 4))) % (EW / 4);
+      for (int c = c_first; c < BN / 32; c += EW / 4) {
         const int col0 = nb * BN + c * 32;
         const int ncols = p.N - col0;  // valid columns of this chunk: >= 32, 16 (N % 32 == 16) or <= 0
         uint8_t* buf = bufs + (nbuf % EPI_BUFS) * GEMM_EPI_BUF;
@@ -357,23 +363,34 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
             for (int j = 0; j < 8; j++) { f[4 * j] += rv[j].x; f[4 * j + 1] += rv[j].y; f[4 * j + 2] += rv[j].z; f[4 * j + 3] += rv[j].w; }
           }
           if (MAP == GEMM_MAP_QPOOL && col0 < e.pool_cols) {
-            // q columns of a Q-pooled block: 2 x 2 max over lanes (l, l+1, l+ws, l+ws+1), anchors store 32 values
+            // q columns of a Q-pooled block: the chunk is staged as 16-bit rows (rounding is monotonic, so the maximum of the
+            // rounded values is the rounded maximum), then lane (j, cg) = (lane / 4, lane % 4) reduces pooled token j of
+            // this 32-row block — rows (a, a + 1, a + ws, a + ws + 1) of its anchor a — over 8 columns and stores 16 bytes:
+            // ~25 instructions per thread instead of the 64 shuffles + 64 maxima of a register-resident 2 x 2 maximum
             const int wsl = e.ws;
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
-              float m = fmaxf(f[i], __shfl_down_sync(0xffffffffu, f[i], 1));
-              f[i] = fmaxf(m, __shfl_down_sync(0xffffffffu, m, wsl));
+            for (int j = 0; j < 4; j++) {
+              uint32_t w[4];
+#pragma unroll
+              for (int k = 0; k < 4; k++) w[k] = tc::pack16(e.fp16, f[8 * j + 2 * k], f[8 * j + 2 * k + 1]);
+              *(uint4*)(buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            if (dest[0] >= 0) {
-              uint4* o = (uint4*)(e.pool_out + (long long)dest[0] * e.ld_pool + col0);
+            __syncwarp();
+            {
+              const int pj = lane >> 2, cgq = lane & 3, half = wsl >> 1;
+              const int a = (pj / half) * 2 * wsl + (pj % half) * 2;
+              const int dd = __shfl_sync(0xffffffffu, dest[0], a);
+              uint4 m = *(const uint4*)(buf + a * 64 + ((cgq ^ ((a >> 1) & 3)) << 4));
 #pragma unroll
-              for (int j = 0; j < 4; j++) {
-                uint32_t w[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) w[k] = tc::pack16(e.fp16, f[8 * j + 2 * k], f[8 * j + 2 * k + 1]);
-                o[j] = make_uint4(w[0], w[1], w[2], w[3]);
+              for (int s2 = 1; s2 < 4; s2++) {
+                const int r = a + (s2 & 1) + (s2 >> 1) * wsl;
+                const uint4 o = *(const uint4*)(buf + r * 64 + ((cgq ^ ((r >> 1) & 3)) << 4));
+                m.x = tc::max16x2(e.fp16, m.x, o.x); m.y = tc::max16x2(e.fp16, m.y, o.y);
+                m.z = tc::max16x2(e.fp16, m.z, o.z); m.w = tc::max16x2(e.fp16, m.w, o.w);
               }
+              if (dd >= 0) *(uint4*)(e.pool_out + (long long)dd * e.ld_pool + col0 + cgq * 8) = m;
             }
+            __syncwarp();
             continue;
           }
           if (OUT == 0) {
@@ -404,19 +421,35 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
             tc::tma_store_commit();
           }
         } else if (MAP == GEMM_MAP_POOL2) {
-          // 2 x 2 max over lanes (l, l+1, l+ws, l+ws+1): valid on the anchor lanes, which store 32 contiguous floats
+          // 2 x 2 maximum over rows (a, a + 1, a + ws, a + ws + 1) of each anchor row a: the chunk goes through the swizzled fp32
+          // staging buffer and lane (j, cg) = (lane / 4, lane % 4) reduces pooled token j over 8 columns (two float4 per
+          // row) and stores 32 contiguous bytes; 4 lanes cover a 128-byte line of the pooled row
           const int wsl = e.ws;
 #pragma unroll
-          for (int i = 0; i < 32; i++) {
-            float m = fmaxf(f[i], __shfl_down_sync(0xffffffffu, f[i], 1));
-            f[i] = fmaxf(m, __shfl_down_sync(0xffffffffu, m, wsl));
-          }
-          if (dest[0] >= 0 && col0 < p.N) {
-            float4* o = (float4*)(e.out_f32 + (long long)dest[0] * e.ld_f32 + col0);
+          for (int j = 0; j < 8; j++)
+            *(float4*)(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          __syncwarp();
+          {
+            const int pj = lane >> 2, cgq = lane & 3, half = wsl >> 1;
+            const int a = (pj / half) * 2 * wsl + (pj % half) * 2;
+            const int dd = __shfl_sync(0xffffffffu, dest[0], a);
+            float4 m0 = *(const float4*)(buf + a * 128 + (((2 * cgq) ^ (a & 7)) << 4));
+            float4 m1 = *(const float4*)(buf + a * 128 + (((2 * cgq + 1) ^ (a & 7)) << 4));
 #pragma unroll
-            for (int j = 0; j < 8; j++)
-              if (4 * j < ncols) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            for (int s2 = 1; s2 < 4; s2++) {
+              const int r = a + (s2 & 1) + (s2 >> 1) * wsl;
+              const float4 o0 = *(const float4*)(buf + r * 128 + (((2 * cgq) ^ (r & 7)) << 4));
+              const float4 o1 = *(const float4*)(buf + r * 128 + (((2 * cgq + 1) ^ (r & 7)) << 4));
+              m0.x = fmaxf(m0.x, o0.x); m0.y = fmaxf(m0.y, o0.y); m0.z = fmaxf(m0.z, o0.z); m0.w = fmaxf(m0.w, o0.w);
+              m1.x = fmaxf(m1.x, o1.x); m1.y = fmaxf(m1.y, o1.y); m1.z = fmaxf(m1.z, o1.z); m1.w = fmaxf(m1.w, o1.w);
+            }
+            if (dd >= 0 && col0 + cgq * 8 < p.N) {
+              float4* o = (float4*)(e.out_f32 + (long long)dd * e.ld_f32 + col0 + cgq * 8);
+              o[0] = m0;
+              if (col0 + cgq * 8 + 4 < p.N) o[1] = m1;
+            }
           }
+          __syncwarp();
         } else {
           if (!rba) {
 #pragma unroll
@@ -499,6 +532,8 @@ static int launch_cfg(const __nv_bfloat16* A, long long lda, const __nv_bfloat16
   p.M = M; p.N = N; p.K = K;
   p.n_tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
   p.n_tiles_n = (N + BN - 1) / BN;
+  static const int rotate_on = getenv("CVB_GEMM_ROT") ? atoi(getenv("CVB_GEMM_ROT")) : 1;
+  p.rotate = rotate_on;
   long long tiles = (long long)((p.n_tiles_m + CG - 1) / CG) * p.n_tiles_n;
   const int max_groups = num_sms / CG;
   int grid = (int)(tiles < max_groups ? tiles : max_groups) * CG;

@@ -46,6 +46,7 @@ struct GemmEpilogue {
 struct GemmProblem {
   int M, N, K;
   int n_tiles_m, n_tiles_n;
+  int rotate;  // epilogue: the column-chunk group a warp takes rotates from tile to tile (balances BN / 32 chunks over EW / 4 groups)
 };
 
 // Host launcher.  Returns CV_OK or a CV_ERR_* status (message via cv_last_error()).

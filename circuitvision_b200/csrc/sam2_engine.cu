@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "mlp_fused.cuh"
+#include "patch_embed.cuh"
 #include "sam2_kernels.cuh"
 
 namespace cvb {
@@ -274,7 +275,7 @@ static int gemm(cv_sam2* h, const bf16* A, long long lda, const bf16* W, int M, 
 
 // one Hiera block; X is the fp32 residual stream of the block's stage (updated in place), Xn the next
 // stage's stream for Q-pooled blocks.
-static int run_block(cv_sam2* h, int i, int B, float* X, float* Xn, cudaStream_t st) {
+static int run_block(cv_sam2* h, int i, int B, float* X, float* Xn, cudaStream_t st, bool ln1_done = false) {
   const BlockPlan& p = h->plan[i];
   const std::string pre = "b" + std::to_string(i);
   const int ws = p.ws, H = p.H, W = p.W, Cin = p.dim_in, C = p.dim_out;
@@ -287,8 +288,10 @@ static int run_block(cv_sam2* h, int i, int B, float* X, float* Xn, cudaStream_t
   bf16* AO = BUF<bf16>(h, "AO");
   bf16* Hd = BUF<bf16>(h, "Hd");
   // norm1 (+ window partition with zero pad rows)
-  TRY(launch_ln_rows(X, T, Cin, WF(h, pre + ".n1.g"), WF(h, pre + ".n1.b"), 1e-6f, B, H, W, ws, h->f16, A, nullptr, st));
-  h->launches++;
+  if (!ln1_done) {  // (block 0 after the fused patch embedding: "A" already holds norm1(X) in window-major order)
+    TRY(launch_ln_rows(X, T, Cin, WF(h, pre + ".n1.g"), WF(h, pre + ".n1.b"), 1e-6f, B, H, W, ws, h->f16, A, nullptr, st));
+    h->launches++;
+  }
   GemmEpilogue e;
   e.bias = WF(h, pre + ".qkv.b");
   e.out_bf16 = QKV;
@@ -498,13 +501,28 @@ extern "C" int cv_sam2_forward(cv_sam2* h, const void* images, int input_kind, i
   float* X[4] = {BUF<float>(h, "X0"), BUF<float>(h, "X1"), BUF<float>(h, "X2"), BUF<float>(h, "X3")};
   // ---- patch embed (two-term bf16 split of the pixels) + positional embedding
   (void)mean; (void)istd;
+  bool ln1_fused = false;
   if (input_kind == 0) {
     // raw pixels (exact in bf16); 1/255, mean/std, the conv bias and the positional embedding live in pe.w8 / pos8
-    TRY(launch_im2col_u8raw((const uint8_t*)images, B, 1024, swap_rb, h->f16, A, st));
-    GemmEpilogue e;
-    e.res = WF(h, "pos8"); e.ld_res = E; e.res_row_mod = 65536;
-    e.out_f32 = X[0]; e.ld_f32 = E;
-    TRY(gemm(h, A, PE_K8, WB(h, "pe.w8"), B * 65536, E, PE_K8, e, st));
+    if (patch_embed_supported(E, 1024)) {
+      // pixels -> conv -> + pos -> X0 and, when block 0 is an 8 x 8 windowed block of the same width, its norm1 output as well
+      const BlockPlan& p0 = h->plan[0];
+      ln1_fused = !p0.pool && p0.ws == 8 && p0.dim_in == E && p0.H == 256 && p0.W == 256;
+      PatchEmbedArgs pa;
+      pa.img = (const uint8_t*)images; pa.B = B; pa.S = 1024; pa.swap_rb = swap_rb; pa.fp16 = h->f16;
+      pa.W = WB(h, "pe.w8"); pa.E = E; pa.pos = WF(h, "pos8"); pa.X0 = X[0];
+      pa.gamma = ln1_fused ? WF(h, "b0.n1.g") : nullptr;
+      pa.beta = ln1_fused ? WF(h, "b0.n1.b") : nullptr;
+      pa.eps = 1e-6f;
+      pa.A16 = ln1_fused ? A : nullptr;
+      TRY(patch_embed_launch(pa, device_sm_count(), st));
+    } else {
+      TRY(launch_im2col_u8raw((const uint8_t*)images, B, 1024, swap_rb, h->f16, A, st));
+      GemmEpilogue e;
+      e.res = WF(h, "pos8"); e.ld_res = E; e.res_row_mod = 65536;
+      e.out_f32 = X[0]; e.ld_f32 = E;
+      TRY(gemm(h, A, PE_K8, WB(h, "pe.w8"), B * 65536, E, PE_K8, e, st));
+    }
   } else {
     TRY(launch_im2col_f32((const float*)images, B, 1024, h->f16, A, st));
     GemmEpilogue e;
@@ -518,7 +536,7 @@ extern "C" int cv_sam2_forward(cv_sam2* h, const void* images, int input_kind, i
   int stage = 0;
   for (size_t i = 0; i < h->plan.size(); i++) {
     if (h->plan[i].pool) stage++;
-    TRY(run_block(h, (int)i, B, h->plan[i].pool ? X[stage - 1] : X[stage], X[stage], st));
+    TRY(run_block(h, (int)i, B, h->plan[i].pool ? X[stage - 1] : X[stage], X[stage], st, i == 0 && ln1_fused));
   }
   // ---- neck (level 3 lateral, level 2 lateral + top-down + dense prompt) and the folded conv_s0 / conv_s1
   float* keys32 = BUF<float>(h, "keys32");

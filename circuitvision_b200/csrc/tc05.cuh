@@ -251,6 +251,14 @@ __device__ __forceinline__ uint32_t pack16(int fp16, float a, float b) {
   return *(uint32_t*)&t;
 }
 
+// element-wise maximum of two packed 16-bit pairs (fp16 or bf16)
+__device__ __forceinline__ uint32_t max16x2(int fp16, uint32_t a, uint32_t b) {
+  uint32_t r;
+  if (fp16) asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  else asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
