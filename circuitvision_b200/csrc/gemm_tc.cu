@@ -584,7 +584,10 @@ static int launch_bn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16*
     // GELU form of the 16-bit-output epilogues (act.cuh): 2 = tanh form (default), 1 = sigmoid form, 0 = A&S erf
     static const int gelu_form = getenv("CVB_GELU_FORM") ? atoi(getenv("CVB_GELU_FORM")) : 2;
     const bool gelu_sig = gelu_form == 1, gelu_tanh = gelu_form == 2;
-    if (pairs_on && BN >= 128 && BN >= pair_min_bn && K >= 256 && M >= 1024) {
+    // 192- / 224-wide tiles: only the long-K residual GEMMs (fc2 of stages 3-4) gain from the pair (their operand stream is what
+    // binds them: +7 % at N384 K1536, +10 % at N448 K1792); the K = 384 qkv shapes lose 7 % to the pair's extra synchronisation
+    const bool pair_fc2 = BN >= 192 && f32 && res && K >= 1024;
+    if (pairs_on && BN >= 128 && (BN >= pair_min_bn || pair_fc2) && K >= 256 && M >= 1024) {
       if (b16 && !res && e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 0, 1, 0, 0, 2>(CVB_GEMM_ARGS);
       // 16 epilogue warps for the GELU epilogue of the CTA-pair shapes (fc1 of stages 3-4, epilogue-bound): 844 -> 880 TFLOP/s on
       // M262144 N1536 K384 once the MMA issue no longer co-limited (CVB_GELU_EW16=0 restores 8)
