@@ -374,7 +374,10 @@ __device__ __forceinline__ WinItem win_item(const AttnParams& p, int n_items, in
   return w;
 }
 
-template <int D>
+// UNI: every warp's rows lie in one window (8 x 8 windows with 128-row items, 14 x 14 with window-aligned 98-row items), so whole
+// 32-column chunks are visible to all of them and skip the per-element visibility tests (they were half of the softmax
+// instructions); the other geometries keep the masked code only (a kernel carrying both paths ran them 10-15 % slower).
+template <int D, bool UNI>
 __global__ void __launch_bounds__(AW_THREADS, 1)
 k_attn_win(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
            const __grid_constant__ CUtensorMap tv, AttnParams p, int n_items) {
@@ -552,6 +555,11 @@ k_attn_win(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUten
         const bool sees = c_hi > c_lo;
         const int cb = p.skip_chunks ? (__reduce_min_sync(0xffffffffu, sees ? c_lo : ATT_BN) >> 5) : 0;
         const int ce = p.skip_chunks ? ((__reduce_max_sync(0xffffffffu, sees ? c_hi : 0) + 31) >> 5) : ATT_BN / 32;
+        // columns every row of the warp sees: chunks inside [u_lo, u_hi) need no per-element visibility test (all chunks of the
+        // 8 x 8 and 14 x 14 window cases except the last partial one; the masks were half of the softmax instructions there)
+        // (rows past the item's last row are never stored: whatever they compute is "don't care", they do not restrict the range)
+        const int u_lo = UNI ? __reduce_max_sync(0xffffffffu, row_ok ? (sees ? c_lo : ATT_BN) : 0) : ATT_BN;
+        const int u_hi = UNI ? __reduce_min_sync(0xffffffffu, row_ok ? (sees ? c_hi : 0) : ATT_BN) : 0;
         tc::mbar_wait(&s_full[g], s_uses & 1);
         s_uses++;
         tc::tc_fence_after();
@@ -562,10 +570,22 @@ k_attn_win(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUten
           uint32_t v[32];
           tc::tmem_ld_32x32(tS + c * 32, v);
           tc::tmem_ld_wait();
+          if (UNI && c * 32 >= u_lo && c * 32 + 32 <= u_hi) {
+            float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
 #pragma unroll
-          for (int i = 0; i < 32; i++) {
-            int col = c * 32 + i;
-            if (col >= c_lo && col < c_hi) tmx = fmaxf(tmx, __uint_as_float(v[i]));
+            for (int i = 4; i < 32; i += 4) {
+              m0 = fmaxf(m0, __uint_as_float(v[i]));
+              m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+              m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+              m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+            }
+            tmx = fmaxf(tmx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+              int col = c * 32 + i;
+              if (col >= c_lo && col < c_hi) tmx = fmaxf(tmx, __uint_as_float(v[i]));
+            }
           }
         }
         const float tm = tmx * p.scale_log2;  // -inf when the row sees nothing in this tile
@@ -604,15 +624,28 @@ k_attn_win(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUten
           uint32_t v[32];
           tc::tmem_ld_32x32(tS + c * 32, v);
           tc::tmem_ld_wait();
+          if (UNI && c * 32 >= u_lo && c * 32 + 32 <= u_hi) {
+            float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const int col = c * 32 + i;
-            float p0 = ex2(fmaf(__uint_as_float(v[i]), p.scale_log2, -mr));
-            float p1 = ex2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -mr));
-            if (col < c_lo || col >= c_hi) p0 = 0.f;
-            if (col + 1 < c_lo || col + 1 >= c_hi) p1 = 0.f;
-            rowsum += p0 + p1;
-            pk[c][i >> 1] = tc::pack16(p.fp16, p0, p1);
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = ex2(fmaf(__uint_as_float(v[i]), p.scale_log2, -mr));
+              const float p1 = ex2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -mr));
+              rs0 += p0;
+              rs1 += p1;
+              pk[c][i >> 1] = tc::pack16(p.fp16, p0, p1);
+            }
+            rowsum += rs0 + rs1;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const int col = c * 32 + i;
+              float p0 = ex2(fmaf(__uint_as_float(v[i]), p.scale_log2, -mr));
+              float p1 = ex2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -mr));
+              if (col < c_lo || col >= c_hi) p0 = 0.f;
+              if (col + 1 < c_lo || col + 1 >= c_hi) p1 = 0.f;
+              rowsum += p0 + p1;
+              pk[c][i >> 1] = tc::pack16(p.fp16, p0, p1);
+            }
           }
         }
 #pragma unroll
@@ -680,13 +713,22 @@ static int attn_launch_d(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
   }
   static std::atomic<unsigned long long> attr_set_w{0};
   if (cvb_once_per_device(attr_set_w)) {
-    cudaError_t e = cudaFuncSetAttribute(k_attn_win<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, aw_smem<D>());
+    cudaError_t e = cudaFuncSetAttribute(k_attn_win<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, aw_smem<D>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_win<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, aw_smem<D>());
     if (e != cudaSuccess) return cvb_fail_cuda(e, "cudaFuncSetAttribute(k_attn_win)");
   }
   const int n_items = ((p.Mq + p.q_rows - 1) / p.q_rows) * p.heads;
   const int n_pairs = (n_items + 1) / 2;
   const int grid = n_pairs < device_sm_count() ? n_pairs : device_sm_count();
-  CVB_LAUNCH((k_attn_win<D>), dim3(grid), dim3(AW_THREADS), aw_smem<D>(), st, tq, tk, tv, p, n_items);
+  // rows 32 w .. 32 w + 31 of an item in one window: windows of a multiple of 32 rows with 32-aligned items, or items that do
+  // not cross a window at all
+  static const int uni_on = getenv("CVB_ATTN_UNI") ? atoi(getenv("CVB_ATTN_UNI")) : 1;
+  const bool uni = uni_on && ((p.Wq % 32 == 0 && p.q_rows % 32 == 0) || (p.Wq % p.q_rows == 0));
+  if (uni) {
+    CVB_LAUNCH((k_attn_win<D, true>), dim3(grid), dim3(AW_THREADS), aw_smem<D>(), st, tq, tk, tv, p, n_items);
+  } else {
+    CVB_LAUNCH((k_attn_win<D, false>), dim3(grid), dim3(AW_THREADS), aw_smem<D>(), st, tq, tk, tv, p, n_items);
+  }
   return CV_OK;
 }
 
