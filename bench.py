@@ -258,13 +258,14 @@ def _shape_row(r, steps, tens_peak, hbm_peak):
     if gb:
         row["tensor_frac"] = gb[1] / sec / 1e12 / tens_peak
         row["hbm_frac"] = gb[0] / sec / 1e9 / hbm_peak
-    elif r["name"].startswith(("attn", "mlp")):
+    elif r["name"].startswith(("attn", "mlp", "patch_embed")):
         row["tensor_frac"] = row["rate_T_per_s"] / tens_peak
     return row
 
 
-TENSOR_KERNELS = ("k_gemm_tc", "k_attn_tc", "k_attn_global", "k_mlp_fused")
-ALIAS = {"gemm ": "k_gemm_tc", "attn_global ": "k_attn_global", "attn ": "k_attn_tc", "ln_rows ": "k_ln_rows", "mlp ": "k_mlp_fused"}
+TENSOR_KERNELS = ("k_gemm_tc", "k_attn_tc", "k_attn_global", "k_mlp_fused", "k_patch_embed")
+ALIAS = {"gemm ": "k_gemm_tc", "attn_global ": "k_attn_global", "attn ": "k_attn_tc", "ln_rows ": "k_ln_rows", "mlp ": "k_mlp_fused",
+         "patch_embed ": "k_patch_embed"}
 
 
 def fold_table(table):
