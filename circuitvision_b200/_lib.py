@@ -39,6 +39,15 @@ CV_BOX_ZERO_IN_MASK, CV_BOX_IS_COMPONENT, CV_BOX_IS_SOURCE, CV_BOX_IS_TERMINAL =
 DEFAULT_CAPS = dict(max_external=32768, max_contours=2560, max_points=262144, max_pairs=8192)
 
 
+class cv_gemm_epilogue(C.Structure):
+    """include/cv_b200.h cv_gemm_epilogue (field order and types must match)."""
+    _fields_ = [("bias", C.c_void_p), ("act", C.c_int), ("res_before_act", C.c_int), ("residual", C.c_void_p),
+                ("ld_res", C.c_longlong), ("res_row_mod", C.c_longlong), ("out_f32", C.c_void_p), ("ld_f32", C.c_longlong),
+                ("out_16", C.c_void_p), ("ld_16", C.c_longlong), ("map_mode", C.c_int), ("ws", C.c_int), ("nwx", C.c_int),
+                ("nwy", C.c_int), ("H", C.c_int), ("W", C.c_int), ("cout", C.c_int), ("pool_cols", C.c_int),
+                ("pool_out", C.c_void_p), ("ld_pool", C.c_longlong), ("operand_fp16", C.c_int)]
+
+
 def _declare(lib):
     vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
     lib.cv_last_error.restype = C.c_char_p
@@ -60,6 +69,8 @@ def _declare(lib):
     lib.cv_ccl_label.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, sz, vp]
     ll = C.c_longlong
     lib.cv_gemm_bf16.argtypes = [vp, ll, vp, ll, i32, i32, i32, vp, i32, vp, ll, vp, ll, vp, ll, vp]
+    lib.cv_gemm_ex.argtypes = [vp, ll, vp, ll, i32, i32, i32, C.POINTER(cv_gemm_epilogue), vp]
+    lib.cv_attn_set_trace.argtypes = [vp]
     lib.cv_mlp_fused.argtypes = [vp, i32, i32, vp, vp, C.c_float, vp, vp, vp, vp, i32, vp]
     lib.cv_attention_bf16.argtypes = [vp, ll, i32, i32, vp, ll, i32, i32, vp, ll, i32, i32, i32, i32, i32, i32, i32,
                                       i32, C.c_float, vp, ll, vp]

@@ -34,7 +34,26 @@ struct AttnParams {
                             // split of one window, so that an item never straddles windows it does not need
   __nv_bfloat16* out;       // [Mq, heads*96]
   long long ld_out;
+  unsigned long long* trace;  // debug timeline of CTA (0, 0) of the global kernel (cv_attn_set_trace), else nullptr
 };
+
+// Debug timeline (scripts/attn_trace.py): one record (event, index, %globaltimer) per pipeline event of CTA (0, 0).
+// Records go to a shared-memory array (a global atomic per event costs the recording warp ~0.5 us and distorts the timeline);
+// slot = ev * 64 + idx (idx < 64), dumped by attn_trace_dump at the end of the kernel.
+constexpr int ATT_TRACE_SLOTS = 8 * 64;
+__device__ __forceinline__ void attn_trace(const AttnParams& p, unsigned long long* tbuf, unsigned ev, unsigned idx) {
+  if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && idx < 64) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    tbuf[ev * 64 + idx] = ((unsigned long long)(ev * 4096u + idx) << 44) | (t & 0xFFFFFFFFFFFull);
+  }
+}
+__device__ __forceinline__ void attn_trace_dump(const AttnParams& p, const unsigned long long* tbuf) {
+  if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) {
+    for (int i = threadIdx.x; i < ATT_TRACE_SLOTS; i += blockDim.x) p.trace[1 + i] = tbuf[i];
+    if (threadIdx.x == 0) p.trace[0] = ATT_TRACE_SLOTS;
+  }
+}
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -100,7 +119,7 @@ k_attn_global(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
   uint64_t* o_full = bars + 13;    // [2]
   uint32_t* tmem_slot = (uint32_t*)(bars + 15);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // shuffle: warp-uniform for the compiler
   const int q0 = blockIdx.x * 2 * ATT_BM;
   const int head = blockIdx.y;
   const int kv_start = (q0 / p.Wq) * p.Wkv;
@@ -128,7 +147,7 @@ k_attn_global(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -339,6 +358,286 @@ k_attn_global(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CU
   }
 }
 
+// Two softmax threads per query row (k_attn_global2): ncu of k_attn_global showed its softmax warps neither XU- nor issue-bound
+// (two warps per scheduler at IPC 0.33: every warp is one long dependent stream of TMEM load -> 32 exponentials -> TMEM store) and
+// waiting for S 36 % of the time because softmax -> P V -> Q K^T of ONE query tile is a serial chain (P overwrites S).  Here a
+// row's 128 scores are split between two warps of the same TMEM lane quadrant (columns 0-63 / 64-127): twice the warps per
+// scheduler hide the latencies, and the chain's softmax link is half as long.  The two threads of a row agree on the reference
+// maximum through a small shared-memory exchange and a 64-thread named barrier per key tile; the P of the upper half lives in
+// the upper half's own S columns (64..95), so no thread overwrites scores its partner has not read yet.
+constexpr int AG2_THREADS = 640;
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+template <int D, bool EXP_FMA>
+__global__ void __launch_bounds__(AG2_THREADS, 1)
+k_attn_global2(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+               const __grid_constant__ CUtensorMap tv, AttnParams p) {
+  constexpr int ATT_D = D, ATT_TILE_BYTES = att_tile_bytes<D>(), DH = D / 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;                      // [2]
+  uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;   // [2]
+  uint8_t* sV = sK + 2 * ATT_TILE_BYTES;   // [2]
+  float* xch = (float*)(sV + 2 * ATT_TILE_BYTES);  // [3 slots][2 tiles][2 halves][128 rows]: tile maxima (two slots) and row sums
+  unsigned long long* tbuf = (unsigned long long*)(xch + 3 * 2 * 2 * 128);  // debug timeline (ATT_TRACE_SLOTS records)
+  uint64_t* bars = (uint64_t*)(tbuf + ATT_TRACE_SLOTS);
+  uint64_t* q_full = bars;         // 1
+  uint64_t* k_full = bars + 1;     // [2]
+  uint64_t* k_empty = bars + 3;    // [2]
+  uint64_t* v_full = bars + 5;     // [2]
+  uint64_t* v_empty = bars + 7;    // [2]
+  uint64_t* s_full = bars + 9;     // [2] per query tile
+  uint64_t* p_full = bars + 11;    // [2]
+  uint64_t* o_full = bars + 13;    // [2]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 15);
+
+  // warp index through a shuffle: tells the compiler it is warp-uniform, so the role branches are uniform branches and the MMA
+  // warp's descriptor arithmetic can live in uniform registers (CUTLASS's canonical_warp_idx_sync trick)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 2 * ATT_BM;
+  const int head = blockIdx.y;
+  const int kv_start = (q0 / p.Wq) * p.Wkv;
+  const int n_tiles = p.Wkv / ATT_BN;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tq);
+    tc::prefetch_tmap(&tk);
+    tc::prefetch_tmap(&tv);
+  }
+  if (warp == 1 && lane == 0) {
+    tc::mbar_init(q_full, 1);
+    for (int i = 0; i < 2; i++) {
+      tc::mbar_init(&k_full[i], 1);
+      tc::mbar_init(&k_empty[i], 1);
+      tc::mbar_init(&v_full[i], 1);
+      tc::mbar_init(&v_empty[i], 1);
+      tc::mbar_init(&s_full[i], 1);
+      tc::mbar_init(&p_full[i], 8);  // one arrival per softmax warp of the tile
+      tc::mbar_init(&o_full[i], 1);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc<512>(tmem_slot);
+  if (p.trace)
+    for (int i = threadIdx.x; i < ATT_TRACE_SLOTS; i += AG2_THREADS) tbuf[i] = 0ull;
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tc::mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+      for (int g = 0; g < 2; g++) {
+        tc::tma_load_2d(sQ + g * ATT_TILE_BYTES, &tq, q_full, p.qcol0 + head * ATT_D, q0 + g * ATT_BM);
+        if (D > 64) tc::tma_load_2d(sQ + g * ATT_TILE_BYTES + ATT_BM * 128, &tq, q_full, p.qcol0 + head * ATT_D + 64, q0 + g * ATT_BM);
+      }
+      for (int j = 0; j < n_tiles; j++) {
+        const int s = j & 1;
+        const uint32_t par = ((j >> 1) & 1) ^ 1;
+        const int row = kv_start + j * ATT_BN;
+        tc::mbar_wait(&k_empty[s], par);
+        tc::mbar_arrive_expect_tx(&k_full[s], ATT_TILE_BYTES);
+        uint8_t* k = sK + s * ATT_TILE_BYTES;
+        tc::tma_load_2d(k, &tk, &k_full[s], p.kcol0 + head * ATT_D, row);
+        if (D > 64) tc::tma_load_2d(k + ATT_BN * 128, &tk, &k_full[s], p.kcol0 + head * ATT_D + 64, row);
+        tc::mbar_wait(&v_empty[s], par);
+        tc::mbar_arrive_expect_tx(&v_full[s], ATT_TILE_BYTES);
+        uint8_t* v = sV + s * ATT_TILE_BYTES;
+        tc::tma_load_2d(v, &tv, &v_full[s], p.vcol0 + head * ATT_D, row);
+        if (D > 64) tc::tma_load_2d(v + ATT_BN * 128, &tv, &v_full[s], p.vcol0 + head * ATT_D + 64, row);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc_qk = tc::idesc_bf16(ATT_BM, ATT_BN, false, false, p.fp16 != 0);
+    const uint32_t idesc_pv = tc::idesc_bf16(ATT_BM, ATT_D, false, true, p.fp16 != 0);  // A = P (TMEM, K-major), B = V MN-major
+    auto issue_qk = [&](int g, int j, uint64_t* also) {
+      const uint64_t dq = tc::desc_kmajor(tc::smem_u32(sQ + g * ATT_TILE_BYTES));
+      const uint64_t dk = tc::desc_kmajor(tc::smem_u32(sK + (j & 1) * ATT_TILE_BYTES));
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; k++) {
+          const uint32_t off = ((k >> 2) * (ATT_BM * 128) + (k & 3) * 32) >> 4;  // descriptor address units of 16 bytes
+          tc::mma_f16_ss(tmem_base + g * 128, dq + off, dk + off, idesc_qk, k > 0 ? 1u : 0u);
+        }
+        tc::mma_commit(&s_full[g]);
+        if (also) tc::mma_commit(also);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int g, int j, uint64_t* also) {
+      const uint64_t dv = tc::smem_desc_sw128(tc::smem_u32(sV + (j & 1) * ATT_TILE_BYTES), ATT_BN * 128, 1024);
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int k = 0; k < ATT_BN / 16; k++)
+          // A: 16 keys = 8 packed columns; keys 0-63 sit at columns 0-31 of the tile's S region, keys 64-127 at columns 64-95
+          tc::mma_f16_ts(tmem_base + 256 + g * ATT_D, tmem_base + g * 128 + (k >> 2) * 64 + (k & 3) * 8, dv + (k * 2048 >> 4), idesc_pv,
+                         (j > 0 || k > 0) ? 1u : 0u);
+        tc::mma_commit(&o_full[g]);
+        if (also) tc::mma_commit(also);
+      }
+      __syncwarp();
+    };
+    tc::mbar_wait(q_full, 0);
+    tc::mbar_wait(&k_full[0], 0);
+    tc::tc_fence_after();
+    issue_qk(0, 0, nullptr);
+    issue_qk(1, 0, &k_empty[0]);
+    for (int j = 0; j < n_tiles; j++) {
+      const bool more = j + 1 < n_tiles;
+      tc::mbar_wait(&v_full[j & 1], (j >> 1) & 1);
+      tc::mbar_wait(&p_full[0], j & 1);
+      tc::tc_fence_after();
+      if (lane == 0) attn_trace(p, tbuf, 1, j * 2);
+      issue_pv(0, j, nullptr);
+      if (lane == 0) attn_trace(p, tbuf, 6, j * 2);
+      if (more) {
+        tc::mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+        tc::tc_fence_after();
+        if (lane == 0) attn_trace(p, tbuf, 7, j * 2);
+        issue_qk(0, j + 1, nullptr);
+      }
+      if (lane == 0) attn_trace(p, tbuf, 2, j * 2);
+      tc::mbar_wait(&p_full[1], j & 1);
+      tc::tc_fence_after();
+      if (lane == 0) attn_trace(p, tbuf, 1, j * 2 + 1);
+      issue_pv(1, j, &v_empty[j & 1]);
+      if (lane == 0) attn_trace(p, tbuf, 6, j * 2 + 1);
+      if (more) issue_qk(1, j + 1, &k_empty[(j + 1) & 1]);
+      if (lane == 0) attn_trace(p, tbuf, 2, j * 2 + 1);
+    }
+  } else if (warp >= 4) {
+    const int g = (warp - 4) >> 3;         // query tile of this warp
+    const int ch = ((warp - 4) >> 2) & 1;  // column half of the score tile
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const int grow = q0 + g * ATT_BM + r;
+    const int pair_id = 1 + g * 4 + quad;  // named barrier of the two warps that share these 32 rows
+    const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
+    const uint32_t tS = tmem_base + lane_sel + g * 128 + ch * 64;   // my 64 score columns; my P goes over their first 32
+    const uint32_t tO = tmem_base + lane_sel + 256 + g * ATT_D + ch * DH;
+    float* xme = xch + (g * 2 + ch) * 128 + r;        // + slot * 512
+    float* xpt = xch + (g * 2 + (ch ^ 1)) * 128 + r;
+    float m_ref = 0.f, l = 0.f;
+    for (int j = 0; j < n_tiles; j++) {
+      tc::mbar_wait(&s_full[g], j & 1);
+      tc::tc_fence_after();
+      if (ch == 0 && quad == 0 && lane == 0) attn_trace(p, tbuf, 4, j * 2 + g);
+      if (j == 0) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          uint32_t v[32];
+          tc::tmem_ld_32x32(tS + c * 32, v);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+        xme[2 * 512] = mx;
+        pair_sync(pair_id);
+        mx = fmaxf(mx, xpt[2 * 512]);
+        m_ref = mx * p.scale_log2;
+      }
+      float tmax = -INFINITY;
+      uint64_t rs2 = pk2(0.f, 0.f);
+      const uint64_t sc2 = pk2(p.scale_log2, p.scale_log2), mr2 = pk2(-m_ref, -m_ref);
+      uint32_t v[2][32];
+      tc::tmem_ld_32x32(tS, v[0]);
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        tc::tmem_ld_wait();
+        if (c + 1 < 2) tc::tmem_ld_32x32(tS + (c + 1) * 32, v[(c + 1) & 1]);
+        uint32_t pk[16];
+        float pe[32];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float s0 = __uint_as_float(v[c & 1][i]), s1 = __uint_as_float(v[c & 1][i + 1]);
+          asm("max.f32 %0, %0, %1, %2;" : "+f"(tmax) : "f"(s0), "f"(s1));
+          float x0, x1;
+          up2(fma2(pk2(s0, s1), sc2, mr2), x0, x1);
+          if (EXP_FMA && ((i >> 1) % 3) == 2) {  // every third pair: exponentials on the FMA pipe
+            ex2_poly2(x0, x1, pe[i], pe[i + 1]);
+          } else {
+            pe[i] = ex2(x0);
+            pe[i + 1] = ex2(x1);
+          }
+          const uint64_t pp = pk2(pe[i], pe[i + 1]);
+          asm("add.rn.f32x2 %0, %0, %1;" : "+l"(rs2) : "l"(pp));
+        }
+        if (p.fp16) {
+#pragma unroll
+          for (int i = 0; i < 16; i++) pk[i] = tc::pack16(1, pe[2 * i], pe[2 * i + 1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; i++) pk[i] = tc::pack16(0, pe[2 * i], pe[2 * i + 1]);
+        }
+        tc::tmem_st_32x16(tS + c * 16, pk);  // P over the already-consumed head of my own score columns
+      }
+      float rs_lo, rs_hi;
+      up2(rs2, rs_lo, rs_hi);
+      const float rowsum = rs_lo + rs_hi;
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&p_full[g]);
+      if (ch == 0 && quad == 0 && lane == 0) attn_trace(p, tbuf, 5, j * 2 + g);
+      l += rowsum;
+      // both threads of the row must take the same rescale decision: exchange the half-row maxima (slot = tile parity)
+      xme[(j & 1) * 512] = tmax;
+      pair_sync(pair_id);
+      tmax = fmaxf(tmax, xpt[(j & 1) * 512]);
+      const float tm = tmax * p.scale_log2;
+      const bool need = tm > m_ref + 8.0f;
+      if (__any_sync(0xffffffffu, need)) {
+        // rescale my half of O (and my partial l) to the new reference once P V of this tile has been accumulated
+        tc::mbar_wait(&o_full[g], j & 1);
+        tc::tc_fence_after();
+        const float alpha = need ? ex2(m_ref - tm) : 1.0f;
+#pragma unroll
+        for (int c = 0; c < DH / 16; c++) {
+          uint32_t w[16];
+          tc::tmem_ld_32x16(tO + c * 16, w);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; i++) w[i] = __float_as_uint(__uint_as_float(w[i]) * alpha);
+          tc::tmem_st_32x16(tO + c * 16, w);
+        }
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        l *= alpha;
+        if (need) m_ref = tm;
+      }
+    }
+    tc::mbar_wait(&o_full[g], (n_tiles - 1) & 1);
+    tc::tc_fence_after();
+    xme[2 * 512] = l;  // (slot 2 was last used before tile 0's first barrier)
+    pair_sync(pair_id);
+    l += xpt[2 * 512];
+    const float inv = 1.f / l;
+    __nv_bfloat16* o = p.out + (long long)grow * p.ld_out + head * ATT_D + ch * DH;
+#pragma unroll
+    for (int c = 0; c < DH / 16; c++) {
+      uint32_t w[16];
+      tc::tmem_ld_32x16(tO + c * 16, w);
+      tc::tmem_ld_wait();
+      if (grow < p.Mq) {
+        uint32_t q[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) q[k] = tc::pack16(p.fp16, __uint_as_float(w[2 * k]) * inv, __uint_as_float(w[2 * k + 1]) * inv);
+        *(uint4*)(o + c * 16) = make_uint4(q[0], q[1], q[2], q[3]);
+        *(uint4*)(o + c * 16 + 8) = make_uint4(q[4], q[5], q[6], q[7]);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  attn_trace_dump(p, tbuf);
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ windowed attention
 // Persistent kernel for every block-diagonal case that is not global (Hiera's 8x8 / 4x4 / 14x14 / 7x7 windows and their
 // Q-pooled variants).  These are HBM-bound (a few hundred keys per query), so the design goal is streaming efficiency:
@@ -397,7 +696,7 @@ k_attn_win(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUten
   uint64_t* o_free = s_full + 6;            // [2]
   uint32_t* tmem_slot = (uint32_t*)(s_full + 8);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // shuffle: warp-uniform for the compiler
   const int n_pairs = (n_items + 1) / 2;
 
   if (warp == 0 && lane == 0) {
@@ -424,7 +723,7 @@ k_attn_win(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUten
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     // ===================== TMA producer: Q per slot, K/V through the ring in MMA consumption order
@@ -691,6 +990,7 @@ k_attn_win(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUten
 }
 
 int device_sm_count();
+static unsigned long long* g_attn_trace = nullptr;
 
 template <int D>
 static int attn_launch_d(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, bool glob,
@@ -704,6 +1004,24 @@ static int attn_launch_d(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
     }
     // CVB_ATTN_EXPFMA=0: every exponential on the XU pipe (A/B switch)
     static const bool exp_fma = getenv("CVB_ATTN_EXPFMA") ? atoi(getenv("CVB_ATTN_EXPFMA")) != 0 : true;
+    // two softmax threads per row (k_attn_global2): same speed within run-to-run noise (5.47-5.97 ms against 5.47-5.81 ms per
+    // step over repeated same-box runs), so the one-thread-per-row kernel stays the default; scripts/attn_trace.py uses this one
+    static const bool two = getenv("CVB_ATTN_G2") ? atoi(getenv("CVB_ATTN_G2")) != 0 : false;
+    if (two) {
+      constexpr int smem2 = ag_smem<D>() + 3 * 2 * 2 * 128 * 4 + ATT_TRACE_SLOTS * 8;
+      static std::atomic<unsigned long long> attr_set_2{0};
+      if (cvb_once_per_device(attr_set_2)) {
+        cudaError_t e = cudaFuncSetAttribute(k_attn_global2<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_global2<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+        if (e != cudaSuccess) return cvb_fail_cuda(e, "cudaFuncSetAttribute(k_attn_global2)");
+      }
+      if (exp_fma) {
+        CVB_LAUNCH((k_attn_global2<D, true>), dim3(p.Mq / (2 * ATT_BM), p.heads), dim3(AG2_THREADS), smem2, st, tq, tk, tv, p);
+      } else {
+        CVB_LAUNCH((k_attn_global2<D, false>), dim3(p.Mq / (2 * ATT_BM), p.heads), dim3(AG2_THREADS), smem2, st, tq, tk, tv, p);
+      }
+      return CV_OK;
+    }
     if (exp_fma) {
       CVB_LAUNCH((k_attn_global<D, true>), dim3(p.Mq / (2 * ATT_BM), p.heads), dim3(AG_THREADS), ag_smem<D>(), st, tq, tk, tv, p);
     } else {
@@ -773,6 +1091,7 @@ int attn_tc_launch(const __nv_bfloat16* q, long long ldq, int qcols, int qcol0, 
     }
   }
   p.out = out; p.ld_out = ld_out;
+  p.trace = g_attn_trace;
   const bool glob = Wq == Wkv && (Wkv % ATT_BN) == 0 && (Wq % (2 * ATT_BM)) == 0 && (Mq % (2 * ATT_BM)) == 0;
   // algorithmic flops: every query row against the keys of its own window, QK^T and PV (padded head dim as executed)
   cvb_next_work(4.0 * (double)Mq * (double)Wkv * D * heads);
@@ -787,6 +1106,11 @@ int attn_tc_launch(const __nv_bfloat16* q, long long ldq, int qcols, int qcol0, 
 }  // namespace cvb
 
 using namespace cvb;
+
+extern "C" int cv_attn_set_trace(void* device_buffer) {
+  g_attn_trace = (unsigned long long*)device_buffer;
+  return CV_OK;
+}
 
 extern "C" int cv_attention_bf16(const void* qkv_q, long long ldq, int qcols, int qcol0, const void* qkv_k,
                                  long long ldk, int kcols, int kcol0, const void* qkv_v, long long ldv, int vcols,

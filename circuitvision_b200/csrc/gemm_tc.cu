@@ -140,7 +140,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
   uint64_t* tempty = tfull + 2;              // [2]
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // shuffle: warp-uniform for the compiler
   // CG == 2: a tile is 256 rows; CTA `rank` of the pair owns rows [tile_m*256 + rank*128, +128)
   const int rank = CG == 2 ? (int)tc::cluster_ctarank() : 0;
   const int n_tiles = ((p.n_tiles_m + CG - 1) / CG) * p.n_tiles_n;
@@ -171,7 +171,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
   __syncthreads();
   if (CG == 2) tc::cluster_sync();  // the peer's barriers are initialised before anything arrives on them
   tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     // ===================== TMA producer
@@ -685,6 +685,31 @@ extern "C" int cv_gemm_bf16(const void* A, long long lda, const void* W, long lo
   e.ld_f32 = ld_f32;
   e.out_bf16 = (__nv_bfloat16*)out_bf16;
   e.ld_bf16 = ld_bf16;
+  return gemm_tc_launch((const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)W, ldw, M, N, K, e, device_sm_count(),
+                        (cudaStream_t)stream);
+}
+
+extern "C" int cv_gemm_ex(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
+                          const cv_gemm_epilogue* x, void* stream) {
+  cvb_reset_launches();
+  if (!A || !W || !x || (!x->out_f32 && !x->out_16)) return cvb_fail(CV_ERR_INVALID, "cv_gemm_ex: null pointer");
+  GemmEpilogue e;
+  e.bias = x->bias;
+  e.act = x->act;
+  e.res_before_act = x->res_before_act;
+  e.res = x->residual;
+  e.ld_res = x->ld_res;
+  e.res_row_mod = x->res_row_mod;
+  e.out_f32 = x->out_f32;
+  e.ld_f32 = x->ld_f32;
+  e.out_bf16 = (__nv_bfloat16*)x->out_16;
+  e.ld_bf16 = x->ld_16;
+  e.map_mode = x->map_mode;
+  e.ws = x->ws; e.nwx = x->nwx; e.nwy = x->nwy; e.H = x->H; e.W = x->W; e.cout = x->cout;
+  e.pool_cols = x->pool_cols;
+  e.pool_out = (__nv_bfloat16*)x->pool_out;
+  e.ld_pool = x->ld_pool;
+  e.fp16 = x->operand_fp16;
   return gemm_tc_launch((const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)W, ldw, M, N, K, e, device_sm_count(),
                         (cudaStream_t)stream);
 }

@@ -80,7 +80,7 @@ k_patch_embed(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   uint64_t* t_empty = bars + 9 + PE_NACC;   // [PE_NACC]
   uint32_t* tmem_slot = (uint32_t*)(bars + 9 + 2 * PE_NACC);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // shuffle: warp-uniform for the compiler
   const int G = a.S >> 2;                   // tokens per image row
   const int tiles_per_row = G >> 7;
   const int tiles_per_img = G * tiles_per_row;
@@ -117,7 +117,7 @@ k_patch_embed(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     if (lane == 0) {

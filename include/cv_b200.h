@@ -145,6 +145,32 @@ int cv_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int
                  int act, const float* residual, long long ld_res, float* out_f32, long long ld_f32, void* out_bf16,
                  long long ld_bf16, void* stream);
 
+/* The same GEMM with every epilogue the SAM 2.1 engine uses (the entry the parity tests drive; cv_sam2_forward calls the same
+ * launcher).  map_mode: 0 identity, 1 window un-partition (Hiera window_unpartition), 2 ConvTranspose2d(k=2,s=2) pixel shuffle,
+ * 3 2x2 max-pool of window-major rows into the pooled grid (Q-pool shortcut, do_pool(proj(x))), 4 qkv of a Q-pooled block: the
+ * first pool_cols columns are 2x2 max-pooled into pool_out, the rest stored as 16-bit rows.  operand_fp16: A / W / 16-bit
+ * outputs are IEEE half instead of bf16.  res_row_mod > 0: residual row = destination row % res_row_mod.                    */
+typedef struct cv_gemm_epilogue {
+  const float* bias;
+  int act;            /* 0 none, 1 GELU, 2 ReLU */
+  int res_before_act; /* 1: act(acc + bias + residual) */
+  const float* residual;
+  long long ld_res;
+  long long res_row_mod;
+  float* out_f32;
+  long long ld_f32;
+  void* out_16;
+  long long ld_16;
+  int map_mode;
+  int ws, nwx, nwy, H, W, cout;
+  int pool_cols;
+  void* pool_out;
+  long long ld_pool;
+  int operand_fp16;
+} cv_gemm_epilogue;
+int cv_gemm_ex(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, const cv_gemm_epilogue* epilogue,
+               void* stream);
+
 /* Fused Hiera MLP half-block (sam2 MultiScaleBlock: x + mlp(norm2(x)), called from sam2_infer.py:226 through the sam2
  * package):  X[M,C] (fp32, in place)  <-  X + fc2(GELU(fc1(LayerNorm(X; gamma, beta, eps)))).  W1 [4C,C] and W2 [C,4C] are
  * 16-bit K-major weights in the operand format selected by operand_fp16, b1 [4C] / b2 [C] fp32.  The normalised operand,
@@ -155,6 +181,8 @@ int cv_mlp_fused(float* X, int M, int C, const float* gamma, const float* beta, 
 /* Debug: a zeroed device buffer of >= 4001 uint64 that the following cv_mlp_fused calls fill with the pipeline timeline of
  * CTA 0 (record = (event * 4096 + index) << 44 | globaltimer ns; buffer[0] = number of records); NULL switches it off. */
 int cv_mlp_fused_set_trace(void* device_buffer);
+/* same for the global-attention kernel (scripts/attn_trace.py): 4001 uint64, NULL switches it off */
+int cv_attn_set_trace(void* device_buffer);
 
 /* Block-diagonal flash attention on tcgen05 (head_dim 96): tokens are window-major; query row i (window i / Wq)
  * attends the Wkv keys of the same window.  Covers Hiera's windowed, Q-pooled (Wq = Wkv/4) and global
