@@ -1,6 +1,7 @@
 // Activation helpers shared by the GEMM epilogue and the CUDA-core kernels: exact-erf GELU evaluated with the
 // Abramowitz & Stegun 7.1.26 erf (|error| <= 1.5e-7) on scalar and on packed fp32x2 (FFMA2) arithmetic.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -114,6 +115,33 @@ __device__ __forceinline__ void gelu_tanh2(float& x0, float& x1) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a1));
   const uint64_t hx = mul2(x, pk2(0.5f, 0.5f));
   up2(fma2(hx, pk2(t0, t1), hx), x0, x1);
+}
+
+// The same tanh-form GELU on a packed fp16 PAIR, for epilogues whose output is fp16 anyway: every step is one half2 instruction
+// on a 32-bit register (no 64-bit register pairing, one MUFU.TANH per TWO elements): 10 instructions + 1 MUFU per pair against
+// ~19 + 2 of the fp32x2 form as compiled (the pair packing / unpacking around the scalar clamps and MUFUs costs moves).  The logit
+// polynomial is evaluated in v = x^2 / 32 <= 0.9453 so that every coefficient is O(1) in fp16:
+//   g / 2 = x (0.79783049 + 1.16843405 v - 0.19547042 v^2 - 0.43554282 v^3)
+// Error budget: x is rounded to fp16 first (|GELU'| <= 1.13, i.e. about the final rounding again), the fp16 Horner steps add
+// ~1.5e-3 relative to the logit (<= 6e-4 absolute after tanh), tanh.approx.f16x2 2^-11 absolute: |GELU error| <~ 4e-4 |x|, about
+// 2 fp16 ulps of the result where it matters; the parity fixtures decide (tests/test_sam2_golden_gpu.py).
+__device__ __forceinline__ uint32_t h2const(float v) {
+  const __half2 h = __float2half2_rn(v);
+  return *(const uint32_t*)&h;
+}
+__device__ __forceinline__ uint32_t gelu_tanh_h2(uint32_t x) {
+  uint32_t xs, v, g, a, t, hx, y;
+  asm("mul.f16x2 %0, %1, %2;" : "=r"(xs) : "r"(x), "r"(h2const(0.03125f)));
+  asm("mul.f16x2 %0, %1, %2;" : "=r"(v) : "r"(xs), "r"(x));
+  asm("min.f16x2 %0, %1, %2;" : "=r"(v) : "r"(v), "r"(h2const(0.9453125f)));
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(g) : "r"(v), "r"(h2const(-0.43554282f)), "r"(h2const(-0.19547042f)));
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(g) : "r"(g), "r"(v), "r"(h2const(1.16843405f)));
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(g) : "r"(g), "r"(v), "r"(h2const(0.79783049f)));
+  asm("mul.f16x2 %0, %1, %2;" : "=r"(a) : "r"(g), "r"(x));
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(a));
+  asm("mul.f16x2 %0, %1, %2;" : "=r"(hx) : "r"(x), "r"(h2const(0.5f)));
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(y) : "r"(hx), "r"(t), "r"(hx));
+  return y;
 }
 
 }  // namespace cvb

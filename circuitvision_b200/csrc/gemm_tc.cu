@@ -92,6 +92,16 @@ __device__ __forceinline__ long long gemm_dest_row(const GemmEpilogue& e, int ma
 template <int V>
 __device__ __forceinline__ int pick(int runtime) { return V < 0 ? runtime : V; }
 
+// Debug timeline (scripts/gemm_trace.py): plain global stores into fixed slots, no atomics (an atomic costs the recording
+// warp ~0.5 us and distorts what it measures).
+__device__ __forceinline__ void gemm_trace(const GemmProblem& p, unsigned ev, int idx) {
+  if (p.trace && blockIdx.x == 0 && idx < 256) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[1 + ev * 256 + idx] = ((unsigned long long)(ev * 4096u + (unsigned)idx) << 44) | (t & 0xFFFFFFFFFFFull);
+  }
+}
+
 __device__ __forceinline__ float apply_act(int act, float x) {
   if (act == GEMM_ACT_GELU) return gelu_fast(x);
   if (act == GEMM_ACT_RELU) return fmaxf(x, 0.f);
@@ -178,11 +188,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = tile0; t < n_tiles; t += tile_stride) {
+      int lt = 0;
+      for (int t = tile0; t < n_tiles; t += tile_stride, lt++) {
         int tm = t / p.n_tiles_n, nb = t - tm * p.n_tiles_n;
         const int mb = tm * CG + rank;
         for (int kb = 0; kb < n_kb; kb++) {
           tc::mbar_wait(&empty[stage], phase ^ 1);
+          if (kb == 0) gemm_trace(p, 5, lt);
           if (CG == 2) {
             // both CTAs load their half; the bytes of both are counted on the leader's full barrier
             if (rank == 0) tc::mbar_arrive_expect_tx(&full[stage], 2 * (A_BYTES + B_BYTES));
@@ -208,13 +220,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = tile0; t < n_tiles; t += tile_stride) {
+      int lt = 0;
+      for (int t = tile0; t < n_tiles; t += tile_stride, lt++) {
         tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc::tc_fence_after();
+        if (lane == 0) gemm_trace(p, 0, lt);
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < n_kb; kb++) {
           tc::mbar_wait(&full[stage], phase);
           tc::tc_fence_after();
+          if (kb == 0 && lane == 0) gemm_trace(p, 1, lt);
           const uint64_t da = tc::desc_kmajor(tc::smem_u32(sA + stage * A_BYTES));
           const uint64_t db = tc::desc_kmajor(tc::smem_u32(sB + stage * B_BYTES));
           const int ksteps = min(GEMM_BK / 16, (p.K - kb * GEMM_BK + 15) / 16);
@@ -236,6 +251,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
           else tc::mma_commit(&tfull[acc]);
         }
         __syncwarp();
+        if (lane == 0) gemm_trace(p, 2, lt);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -256,7 +272,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
     uint32_t nbuf = 0;
     const int sub_row = lane >> 3, sub_c = lane & 7;
     int cg_rot = cgroup;
+    int lt = -1;
     for (int t = tile0; t < n_tiles; t += tile_stride) {
+      lt++;
       int tm = t / p.n_tiles_n, nb = t - tm * p.n_tiles_n;
       const int mb = tm * CG + rank;
       const long long row0 = (long long)mb * GEMM_BM + quad * 32;
@@ -283,6 +301,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
       }
       tc::mbar_wait(&tfull[acc], acc_phase);
       tc::tc_fence_after();
+      if (ew == 0 && lane == 0) gemm_trace(p, 3, lt);
 #pragma unroll 1
       // BN / 32 chunks over EW / 4 warp groups: with 3 chunks and 2 groups one group would take two chunks of EVERY tile;
       // rotating the start group evens that out over consecutive tiles (the accumulators are double-buffered, so a group
@@ -356,8 +375,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
 #pragma unroll
             for (int j = 0; j < 8; j++) { f[4 * j] += rv[j].x; f[4 * j + 1] += rv[j].y; f[4 * j + 2] += rv[j].z; f[4 * j + 3] += rv[j].w; }
           }
+          // fp16 output + tanh-form GELU: the activation runs on the packed halves below (one MUFU per two elements)
+          const bool act_h2 = ACT == GEMM_ACT_GELU_TANH && OUT == 1 && e.gelu_h2;
+          if (!act_h2) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) apply_act2(act, f[i], f[i + 1]);
+            for (int i = 0; i < 32; i += 2) apply_act2(act, f[i], f[i + 1]);
+          }
           if (has_res && !rba) {
 #pragma unroll
             for (int j = 0; j < 8; j++) { f[4 * j] += rv[j].x; f[4 * j + 1] += rv[j].y; f[4 * j + 2] += rv[j].z; f[4 * j + 3] += rv[j].w; }
@@ -404,7 +427,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
             for (int j = 0; j < 4; j++) {
               uint32_t w[4];
               // one uniform branch per 8 values instead of a predicated pair of conversions per value pair
-              if (e.fp16) {
+              if (act_h2) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) w[k] = gelu_tanh_h2(tc::pack16(1, f[8 * j + 2 * k], f[8 * j + 2 * k + 1]));
+              } else if (e.fp16) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) w[k] = tc::pack16(1, f[8 * j + 2 * k], f[8 * j + 2 * k + 1]);
               } else {
@@ -485,8 +511,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (CG == 2) tc::mbar_arrive_leader(&tempty[acc]);
+        if (CG == 2) tc::mbar_arrive_leader_relaxed(&tempty[acc]);  // (tmem_ld_wait + tcgen05 fence above: the reads are complete)
         else tc::mbar_arrive(&tempty[acc]);
+        if (ew == 0) gemm_trace(p, 4, lt);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -501,6 +528,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
     else tc::tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
+
+static unsigned long long* g_gemm_trace = nullptr;
 
 template <int BN, int ACT, int RES, int OUT, int MAP, int RBA, int CG = 1, int EW = 8>
 static int launch_cfg(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M, int N, int K,
@@ -534,6 +563,7 @@ static int launch_cfg(const __nv_bfloat16* A, long long lda, const __nv_bfloat16
   p.n_tiles_n = (N + BN - 1) / BN;
   static const int rotate_on = getenv("CVB_GEMM_ROT") ? atoi(getenv("CVB_GEMM_ROT")) : 1;
   p.rotate = rotate_on;
+  p.trace = g_gemm_trace;
   long long tiles = (long long)((p.n_tiles_m + CG - 1) / CG) * p.n_tiles_n;
   const int max_groups = num_sms / CG;
   int grid = (int)(tiles < max_groups ? tiles : max_groups) * CG;
@@ -629,7 +659,11 @@ static int launch_bn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16*
 }
 
 int gemm_tc_launch(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M, int N, int K,
-                   const GemmEpilogue& epi, int num_sms, cudaStream_t st) {
+                   const GemmEpilogue& epi_in, int num_sms, cudaStream_t st) {
+  // CVB_GELU_H2=0: keep the fp32x2 GELU for fp16 outputs as well (A/B switch)
+  static const int gelu_h2_on = getenv("CVB_GELU_H2") ? atoi(getenv("CVB_GELU_H2")) : 1;
+  GemmEpilogue epi = epi_in;
+  epi.gelu_h2 = gelu_h2_on && epi.fp16 && epi.act == GEMM_ACT_GELU && epi.out_bf16 && !epi.out_f32 && !epi.res;
   if (M <= 0 || N <= 0 || K <= 0) return cvb_fail(CV_ERR_INVALID, "gemm: non-positive size");
   if ((N % 16) || (K % 8) || (lda % 8) || (ldw % 8)) return cvb_fail(CV_ERR_INVALID, "gemm: N%16, K%8, lda%8, ldw%8 must be 0");
   if (((uintptr_t)A | (uintptr_t)W) & 15) return cvb_fail(CV_ERR_INVALID, "gemm: operands must be 16-byte aligned");
@@ -712,4 +746,9 @@ extern "C" int cv_gemm_ex(const void* A, long long lda, const void* W, long long
   e.fp16 = x->operand_fp16;
   return gemm_tc_launch((const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)W, ldw, M, N, K, e, device_sm_count(),
                         (cudaStream_t)stream);
+}
+
+extern "C" int cv_gemm_set_trace(void* device_buffer) {
+  g_gemm_trace = (unsigned long long*)device_buffer;
+  return CV_OK;
 }

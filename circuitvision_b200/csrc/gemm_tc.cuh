@@ -41,12 +41,14 @@ struct GemmEpilogue {
   __nv_bfloat16* pool_out = nullptr;
   long long ld_pool = 0;
   int fp16 = 0;                      // operands (A, W) and the 16-bit output are IEEE half instead of bf16
+  int gelu_h2 = 0;                   // (set by the launcher) fp16 output + tanh-form GELU: evaluate the GELU in half2 (act.cuh)
 };
 
 struct GemmProblem {
   int M, N, K;
   int n_tiles_m, n_tiles_n;
   int rotate;  // epilogue: the column-chunk group a warp takes rotates from tile to tile (balances BN / 32 chunks over EW / 4 groups)
+  unsigned long long* trace;  // debug timeline of CTA 0 (cv_gemm_set_trace): slot = event * 256 + local tile index, else nullptr
 };
 
 // Host launcher.  Returns CV_OK or a CV_ERR_* status (message via cv_last_error()).

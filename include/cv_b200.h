@@ -183,6 +183,8 @@ int cv_mlp_fused(float* X, int M, int C, const float* gamma, const float* beta, 
 int cv_mlp_fused_set_trace(void* device_buffer);
 /* same for the global-attention kernel (scripts/attn_trace.py): 4001 uint64, NULL switches it off */
 int cv_attn_set_trace(void* device_buffer);
+/* same for k_gemm_tc (scripts/gemm_trace.py): a zeroed buffer of 1 + 8 * 256 uint64, slot = 1 + event * 256 + tile index of CTA 0 */
+int cv_gemm_set_trace(void* device_buffer);
 
 /* Block-diagonal flash attention on tcgen05 (head_dim 96): tokens are window-major; query row i (window i / Wq)
  * attends the Wkv keys of the same window.  Covers Hiera's windowed, Q-pooled (Wq = Wkv/4) and global
