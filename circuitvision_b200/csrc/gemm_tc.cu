@@ -616,8 +616,13 @@ static int launch_bn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16*
     const bool gelu_sig = gelu_form == 1, gelu_tanh = gelu_form == 2;
     // 192- / 224-wide tiles: only the long-K residual GEMMs (fc2 of stages 3-4) gain from the pair (their operand stream is what
     // binds them: +7 % at N384 K1536, +10 % at N448 K1792); the K = 384 qkv shapes lose 7 % to the pair's extra synchronisation
-    const bool pair_fc2 = BN >= 192 && f32 && res && K >= 1024;
-    if (pairs_on && BN >= 128 && (BN >= pair_min_bn || pair_fc2) && K >= 256 && M >= 1024) {
+    static const int pair_fc2_on = getenv("CVB_PAIR_FC2") ? atoi(getenv("CVB_PAIR_FC2")) : 1;
+    static const int pair_qkv_on = getenv("CVB_PAIR_QKV") ? atoi(getenv("CVB_PAIR_QKV")) : 1;
+    const bool pair_fc2 = pair_fc2_on && BN >= 192 && f32 && res && K >= 1024;
+    // ... and, once the accumulator hand-back of a pair no longer paid a cluster-scope release fence, the 16-bit K = 384 / 448 qkv
+    // shapes as well (N1152 K384: 920 -> 1080 TFLOP/s)
+    const bool pair_qkv = pair_qkv_on && BN >= 192 && b16 && !res;
+    if (pairs_on && BN >= 128 && (BN >= pair_min_bn || pair_fc2 || pair_qkv) && K >= 256 && M >= 1024) {
       if (b16 && !res && e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 0, 1, 0, 0, 2>(CVB_GEMM_ARGS);
       // 16 epilogue warps for the GELU epilogue of the CTA-pair shapes (fc1 of stages 3-4, epilogue-bound): 844 -> 880 TFLOP/s on
       // M262144 N1536 K384 once the MMA issue no longer co-limited (CVB_GELU_EW16=0 restores 8)
