@@ -315,7 +315,19 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
         nbuf++;
         // residual for the TMA path: this thread's own row, 32 consecutive floats (issued before the TMEM wait)
         float4 rv[8];
-        if (TMA_OUT && has_res) {
+        // residual through the staging buffer (fp32 boxes): loaded with lanes ALONG the columns (8 lanes per 128-byte row piece,
+        // 4 rows per instruction = 4 L1 wavefronts instead of the 32 of a row-per-thread load), handed to the row-owning thread
+        // through the buffer that then carries the result
+        const bool res_staged = TMA_OUT && OUT == 0 && RES == 1 && p.res_stage;
+        if (res_staged) {
+          const int prow = lane >> 3, pcol = lane & 7;
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const long long r = row0 + prow + 4 * i;
+            const long long rr = e.res_row_mod > 0 ? r % e.res_row_mod : r;
+            rv[i] = (r < p.M && pcol * 4 < ncols) ? *(const float4*)(e.res + rr * e.ld_res + col0 + pcol * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        } else if (TMA_OUT && has_res) {
           if (myrow < p.M) {
             long long rr = e.res_row_mod > 0 ? myrow % e.res_row_mod : myrow;
             const float4* rp = (const float4*)(e.res + rr * e.ld_res + col0);
@@ -359,6 +371,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
         if (TMA_OUT) {
           if (lane == 0) tc::tma_store_wait_read<EPI_BUFS - 1>();  // the store that last read `buf` has drained it
           __syncwarp();
+        }
+        if (res_staged) {
+          const int prow = lane >> 3, pcol = lane & 7;
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int rr = prow + 4 * i;
+            *(float4*)(buf + rr * 128 + ((pcol ^ (rr & 7)) << 4)) = rv[i];
+          }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; j++) rv[j] = *(const float4*)(buf + lane * 128 + ((j ^ (lane & 7)) << 4));
         }
         tc::tmem_ld_wait();
         float f[32];
@@ -564,6 +587,10 @@ static int launch_cfg(const __nv_bfloat16* A, long long lda, const __nv_bfloat16
   static const int rotate_on = getenv("CVB_GEMM_ROT") ? atoi(getenv("CVB_GEMM_ROT")) : 1;
   p.rotate = rotate_on;
   p.trace = g_gemm_trace;
+  static const int res_stage_on = getenv("CVB_GEMM_RES_STAGE") ? atoi(getenv("CVB_GEMM_RES_STAGE")) : 1;
+  // same-box A/B (10 reps): N384 K1536 843 -> 982 TFLOP/s, N768 K3072 1178 -> 1292, N192 K192 / N384 K384 +9 %; the 96-wide
+  // shapes, already at 5.5 TB/s, lose 3 % to the extra shared-memory round trip and keep the direct loads
+  p.res_stage = res_stage_on && N >= 128;
   long long tiles = (long long)((p.n_tiles_m + CG - 1) / CG) * p.n_tiles_n;
   const int max_groups = num_sms / CG;
   int grid = (int)(tiles < max_groups ? tiles : max_groups) * CG;
