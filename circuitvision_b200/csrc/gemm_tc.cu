@@ -44,6 +44,22 @@ constexpr int gemm_stages() {
   int s = (GEMM_SMEM_MAX - 1024 - 256 - EW * gemm_epi_bufs<BN, CG, EW>() * EB) / gemm_stage_bytes<BN, CG>();
   return s > 8 ? 8 : (CG == 1 && s > 4 ? 4 : s);
 }
+// A-stationary CTA pairs (AST): the A rows of an M tile pair stay in shared memory (AST 64-wide k-blocks, K <= 448) while the
+// pair walks every N tile of that row block; only the weights stream through the ring.  The K = 384 / 448 shapes are bound by
+// the L2 slice throughput (gemm_trace: the MMA loop waits for operands at 38-42 B/clk/SM = 6300 B/clk chip-wide); this halves
+// the L2 bytes per flop (A once per row block instead of once per tile).
+// (the template value AST is the number of resident k-blocks: 6 for K <= 384, 7 for K <= 448)
+constexpr int AST_MAX = 7;
+template <int BN, int EW, int EB, int NKB>
+constexpr int gemm_ast_stages() {
+  int s = (GEMM_SMEM_MAX - 1024 - 512 - EW * 2 * EB - NKB * GEMM_BM * 128) / ((BN / 2) * 128);
+  return s > 8 ? 8 : s;
+}
+template <int BN, int EW, int EB, int NKB>
+constexpr int gemm_ast_smem_bytes() {
+  return 1024 + NKB * GEMM_BM * 128 + gemm_ast_stages<BN, EW, EB, NKB>() * (BN / 2) * 128 + EW * 2 * EB + 512;
+}
+
 template <int BN, int CG, int EW, int EB>
 constexpr int gemm_smem_bytes() {
   return 1024 /*align slack*/ + gemm_stages<BN, CG, EW, EB>() * gemm_stage_bytes<BN, CG>() + EW * gemm_epi_bufs<BN, CG, EW>() * EB + 256;
@@ -124,37 +140,55 @@ __device__ __forceinline__ void apply_act2(int act, float& a, float& b) {
 
 // ACT / RES / OUT / MAP / RBA: compile-time epilogue configuration, -1 = read from GemmEpilogue at run time.
 // OUT: 0 = fp32, 1 = bf16, 2 = both (runtime-only).
-template <int BN, int ACT, int RES, int OUT, int MAP, int RBA, int CG, int EW>
+template <int BN, int ACT, int RES, int OUT, int MAP, int RBA, int CG, int EW, int AST = 0>
 __global__ void __launch_bounds__(128 + 32 * EW, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
           const __grid_constant__ CUtensorMap tmap_out, GemmProblem p, GemmEpilogue e) {
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
   static_assert(CG == 1 || CG == 2, "CG");
   static_assert(EW == 8 || EW == 16, "EW");
+  static_assert(AST == 0 || CG == 2, "A-stationary tiles are a CTA-pair configuration");
   constexpr int GEMM_EPI_BUF = (OUT == 1 && (MAP == GEMM_MAP_IDENTITY || MAP == GEMM_MAP_QPOOL)) ? 2048 : 4096;  // 16-bit TMA box or fp32 staging
-  constexpr int GEMM_STAGES = gemm_stages<BN, CG, EW, GEMM_EPI_BUF>();
-  constexpr int EPI_BUFS = gemm_epi_bufs<BN, CG, EW>();
+  constexpr int GEMM_STAGES = AST ? gemm_ast_stages<BN, EW, GEMM_EPI_BUF, AST ? AST : 1>() : gemm_stages<BN, CG, EW, GEMM_EPI_BUF>();
+  constexpr int EPI_BUFS = AST ? 2 : gemm_epi_bufs<BN, CG, EW>();
   static_assert(GEMM_STAGES >= 2, "smem ring");
   constexpr int A_BYTES = GEMM_BM * 128, B_BYTES = (BN / CG) * 128;
+  constexpr int A_SLOTS = AST ? AST : GEMM_STAGES;  // A: resident k-blocks of the row block, or a ring like B
   constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   constexpr bool TMA_OUT = (MAP == GEMM_MAP_IDENTITY && (OUT == 0 || OUT == 1)) || (MAP == GEMM_MAP_QPOOL && OUT == 1);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + GEMM_STAGES * A_BYTES;
-  uint8_t* epi = smem + GEMM_STAGES * (A_BYTES + B_BYTES);  // [EW warps][EPI_BUFS][GEMM_EPI_BUF], 1024-byte aligned
+  uint8_t* sB = smem + A_SLOTS * A_BYTES;
+  uint8_t* epi = sB + GEMM_STAGES * B_BYTES;  // [EW warps][EPI_BUFS][GEMM_EPI_BUF], 1024-byte aligned
   uint64_t* bars = (uint64_t*)(epi + EW * EPI_BUFS * GEMM_EPI_BUF);
   uint64_t* full = bars;                     // [STAGES]
   uint64_t* empty = bars + GEMM_STAGES;      // [STAGES]
   uint64_t* tfull = bars + 2 * GEMM_STAGES;  // [2]
   uint64_t* tempty = tfull + 2;              // [2]
-  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  uint64_t* a_full = tempty + 2;             // [AST_MAX]  (AST only)
+  uint64_t* a_empty = a_full + AST_MAX;      // [AST_MAX]
+  uint32_t* tmem_slot = (uint32_t*)(a_empty + AST_MAX);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // shuffle: warp-uniform for the compiler
   // CG == 2: a tile is 256 rows; CTA `rank` of the pair owns rows [tile_m*256 + rank*128, +128)
   const int rank = CG == 2 ? (int)tc::cluster_ctarank() : 0;
-  const int n_tiles = ((p.n_tiles_m + CG - 1) / CG) * p.n_tiles_n;
-  const int tile0 = blockIdx.x / CG, tile_stride = gridDim.x / CG;
+  // AST: the loop index runs over (row block of this pair, N tile) with the N tile fastest; otherwise tiles are dealt round-robin
+  const int n_mt = (p.n_tiles_m + CG - 1) / CG;
+  const int my_mt = AST ? (n_mt - (int)(blockIdx.x / CG) + (int)(gridDim.x / CG) - 1) / (int)(gridDim.x / CG) : 0;
+  const int n_tiles = AST ? my_mt * p.n_tiles_n : n_mt * p.n_tiles_n;
+  const int tile0 = AST ? 0 : blockIdx.x / CG, tile_stride = AST ? 1 : gridDim.x / CG;
+  // tile index -> (row block, N tile)
+  auto tile_mn = [&](int t, int& tm, int& nb) {
+    if (AST) {
+      const int i = t / p.n_tiles_n;
+      nb = t - i * p.n_tiles_n;
+      tm = (int)(blockIdx.x / CG) + i * (int)(gridDim.x / CG);
+    } else {
+      tm = t / p.n_tiles_n;
+      nb = t - tm * p.n_tiles_n;
+    }
+  };
   const int n_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
 
   if (warp == 0 && lane == 0) {
@@ -171,6 +205,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
       tc::mbar_init(&tfull[i], 1);
       tc::mbar_init(&tempty[i], EW * CG);  // the leader collects the epilogue warps of both CTAs
     }
+    if (AST)
+      for (int i = 0; i < AST_MAX; i++) {
+        tc::mbar_init(&a_full[i], 1);
+        tc::mbar_init(&a_empty[i], 1);
+      }
     tc::fence_barrier_init();
   }
   if (warp == 2) {
@@ -190,9 +229,26 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
       uint32_t phase = 0;
       int lt = 0;
       for (int t = tile0; t < n_tiles; t += tile_stride, lt++) {
-        int tm = t / p.n_tiles_n, nb = t - tm * p.n_tiles_n;
+        int tm, nb;
+        tile_mn(t, tm, nb);
         const int mb = tm * CG + rank;
         for (int kb = 0; kb < n_kb; kb++) {
+          if (AST) {
+            if (nb == 0) {
+              // k-block kb of the next row block: its slot is free once the LAST N tile of the previous row block has consumed it
+              // (released k-block by k-block, so these loads run under that tile's remaining MMAs)
+              const uint32_t rb = (uint32_t)(t / p.n_tiles_n);
+              tc::mbar_wait(&a_empty[kb], (rb & 1) ^ 1);
+              if (rank == 0) tc::mbar_arrive_expect_tx(&a_full[kb], 2 * A_BYTES);
+              tc::tma_load_2d_2sm(sA + kb * A_BYTES, &tmap_a, &a_full[kb], kb * GEMM_BK, mb * GEMM_BM);
+            }
+            tc::mbar_wait(&empty[stage], phase ^ 1);
+            if (kb == 0) gemm_trace(p, 5, lt);
+            if (rank == 0) tc::mbar_arrive_expect_tx(&full[stage], 2 * B_BYTES);
+            tc::tma_load_2d_2sm(sB + stage * B_BYTES, &tmap_w, &full[stage], kb * GEMM_BK, nb * BN + rank * (BN / 2));
+            if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           tc::mbar_wait(&empty[stage], phase ^ 1);
           if (kb == 0) gemm_trace(p, 5, lt);
           if (CG == 2) {
@@ -226,11 +282,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
         tc::tc_fence_after();
         if (lane == 0) gemm_trace(p, 0, lt);
         const uint32_t d_tmem = tmem_base + acc * BN;
+        const int rb = AST ? t / p.n_tiles_n : 0, nb_ast = AST ? t - rb * p.n_tiles_n : 0;
         for (int kb = 0; kb < n_kb; kb++) {
+          if (AST && nb_ast == 0) tc::mbar_wait(&a_full[kb], rb & 1);
           tc::mbar_wait(&full[stage], phase);
           tc::tc_fence_after();
           if (kb == 0 && lane == 0) gemm_trace(p, 1, lt);
-          const uint64_t da = tc::desc_kmajor(tc::smem_u32(sA + stage * A_BYTES));
+          const uint64_t da = tc::desc_kmajor(tc::smem_u32(sA + (AST ? kb : stage) * A_BYTES));
           const uint64_t db = tc::desc_kmajor(tc::smem_u32(sB + stage * B_BYTES));
           const int ksteps = min(GEMM_BK / 16, (p.K - kb * GEMM_BK + 15) / 16);
           if (tc::elect_one()) {
@@ -242,6 +300,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
               }
             if (CG == 2) tc::mma_commit2(&empty[stage]);
             else tc::mma_commit(&empty[stage]);
+            if (AST && nb_ast == p.n_tiles_n - 1) tc::mma_commit2(&a_empty[kb]);  // last N tile of the row block: A slot kb is free
           }
           __syncwarp();
           if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
@@ -275,7 +334,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
     int lt = -1;
     for (int t = tile0; t < n_tiles; t += tile_stride) {
       lt++;
-      int tm = t / p.n_tiles_n, nb = t - tm * p.n_tiles_n;
+      int tm, nb;
+      tile_mn(t, tm, nb);
       const int mb = tm * CG + rank;
       const long long row0 = (long long)mb * GEMM_BM + quad * 32;
       const long long myrow = row0 + lane;
@@ -554,14 +614,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
 
 static unsigned long long* g_gemm_trace = nullptr;
 
-template <int BN, int ACT, int RES, int OUT, int MAP, int RBA, int CG = 1, int EW = 8>
+template <int BN, int ACT, int RES, int OUT, int MAP, int RBA, int CG = 1, int EW = 8, int AST = 0>
 static int launch_cfg(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, int M, int N, int K,
                       const GemmEpilogue& epi, int num_sms, cudaStream_t st) {
   static std::atomic<unsigned long long> attr_set{0};
   constexpr int GEMM_THREADS = 128 + 32 * EW;
-  constexpr int smem = gemm_smem_bytes<BN, CG, EW, (OUT == 1 && (MAP == GEMM_MAP_IDENTITY || MAP == GEMM_MAP_QPOOL)) ? 2048 : 4096>();
+  constexpr int EB = (OUT == 1 && (MAP == GEMM_MAP_IDENTITY || MAP == GEMM_MAP_QPOOL)) ? 2048 : 4096;
+  constexpr int smem = AST ? gemm_ast_smem_bytes<BN, EW, EB, AST ? AST : 1>() : gemm_smem_bytes<BN, CG, EW, EB>();
   static_assert(smem <= GEMM_SMEM_MAX, "shared memory budget");
-  auto kern = k_gemm_tc<BN, ACT, RES, OUT, MAP, RBA, CG, EW>;
+  static_assert(!AST || gemm_ast_stages<BN, EW, EB, AST ? AST : 1>() >= 2, "A-stationary ring");
+  if (AST && K > AST * GEMM_BK) return cvb_fail(CV_ERR_INVALID, "gemm: row block does not fit the resident A slots");
+  auto kern = k_gemm_tc<BN, ACT, RES, OUT, MAP, RBA, CG, EW, AST>;
   if (cvb_once_per_device(attr_set)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cvb_fail_cuda(e, "cudaFuncSetAttribute(k_gemm_tc)");
@@ -591,14 +654,14 @@ static int launch_cfg(const __nv_bfloat16* A, long long lda, const __nv_bfloat16
   // same-box A/B (10 reps): N384 K1536 843 -> 982 TFLOP/s, N768 K3072 1178 -> 1292, N192 K192 / N384 K384 +9 %; the 96-wide
   // shapes, already at 5.5 TB/s, lose 3 % to the extra shared-memory round trip and keep the direct loads
   p.res_stage = res_stage_on && N >= 128;
-  long long tiles = (long long)((p.n_tiles_m + CG - 1) / CG) * p.n_tiles_n;
+  long long tiles = (long long)((p.n_tiles_m + CG - 1) / CG) * (AST ? 1 : p.n_tiles_n);  // AST: work unit = a row block
   const int max_groups = num_sms / CG;
   int grid = (int)(tiles < max_groups ? tiles : max_groups) * CG;
   cvb_next_work(2.0 * (double)M * (double)N * (double)K);
   if (cvb_profile_on()) {
     char nm[96];
     snprintf(nm, sizeof(nm), "gemm M%d N%d K%d bn%d%s%s%s%s%s%s", M, N, K, BN, epi.out_bf16 ? " ->bf16" : "", epi.out_f32 ? " ->f32" : "",
-             epi.res ? " +res" : "", ACT < 0 ? " generic" : "", CG == 2 ? " 2cta" : "", EW == 16 ? " ew16" : "");
+             epi.res ? " +res" : "", ACT < 0 ? " generic" : "", CG == 2 ? (AST ? " 2cta-ast" : " 2cta") : "", EW == 16 ? " ew16" : "");
     cvb_next_name(nm);
   }
   if (CG == 2) {
@@ -650,6 +713,19 @@ static int launch_bn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16*
     // shapes as well (N1152 K384: 920 -> 1080 TFLOP/s)
     const bool pair_qkv = pair_qkv_on && BN >= 192 && b16 && !res;
     if (pairs_on && BN >= 128 && (BN >= pair_min_bn || pair_fc2 || pair_qkv) && K >= 256 && M >= 1024) {
+      // A-stationary row blocks for the L2-bound K <= 448 shapes with several N tiles (16-bit outputs: qkv, fc1)
+      static const int ast_on = getenv("CVB_GEMM_AST") ? atoi(getenv("CVB_GEMM_AST")) : 1;
+      if constexpr (BN >= 192) {
+        if (ast_on && K <= AST_MAX * GEMM_BK && (N + BN - 1) / BN >= 3 && b16 && !res) {
+          if (K <= 6 * GEMM_BK) {
+            if (e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 0, 1, 0, 0, 2, 8, 6>(CVB_GEMM_ARGS);
+          } else {
+            if (e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 0, 1, 0, 0, 2, 8, 7>(CVB_GEMM_ARGS);
+          }
+          // (the GELU shapes with their 16 epilogue warps keep the ring: 64 KB of staging leave the weight ring 3 stages beside a
+          //  resident A, and N1792 K448 fell from 1100 to 990 TFLOP/s)
+        }
+      }
       if (b16 && !res && e.act == GEMM_ACT_NONE) return launch_cfg<BN, 0, 0, 1, 0, 0, 2>(CVB_GEMM_ARGS);
       // 16 epilogue warps for the GELU epilogue of the CTA-pair shapes (fc1 of stages 3-4, epilogue-bound): 844 -> 880 TFLOP/s on
       // M262144 N1536 K384 once the MMA issue no longer co-limited (CVB_GELU_EW16=0 restores 8)

@@ -62,6 +62,10 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
                "l"((uint64_t)gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// 2-D tile prefetch global -> L2 (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"((uint64_t)m), "r"(c0), "r"(c1) : "memory");
+}
 // 2-D tile store shared -> global (bulk async group); out-of-bounds rows/columns of the box are clipped
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)m),
