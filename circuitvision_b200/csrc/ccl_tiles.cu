@@ -378,7 +378,7 @@ __device__ __noinline__ int ccl_write_multi(int* L, int* dst, uint32_t word, int
   return n_roots;
 }
 
-__global__ void __launch_bounds__(CW_WARPS * 32) k_ccl_write(int* __restrict__ labels, const uint32_t* __restrict__ bits_all,
+__global__ void __launch_bounds__(CW_WARPS * 32, 5) k_ccl_write(int* __restrict__ labels, const uint32_t* __restrict__ bits_all,
                                                            const int* __restrict__ head_all, int H, int W, int wpr, int vec_ok,
                                                            int* __restrict__ ncomp, int* __restrict__ partial) {
   const int b = blockIdx.z, y0 = (blockIdx.y * CW_WARPS + (threadIdx.x >> 5)) * CW_R, c = threadIdx.x & 31;

@@ -262,12 +262,6 @@ k_patch_embed(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
           const int rr = prow_l + 4 * i;
           sts128(buf + rr * 128 + ((pcol_l ^ (rr & 7)) << 4), pr[i]);
         }
-        if (c + 1 < NCH) {
-#pragma unroll
-          for (int i = 0; i < 8; i++)
-            pr[i] = ((c + 1) * 32 + pcol_l * 4 < E) ? __ldg((const float4*)(pbase + (size_t)(4 * i) * E + (c + 1) * 32))
-                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
         __syncwarp();
         tc::tmem_ld_wait();
         float s1 = 0.f;
@@ -289,6 +283,14 @@ k_patch_embed(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         if (lane == 0) {
           tc::tma_store_2d(&tmap_x, stage_p + bsel * PE_STAGE_BYTES, c * 32, (int)((long long)t * 128 + quad * 32));
           tc::tma_store_commit();
+        }
+        // the next chunk's positional rows are requested only now: the proxy fence above is a MEMBAR that waits for every
+        // outstanding load of the thread, so loads issued before it would be waited for there instead of overlapping
+        if (c + 1 < NCH) {
+#pragma unroll
+          for (int i = 0; i < 8; i++)
+            pr[i] = ((c + 1) * 32 + pcol_l * 4 < E) ? __ldg((const float4*)(pbase + (size_t)(4 * i) * E + (c + 1) * 32))
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (ln) {
           if (ncols >= 32) tc::tmem_st_32x32(tacc + c * 32, v);
