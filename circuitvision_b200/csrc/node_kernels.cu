@@ -750,6 +750,44 @@ __global__ void k_trace_points(const uint8_t* __restrict__ bin, int h, int w, co
 // pair list has the reference's append order.
 // ------------------------------------------------------------------------------------------------
 #define CVB_HITS_PER_BOX 64
+// contours of one image in id order against one box (a whole warp): AABB pre-test, then a ballot scan of the vertex list for
+// the first "near" vertex.  emit(hit index, pair) is called by every lane for each hit; returns the number of hits.
+template <class Emit>
+__device__ __forceinline__ int contact_scan_box(const cv_box& bx, int bi, const cv_contour* __restrict__ cts, int nK,
+                                                const int32_t* __restrict__ pts, int lane, Emit emit) {
+  int nh = 0;
+  for (int k = 0; k < nK; k++) {
+    const cv_contour& ct = cts[k];
+    int cx = ct.xmin, cy = ct.ymin, cxm = ct.xmax + 1, cym = ct.ymax + 1;  // rect x+w, y+h
+    if (bx.rxmax < cx || bx.rxmin > cxm || bx.rymax < cy || bx.rymin > cym) continue;
+    int n = ct.nverts;
+    const int32_t* cp = pts + (size_t)ct.offset * 2;
+    int hit = -1, hx = 0, hy = 0;
+    for (int v0 = 0; v0 < n && hit < 0; v0 += 32) {
+      int v = v0 + lane;
+      bool near = false;
+      int px = 0, py = 0;
+      if (v < n) {
+        px = cp[2 * v]; py = cp[2 * v + 1];
+        near = point_near_box(px, py, bx.rxmin, bx.rymin, bx.rxmax, bx.rymax, bx.thresh);
+      }
+      unsigned m = __ballot_sync(0xffffffffu, near);
+      if (m) {
+        int src = __ffs(m) - 1;
+        hit = v0 + src;
+        hx = __shfl_sync(0xffffffffu, px, src);
+        hy = __shfl_sync(0xffffffffu, py, src);
+      }
+    }
+    if (hit >= 0) {
+      cv_pair pr; pr.contour = k; pr.box = bi; pr.px = hx; pr.py = hy;
+      emit(nh, pr);
+      nh++;
+    }
+  }
+  return nh;
+}
+
 __global__ void __launch_bounds__(1024) k_contact(const cv_box* __restrict__ boxes, const int32_t* __restrict__ box_offsets,
                                                   const cv_contour* __restrict__ contours, int max_contours,
                                                   const int32_t* __restrict__ points, int max_points,
@@ -765,50 +803,24 @@ __global__ void __launch_bounds__(1024) k_contact(const cv_box* __restrict__ box
   int nK = results[b].n_contours;
   const cv_contour* cts = contours + (size_t)b * max_contours;
   const int32_t* pts = points + (size_t)b * max_points * 2;
+  cv_pair* out = pairs + (size_t)b * max_pairs;
   if (threadIdx.x == 0) s_written = 0;
   __syncthreads();
   int status = 0;
   for (int c0 = 0; c0 < nb; c0 += 32) {
     int bi = c0 + warp;
     int nh = 0;
+    cv_box bx;
+    bool scan = false;
     if (bi < nb) {
-      cv_box bx = boxes[bo + bi];
-      if (bx.flags & CV_BOX_IS_COMPONENT) {
-        for (int k = 0; k < nK; k++) {
-          const cv_contour& ct = cts[k];
-          int cx = ct.xmin, cy = ct.ymin, cxm = ct.xmax + 1, cym = ct.ymax + 1;  // rect x+w, y+h
-          if (bx.rxmax < cx || bx.rxmin > cxm || bx.rymax < cy || bx.rymin > cym) continue;
-          int n = ct.nverts;
-          const int32_t* cp = pts + (size_t)ct.offset * 2;
-          int hit = -1, hx = 0, hy = 0;
-          for (int v0 = 0; v0 < n && hit < 0; v0 += 32) {
-            int v = v0 + lane;
-            bool near = false;
-            int px = 0, py = 0;
-            if (v < n) {
-              px = cp[2 * v]; py = cp[2 * v + 1];
-              near = point_near_box(px, py, bx.rxmin, bx.rymin, bx.rxmax, bx.rymax, bx.thresh);
-            }
-            unsigned m = __ballot_sync(0xffffffffu, near);
-            if (m) {
-              int src = __ffs(m) - 1;
-              hit = v0 + src;
-              hx = __shfl_sync(0xffffffffu, px, src);
-              hy = __shfl_sync(0xffffffffu, py, src);
-            }
-          }
-          if (hit >= 0) {
-            if (nh < CVB_HITS_PER_BOX) {
-              if (lane == 0) { cv_pair pr; pr.contour = k; pr.box = bi; pr.px = hx; pr.py = hy; s_hits[warp][nh] = pr; }
-            } else {
-              status |= CV_STATUS_BOX_HITS_OVERFLOW;  // compile-time staging limit: growing max_pairs cannot help
-            }
-            nh++;
-          }
-        }
-      }
+      bx = boxes[bo + bi];
+      scan = (bx.flags & CV_BOX_IS_COMPONENT) != 0;
     }
-    if (lane == 0) s_nh[warp] = min(nh, CVB_HITS_PER_BOX);
+    if (scan)
+      nh = contact_scan_box(bx, bi, cts, nK, pts, lane, [&](int idx, const cv_pair& pr) {
+        if (idx < CVB_HITS_PER_BOX && lane == 0) s_hits[warp][idx] = pr;
+      });
+    if (lane == 0) s_nh[warp] = nh;
     __syncthreads();
     if (threadIdx.x == 0) {
       int run = s_written;
@@ -816,11 +828,21 @@ __global__ void __launch_bounds__(1024) k_contact(const cv_box* __restrict__ box
       s_base[32] = run;
     }
     __syncthreads();
-    int n_mine = s_nh[warp];
-    for (int j = lane; j < n_mine; j += 32) {
-      int dst = s_base[warp] + j;
-      if (dst < max_pairs) pairs[(size_t)b * max_pairs + dst] = s_hits[warp][j];
+    const int base = s_base[warp];
+    for (int j = lane; j < min(nh, CVB_HITS_PER_BOX); j += 32) {
+      int dst = base + j;
+      if (dst < max_pairs) out[dst] = s_hits[warp][j];
       else status |= CV_STATUS_PAIR_OVERFLOW;
+    }
+    if (nh > CVB_HITS_PER_BOX) {
+      // a box that touches more contours than the staging rows hold (noisy masks): the same walk once more, hits beyond the
+      // staged ones go straight to their slots
+      contact_scan_box(bx, bi, cts, nK, pts, lane, [&](int idx, const cv_pair& pr) {
+        if (idx >= CVB_HITS_PER_BOX) {
+          if (base + idx < max_pairs) { if (lane == 0) out[base + idx] = pr; }
+          else status |= CV_STATUS_PAIR_OVERFLOW;
+        }
+      });
     }
     __syncthreads();
     if (threadIdx.x == 0) s_written = s_base[32];

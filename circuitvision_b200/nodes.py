@@ -345,9 +345,6 @@ class NodeAnalyzer:
                     self.caps["max_points"] *= 4
                 if st & 8:
                     self.caps["max_pairs"] *= 4
-                if st & 16:
-                    raise CvError("node analysis: one component box touches more than 64 kept contours — beyond the contact "
-                                  "kernel's per-box staging limit (CV_STATUS_BOX_HITS_OVERFLOW); growing the tables cannot help")
                 if self.caps["max_pairs"] > (1 << 20) or self.caps["max_points"] > (1 << 24):
                     break
             raise CvError("node analysis capacities could not be satisfied")

@@ -69,7 +69,7 @@ typedef struct cv_pair {              /* one accepted (node, component) attachme
 #define CV_STATUS_CONTOUR_OVERFLOW 2
 #define CV_STATUS_POINT_OVERFLOW 4
 #define CV_STATUS_PAIR_OVERFLOW 8
-#define CV_STATUS_BOX_HITS_OVERFLOW 16 /* one box touches more than 64 kept contours (fixed staging limit of the contact kernel) */
+#define CV_STATUS_BOX_HITS_OVERFLOW 16 /* reserved: not raised any more (boxes beyond the 64 staged contacts take a recompute path) */
 
 typedef struct cv_image_result {
   int32_t n_external;  /* external components before the area filter */

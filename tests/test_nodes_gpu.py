@@ -196,3 +196,35 @@ def test_shared_analyzer_from_several_threads(analyzer):
         rn, remp, renh, _, _ = want[i]
         assert np.array_equal(emptied, remp) and np.array_equal(enhanced, renh), i
         _assert_nodes_equal(nodes, rn, f"thread case {i}")
+
+
+def _ring_of_blobs_case():
+    """One component box with 80+ separate wire blobs just outside its perimeter (a noisy hand-drawn page does this): every
+    blob is a kept contour in contact with the same box — more than the 64 contacts k_contact stages per box."""
+    h, w = 600, 1000
+    mask = np.zeros((h, w), np.uint8)
+    x0, y0, x1, y1 = 100, 100, 900, 500
+    for x in range(x0, x1 - 19, 30):
+        mask[y0 - 20:y0 + 4, x:x + 20] = 255  # straddles the edge: the part inside the box is emptied, the rest touches it
+        mask[y1 - 4:y1 + 20, x:x + 20] = 255
+    for y in range(y0, y1 - 19, 30):
+        mask[y:y + 20, x0 - 20:x0 + 4] = 255
+        mask[y:y + 20, x1 - 4:x1 + 20] = 255
+    boxes = [{"class": "resistor", "xmin": x0, "ymin": y0, "xmax": x1, "ymax": y1, "persistent_uid": "resistor_0"},
+             # a second detection of the same rectangle: nodes need two components to be kept (circuit_analyzer.py:1558)
+             {"class": "capacitor.unpolarized", "xmin": x0, "ymin": y0, "xmax": x1, "ymax": y1, "persistent_uid": "cap_0"}]
+    return mask, boxes
+
+
+def test_box_touching_more_than_64_contours(analyzer):
+    from oracle import node_oracle
+    mask, boxes = _ring_of_blobs_case()
+    ref_nodes, ref_emp, ref_enh, _, ref_pts = node_oracle.get_node_connections(mask, boxes)
+    assert sum(any(c["persistent_uid"] == "resistor_0" for c in n["components"]) for n in ref_nodes) > 64
+    nodes, emptied, enhanced, *_ = analyzer.get_node_connections(None, mask, boxes)
+    assert np.array_equal(emptied, ref_emp) and np.array_equal(enhanced, ref_enh)
+    _assert_nodes_equal(nodes, ref_nodes, "ring of blobs")
+    r = analyzer.get_node_connections_batch(np.stack([mask, mask]), [boxes, boxes])
+    for b in range(2):
+        _assert_nodes_equal(r.nodes(b), ref_nodes, f"ring of blobs, batch item {b}")
+        assert r.connection_points(b) == [tuple(p) for p in ref_pts]
