@@ -4,17 +4,17 @@
 // canonical: labels[p] = 1 + min linear index of p's component, 0 for background.
 //
 // Traffic plan (the path is HBM-bound; algorithmic bytes = 1 B/px mask read + 4 B/px label write), three passes:
-//   pass A  k_ccl_scan       : one WARP per tile of 1024 x 32 pixels, lane = one 32-pixel word column, rows top to bottom.
-//                              Reads the mask once (1 B/px), writes the bit plane (1 bit/px), the parent entries of the run
-//                              elements (in the label image, at run-start pixels only) and head[word] (first pixel of the
-//                              run that enters a word from the left).  No block barriers, no shared atomics: labels flow
-//                              down the rows through two shared-memory rows of slots per warp, ballot / match / shuffle
-//                              resolve the runs that span several words, and only real merges (two different labels
-//                              meeting) touch the global union-find.
-//   pass B  k_ccl_seam_*     : unions across the tile seams (rows y = 32 k: 3.1 % of the image; columns x = 1024 k).
-//   pass C  k_ccl_write      : the label image is written exactly once (4 B/px): run start from the bit plane, root by
-//                              pointer chasing, 16-byte stores.  It also counts the roots.
-// Total ~ 5.3 B/px.  The algorithm is modelled lane by lane in oracle/ccl_scan_model.py (held to cv2 on the CPU by
+//   pass A  k_ccl_scan       : one WARP per tile of 1024 x 64 pixels, lane = one 32-pixel word column, rows top to bottom.
+//                              Reads the mask once (1 B/px), writes the bit plane (1 bit/px), first[word] = label of the word's
+//                              first sub-run (4 B per 32 px, coalesced), and parent entries IN the label image only for roots
+//                              and for the second and later sub-runs of a word.  No block barriers, no shared atomics: labels
+//                              flow down the rows through two shared-memory rows of slots per warp, ballot / shuffle resolve
+//                              the runs that span several words, and only real merges (two different labels meeting) touch the
+//                              global union-find.
+//   pass B  k_ccl_seams      : unions across the tile seams (rows y = 64 k: 1.6 % of the image; columns x = 1024 k), one launch.
+//   pass C  k_ccl_write      : the label image is written exactly once (4 B/px): root by pointer chasing from first[word],
+//                              16-byte stores.  It also counts the roots.
+// Total ~ 5.3 B/px; 0.60 of the HBM copy peak at 256 images per call, 0.45 at 16 (tails of the two big passes).  The algorithm is modelled lane by lane in oracle/ccl_scan_model.py (held to cv2 on the CPU by
 // tests/test_ccl_model_cpu.py); round 1's block-level shared-memory union-find + fix-up pass (6+ B/px, 72 % issue-bound,
 // 35 % of its stalls at __syncthreads) reached 0.32 of the HBM copy peak.
 #include <cuda_runtime.h>
@@ -73,6 +73,25 @@ __device__ __forceinline__ void gunion(int* L, int a, int b) {
 
 // union of two ELEMENTS (run-start pixels with a parent entry)
 __device__ __forceinline__ void gunion_roots(int* L, int a, int b) { gunion(L, a, b); }
+// union of two LABELS (elements that carry a parent entry: roots, former roots), no first hop
+__device__ __forceinline__ void gunion_labels(int* L, int a, int b) {
+  bool done;
+  do {
+    a = gfind_halve(L, a);
+    b = gfind_halve(L, b);
+    if (a < b) {
+      int old = atomicMin(L + b, a + 1) - 1;
+      done = (old == b);
+      b = old;
+    } else if (b < a) {
+      int old = atomicMin(L + a, b + 1) - 1;
+      done = (old == a);
+      a = old;
+    } else {
+      done = true;
+    }
+  } while (!done);
+}
 
 // start of the sub-run of `word` that contains set bit x
 __device__ __forceinline__ int run_start(uint32_t word, int x) {
@@ -121,8 +140,9 @@ __device__ __forceinline__ uint32_t load_word(const uint8_t* __restrict__ im, in
 // lab[parity][lane][start bit >> 1] = label of the word-local sub-run starting at that bit (two runs cannot start at
 // adjacent bits), for the previous and the current row.
 // ================================================================================================
-constexpr int CS_TH = 32;        // rows per tile
-constexpr int CS_WARPS = 8;      // tiles (stacked vertically) per CTA
+constexpr int CS_TH = 64;        // rows per tile (32: twice the seam work, 0.582 -> 0.597 of the HBM peak at 128 images; 128: the
+                                 // scan's tail grows, 0.594, and 16 images no longer fill the GPU)
+constexpr int CS_WARPS = 8;      // tiles (stacked vertically) per CTA (4 / 6 / 8 measured the same at 128 images)
 constexpr int CS_LSTRIDE = 16;   // 16 slots per lane; the slot index is XOR-swizzled with the lane so that the 32 lanes hit 32 banks
                                  // (4 KB per warp: 7 CTAs = 56 warps per SM, the whole 16 x 4096^2 problem in one wave)
 constexpr int CS_INF = 0x7FFFFFFF;
@@ -140,7 +160,7 @@ __device__ __forceinline__ void cs_combine(int* L, int& cd, int t) {
 
 template <int CONN>
 __global__ void __launch_bounds__(CS_WARPS * 32) k_ccl_scan(const uint8_t* __restrict__ masks, int* __restrict__ labels,
-                                                           uint32_t* __restrict__ bits_all, int* __restrict__ head_all, int H,
+                                                           uint32_t* __restrict__ bits_all, int* __restrict__ first_all, int H,
                                                            int W, int wpr, int vec_ok) {
   __shared__ int lab_s[CS_WARPS][2][32 * CS_LSTRIDE];
   const int warp = threadIdx.x >> 5, c = threadIdx.x & 31;
@@ -149,18 +169,15 @@ __global__ void __launch_bounds__(CS_WARPS * 32) k_ccl_scan(const uint8_t* __res
   const uint8_t* im = masks + (size_t)b * H * W;
   int* L = labels + (size_t)b * H * W;
   uint32_t* bits = bits_all + (size_t)b * H * wpr;
-  int* head = head_all + (size_t)b * H * wpr;
+  int* first = first_all + (size_t)b * H * wpr;
   const int wc = blockIdx.x * 32 + c;
   const bool valid = wc < wpr;
   int(*lab)[32 * CS_LSTRIDE] = lab_s[warp];
   uint32_t up = 0, upl = 0, upr = 0;
   const int rows = min(CS_TH, H - y0);
-  // the rows of the tile are walked one after the other (each depends on the labels of the one above): pull the whole tile
-  // towards L2 first, then keep two rows in flight in registers, so that a row costs an L2 hit, not a DRAM round trip
-  if (valid) {
-    const uint8_t* pf = im + (size_t)y0 * W + x0 + c * 32;
-    for (int r = 0; r < rows; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (size_t)r * W));
-  }
+  // the rows of the tile are walked one after the other (each depends on the labels of the one above): two rows are kept in
+  // flight in registers.  (An up-front prefetch.global.L2 of the whole tile helped the 16-image batch of round 1 and costs
+  // 1-2 % at 128+ images, 7 % with 64-row tiles: removed.)
   uint32_t w_next = valid ? load_word(im, H, W, y0, x0 + c * 32, vec_ok != 0) : 0u;
   uint32_t w_next2 = (valid && rows > 1) ? load_word(im, H, W, y0 + 1, x0 + c * 32, vec_ok != 0) : 0u;
   for (int r = 0; r < rows; r++) {
@@ -180,6 +197,7 @@ __global__ void __launch_bounds__(CS_WARPS * 32) k_ccl_scan(const uint8_t* __res
     int* lp = lab[par ^ 1];  // previous row
     int* lc = lab[par];
     int ch = CS_INF, ct = CS_INF, tail_st = 0;
+    const int first_st = __ffs(w) - 1;  // start bit of the word's first sub-run: its label goes to first[], not to the label image
     for (uint32_t s = w & ~(w << 1); s; s &= s - 1) {
       const int st = __ffs(s) - 1;
       const int len = run_len(w, st);
@@ -208,7 +226,9 @@ __global__ void __launch_bounds__(CS_WARPS * 32) k_ccl_scan(const uint8_t* __res
         tail_st = st;
       } else {
         const int m = cd == CS_INF ? rowbase + st : cd;  // nothing touched: a root, named by its first pixel
-        L[rowbase + st] = m + 1;
+        // parent entries in the label image: roots, and sub-runs after the first of their word (the first one is found through
+        // first[]): a 4-byte store per run dirtied a 32-byte sector of the label image per run (read-modify-write in DRAM)
+        if (cd == CS_INF || st != first_st) L[rowbase + st] = m + 1;
         lc[cs_slot(c, st >> 1)] = m;
       }
     }
@@ -231,40 +251,40 @@ __global__ void __launch_bounds__(CS_WARPS * 32) k_ccl_scan(const uint8_t* __res
       if (tail_org) {
         const int tot = min(ct, from_right);
         my_m = tot == CS_INF ? my_start : tot;
+        if (tot == CS_INF || tail_st != first_st) L[my_start] = my_m + 1;  // before the union: a new root needs its entry
         if (ct != CS_INF && ct != my_m) gunion_roots(L, ct, my_m);
-        L[my_start] = my_m + 1;
         lc[cs_slot(c, tail_st >> 1)] = my_m;
       }
-      const int mo = __shfl_sync(0xffffffffu, my_m, origin), so = __shfl_sync(0xffffffffu, my_start, origin);
+      const int mo = __shfl_sync(0xffffffffu, my_m, origin);
       if (cin) {
         if (ch != CS_INF && ch != mo) gunion_roots(L, ch, mo);
         lc[cs_slot(c, 0)] = mo;
-        head[(size_t)y * wpr + wc] = so;
       }
     }
+    // first[word] = label of the word's first sub-run (an element of the same component as every pixel of that sub-run): pass C
+    // starts its root chase there — a coalesced 4-byte read per word instead of a 32-byte sector of the label image per word
+    if (valid && w) first[(size_t)y * wpr + wc] = lc[cs_slot(c, (__ffs(w) - 1) >> 1)];
     __syncwarp();  // label slots and parent entries of this row are visible to every lane before the next row reads them
     up = w; upl = wl; upr = wr;
   }
 }
 
-// first pixel (linear index) of the tile-row run that contains pixel (y, 32 wc + bit); bit is set in bits[y][wc]
-__device__ __forceinline__ int cs_start_of(const uint32_t* __restrict__ bits, const int* __restrict__ head, int W, int wpr, int y,
-                                           int wc, int bit) {
+// label (an element of the same component that carries a parent entry) of the sub-run of word (y, wc) that contains set bit
+// `bit`: first[] for the first sub-run of a word (whether it starts there or entered from the left), one hop through the
+// sub-run's own parent entry otherwise
+__device__ __forceinline__ int cs_label_of(const int* L, const uint32_t* __restrict__ bits, const int* __restrict__ first, int W, int wpr,
+                                           int y, int wc, int bit) {
   const uint32_t wv = bits[(size_t)y * wpr + wc];
   const int st = run_start(wv, bit);
-  if (st == 0 && (wc & 31) && (bits[(size_t)y * wpr + wc - 1] >> 31)) return head[(size_t)y * wpr + wc];
-  return y * W + wc * 32 + st;
+  if (st == __ffs(wv) - 1) return first[(size_t)y * wpr + wc];
+  return __ldcg(L + (size_t)y * W + wc * 32 + st) - 1;
 }
 
 // pass B, horizontal seams: rows y = k CS_TH against the row above, one 32-pixel word per thread
 template <int CONN>
-__global__ void __launch_bounds__(128) k_ccl_seam_rows(int* __restrict__ labels, const uint32_t* __restrict__ bits_all,
-                                                        const int* __restrict__ head_all, int H, int W, int wpr) {
-  const int b = blockIdx.z, y = (blockIdx.y + 1) * CS_TH, wc = blockIdx.x * 128 + threadIdx.x;
+__device__ __forceinline__ void ccl_seam_row_word(int* L, const uint32_t* __restrict__ bits, const int* __restrict__ first, int H, int W,
+                                                  int wpr, int y, int wc) {
   if (y >= H || wc >= wpr) return;
-  int* L = labels + (size_t)b * H * W;
-  const uint32_t* bits = bits_all + (size_t)b * H * wpr;
-  const int* head = head_all + (size_t)b * H * wpr;
   const uint32_t wv = bits[(size_t)y * wpr + wc];
   if (!wv) return;
   const uint32_t uv = bits[(size_t)(y - 1) * wpr + wc];
@@ -283,41 +303,55 @@ __global__ void __launch_bounds__(128) k_ccl_seam_rows(int* __restrict__ labels,
     uint32_t ov = aw & uv;
     const bool dl = CONN == 8 && (rm & 1u) && ul, dr = CONN == 8 && (rm >> 31) && ur;
     if (!ov && !dl && !dr) continue;
-    const int me = cs_start_of(bits, head, W, wpr, y, wc, st);
+    const int me = cs_label_of(L, bits, first, W, wpr, y, wc, st);
     while (ov) {
       const int u = __ffs(ov) - 1;
       const int us = run_start(uv, u);
       ov &= ~run_mask(us, run_len(uv, us));
-      gunion_roots(L, me, cs_start_of(bits, head, W, wpr, y - 1, wc, us));
+      gunion_labels(L, me, cs_label_of(L, bits, first, W, wpr, y - 1, wc, us));
     }
-    if (dl) gunion_roots(L, me, cs_start_of(bits, head, W, wpr, y - 1, wc - 1, 31));
-    if (dr) gunion_roots(L, me, cs_start_of(bits, head, W, wpr, y - 1, wc + 1, 0));
+    if (dl) gunion_labels(L, me, cs_label_of(L, bits, first, W, wpr, y - 1, wc - 1, 31));
+    if (dr) gunion_labels(L, me, cs_label_of(L, bits, first, W, wpr, y - 1, wc + 1, 0));
   }
 }
 
 // pass B, vertical seams: columns x = k 1024 against column x - 1, one row per thread
 template <int CONN>
-__global__ void __launch_bounds__(256) k_ccl_seam_cols(int* __restrict__ labels, const uint32_t* __restrict__ bits_all,
-                                                        const int* __restrict__ head_all, int H, int W, int wpr) {
-  const int b = blockIdx.z;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void ccl_seam_col_pixel(int* L, const uint32_t* __restrict__ bits, const int* __restrict__ first, int H, int W,
+                                                   int wpr, long long t) {
   const int n_seams = (W - 1) / 1024;
   if (t >= (long long)n_seams * H) return;
   const int wc = (int)(t / H + 1) * 32, y = (int)(t % H);
-  int* L = labels + (size_t)b * H * W;
-  const uint32_t* bits = bits_all + (size_t)b * H * wpr;
-  const int* head = head_all + (size_t)b * H * wpr;
   const bool cur = bits[(size_t)y * wpr + wc] & 1u, left = bits[(size_t)y * wpr + wc - 1] >> 31;
   if (cur && left) {
-    gunion_roots(L, cs_start_of(bits, head, W, wpr, y, wc, 0), cs_start_of(bits, head, W, wpr, y, wc - 1, 31));
+    gunion_labels(L, cs_label_of(L, bits, first, W, wpr, y, wc, 0), cs_label_of(L, bits, first, W, wpr, y, wc - 1, 31));
   } else if (CONN == 8 && cur) {
-    const int me = cs_start_of(bits, head, W, wpr, y, wc, 0);
-    if (y > 0 && (bits[(size_t)(y - 1) * wpr + wc - 1] >> 31)) gunion_roots(L, me, cs_start_of(bits, head, W, wpr, y - 1, wc - 1, 31));
-    if (y + 1 < H && (bits[(size_t)(y + 1) * wpr + wc - 1] >> 31)) gunion_roots(L, me, cs_start_of(bits, head, W, wpr, y + 1, wc - 1, 31));
+    const int me = cs_label_of(L, bits, first, W, wpr, y, wc, 0);
+    if (y > 0 && (bits[(size_t)(y - 1) * wpr + wc - 1] >> 31)) gunion_labels(L, me, cs_label_of(L, bits, first, W, wpr, y - 1, wc - 1, 31));
+    if (y + 1 < H && (bits[(size_t)(y + 1) * wpr + wc - 1] >> 31)) gunion_labels(L, me, cs_label_of(L, bits, first, W, wpr, y + 1, wc - 1, 31));
   } else if (CONN == 8 && left) {
-    const int me = cs_start_of(bits, head, W, wpr, y, wc - 1, 31);
-    if (y > 0 && (bits[(size_t)(y - 1) * wpr + wc] & 1u)) gunion_roots(L, me, cs_start_of(bits, head, W, wpr, y - 1, wc, 0));
-    if (y + 1 < H && (bits[(size_t)(y + 1) * wpr + wc] & 1u)) gunion_roots(L, me, cs_start_of(bits, head, W, wpr, y + 1, wc, 0));
+    const int me = cs_label_of(L, bits, first, W, wpr, y, wc - 1, 31);
+    if (y > 0 && (bits[(size_t)(y - 1) * wpr + wc] & 1u)) gunion_labels(L, me, cs_label_of(L, bits, first, W, wpr, y - 1, wc, 0));
+    if (y + 1 < H && (bits[(size_t)(y + 1) * wpr + wc] & 1u)) gunion_labels(L, me, cs_label_of(L, bits, first, W, wpr, y + 1, wc, 0));
+  }
+}
+
+// pass B in one launch: blocks [0, row_blocks) take the horizontal seams (block = 128 words of one seam row), the blocks after
+// them the vertical seams (128 seam pixels each) — the two sets of unions are independent, so they run side by side
+template <int CONN>
+__global__ void __launch_bounds__(128) k_ccl_seams(int* __restrict__ labels, const uint32_t* __restrict__ bits_all,
+                                                    const int* __restrict__ first_all, int H, int W, int wpr, int row_blocks_x,
+                                                    int row_blocks) {
+  const int b = blockIdx.z;
+  int* L = labels + (size_t)b * H * W;
+  const uint32_t* bits = bits_all + (size_t)b * H * wpr;
+  const int* first = first_all + (size_t)b * H * wpr;
+  const int bx = blockIdx.x;
+  if (bx < row_blocks) {
+    const int sy = bx / row_blocks_x, sx = bx - sy * row_blocks_x;
+    ccl_seam_row_word<CONN>(L, bits, first, H, W, wpr, (sy + 1) * CS_TH, sx * 128 + (int)threadIdx.x);
+  } else {
+    ccl_seam_col_pixel<CONN>(L, bits, first, H, W, wpr, (long long)(bx - row_blocks) * 128 + threadIdx.x);
   }
 }
 
@@ -325,15 +359,22 @@ __global__ void __launch_bounds__(256) k_ccl_seam_cols(int* __restrict__ labels,
 // minimum index links every tile's root under the one above it), and pass C would walk it from every pixel.  All those
 // roots are runs of the FIRST row of a tile, so re-pointing the run starts of the seam rows at their final root (3 % of the
 // rows, path-halving finds) bounds every later chase by a few hops.
-__global__ void __launch_bounds__(128) k_ccl_flatten_rows(int* __restrict__ labels, const uint32_t* __restrict__ bits_all, int H, int W,
-                                                          int wpr) {
+__global__ void __launch_bounds__(128) k_ccl_flatten_rows(int* __restrict__ labels, const uint32_t* __restrict__ bits_all,
+                                                          int* __restrict__ first_all, int H, int W, int wpr) {
   const int b = blockIdx.z, y = (blockIdx.y + 1) * CS_TH, wc = blockIdx.x * 128 + threadIdx.x;
   if (y >= H || wc >= wpr) return;
   int* L = labels + (size_t)b * H * W;
   const uint32_t* bits = bits_all + (size_t)b * H * wpr;
+  int* first = first_all + (size_t)b * H * wpr;
   const uint32_t wv = bits[(size_t)y * wpr + wc];
+  if (!wv) return;
+  {  // first sub-run of the word: its label lives in first[]
+    const int lab = first[(size_t)y * wpr + wc];
+    const int r = gfind_halve(L, lab);
+    if (r != lab) first[(size_t)y * wpr + wc] = r;
+  }
   uint32_t starts = wv & ~(wv << 1);
-  if ((wv & 1u) && (wc & 31) && (bits[(size_t)y * wpr + wc - 1] >> 31)) starts &= ~1u;  // continued run: no entry of its own
+  starts &= starts - 1;  // further sub-runs: their own parent entries
   for (; starts; starts &= starts - 1) {
     const int s = y * W + wc * 32 + __ffs(starts) - 1;
     const int r = gfind_halve(L, s);
@@ -342,8 +383,7 @@ __global__ void __launch_bounds__(128) k_ccl_flatten_rows(int* __restrict__ labe
 }
 
 // pass C: the label image is written ONCE.  One warp per row segment of 1024 pixels (= one tile row), lane = one 32-pixel word:
-// the lane resolves the label of its word's run (run start from the bit plane, or head[] when the run entered from the left;
-// root by pointer chasing), then the warp writes the 4 KB of labels cooperatively — per 16-byte store a lane fetches the word
+// the lane resolves the label of its word's first sub-run (first[word] from pass A, root by pointer chasing), then the warp writes the 4 KB of labels cooperatively — per 16-byte store a lane fetches the word
 // and the label of the word it is writing by shuffle, so a store instruction covers 512 contiguous bytes.  Words that hold
 // more than one run (noise, text: ~1 % of the words) are written by their own lane afterwards.  (A thread-per-4-pixels
 // version needed 1.1 instructions per pixel and was bound by them: 0.70 ms for 16 x 4096^2; this one needs ~0.15.)
@@ -379,13 +419,13 @@ __device__ __noinline__ int ccl_write_multi(int* L, int* dst, uint32_t word, int
 }
 
 __global__ void __launch_bounds__(CW_WARPS * 32, 5) k_ccl_write(int* __restrict__ labels, const uint32_t* __restrict__ bits_all,
-                                                           const int* __restrict__ head_all, int H, int W, int wpr, int vec_ok,
+                                                           const int* __restrict__ first_all, int H, int W, int wpr, int vec_ok,
                                                            int* __restrict__ ncomp, int* __restrict__ partial) {
   const int b = blockIdx.z, y0 = (blockIdx.y * CW_WARPS + (threadIdx.x >> 5)) * CW_R, c = threadIdx.x & 31;
   if (y0 >= H) return;
   int* L = labels + (size_t)b * H * W;
   const uint32_t* bits = bits_all + (size_t)b * H * wpr;
-  const int* head = head_all + (size_t)b * H * wpr;
+  const int* first = first_all + (size_t)b * H * wpr;
   const int wc = blockIdx.x * 32 + c;
   uint32_t word[CW_R];
   int cur[CW_R], par[CW_R], start[CW_R];
@@ -397,14 +437,11 @@ __global__ void __launch_bounds__(CW_WARPS * 32, 5) k_ccl_write(int* __restrict_
     uint32_t wl = __shfl_up_sync(0xffffffffu, word[i], 1);
     if (c == 0) wl = 0u;
     cont[i] = (word[i] & 1u) && (wl >> 31);  // the first run of my word entered from the left
-    start[i] = -1;
-    if (word[i]) start[i] = cont[i] ? head[(size_t)(y0 + i) * wpr + wc] : (y0 + i) * W + wc * 32 + __ffs(word[i]) - 1;
+    start[i] = (y0 + i) * W + wc * 32 + __ffs(word[i]) - 1;  // the run's own element, when it starts in this word (!cont)
+    cur[i] = word[i] ? __ldcs(first + (size_t)(y0 + i) * wpr + wc) : -1;  // pass A's label of my first sub-run
   }
 #pragma unroll
-  for (int i = 0; i < CW_R; i++) {
-    cur[i] = start[i];
-    par[i] = start[i] >= 0 ? __ldcg(L + start[i]) - 1 : -1;
-  }
+  for (int i = 0; i < CW_R; i++) par[i] = cur[i] >= 0 ? __ldcg(L + cur[i]) - 1 : -1;
   for (bool moving = true; moving;) {  // all chains advance together
     moving = false;
 #pragma unroll
@@ -472,7 +509,7 @@ static size_t ccl_plane_bytes(int B, int H, int W) { return (((size_t)B * H * ((
 
 template <int CONN>
 static int ccl_run(const uint8_t* masks, int B, int H, int W, int32_t* labels, int32_t* n_components, int* partial,
-                   uint32_t* bits, int* head, cudaStream_t st) {
+                   uint32_t* bits, int* first, cudaStream_t st) {
   const int vec_ok = (W % 16 == 0) && (((uintptr_t)masks & 15) == 0) && (((uintptr_t)labels & 15) == 0);
   const int wpr = (W + 31) / 32;
   const double px = (double)B * H * W;
@@ -480,25 +517,28 @@ static int ccl_run(const uint8_t* masks, int B, int H, int W, int32_t* labels, i
   static std::atomic<unsigned long long> carveout_set{0};
   if (cvb_once_per_device(carveout_set))  // 7 CTAs x 32 KB of label slots per SM: ask for the large shared-memory split
     CVB_CHECK(cudaFuncSetAttribute(k_ccl_scan<CONN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  // (a specialisation without the bounds tests and the byte-wise load path compiled to 40 registers = 6 CTAs per SM and was no
+  //  faster at 128 images and slower at 16, where 1024 CTAs then fill 1.15 waves)
   CVB_LAUNCH((k_ccl_scan<CONN>), dim3((W + 1023) / 1024, (H + CS_TH * CS_WARPS - 1) / (CS_TH * CS_WARPS), B), dim3(CS_WARPS * 32), 0,
-             st, masks, labels, bits, head, H, W, wpr, vec_ok);
+             st, masks, labels, bits, first, H, W, wpr, vec_ok);
   const int seams_h = (H - 1) / CS_TH;
   const long long vpx = (long long)((W - 1) / 1024) * H;
+  const int row_blocks_x = (wpr + 127) / 128, row_blocks = row_blocks_x * seams_h;
+  const long long col_blocks = (vpx + 127) / 128;
+  if (row_blocks + col_blocks > 0)
+    CVB_LAUNCH((k_ccl_seams<CONN>), dim3((unsigned)(row_blocks + col_blocks), 1, B), dim3(128), 0, st, labels, bits, first, H, W, wpr,
+               row_blocks_x, row_blocks);
   if (seams_h > 0)
-    CVB_LAUNCH((k_ccl_seam_rows<CONN>), dim3((wpr + 127) / 128, seams_h, B), dim3(128), 0, st, labels, bits, head, H, W, wpr);
-  if (vpx > 0)
-    CVB_LAUNCH((k_ccl_seam_cols<CONN>), dim3((unsigned)((vpx + 255) / 256), 1, B), dim3(256), 0, st, labels, bits, head, H, W, wpr);
-  if (seams_h > 0)
-    CVB_LAUNCH(k_ccl_flatten_rows, dim3((wpr + 127) / 128, seams_h, B), dim3(128), 0, st, labels, bits, H, W, wpr);
+    CVB_LAUNCH(k_ccl_flatten_rows, dim3((wpr + 127) / 128, seams_h, B), dim3(128), 0, st, labels, bits, first, H, W, wpr);
   cvb_next_work(4.0 * px);
-  CVB_LAUNCH(k_ccl_write, dim3((W + 1023) / 1024, (H + CW_WARPS * CW_R - 1) / (CW_WARPS * CW_R), B), dim3(CW_WARPS * 32), 0, st, labels, bits, head, H, W, wpr, vec_ok, n_components,
+  CVB_LAUNCH(k_ccl_write, dim3((W + 1023) / 1024, (H + CW_WARPS * CW_R - 1) / (CW_WARPS * CW_R), B), dim3(CW_WARPS * 32), 0, st, labels, bits, first, H, W, wpr, vec_ok, n_components,
              partial);
   if (n_components && partial) CVB_LAUNCH(k_ccl_count_finish, dim3(B), dim3(32), 0, st, partial, n_components, B);
   return CV_OK;
 }
 
 extern "C" size_t cv_ccl_workspace_bytes(int B, int H, int W) {
-  // spread component counters | bit plane (1 bit / pixel) | head[] (one int per 32-pixel word)
+  // spread component counters | bit plane (1 bit / pixel) | first[] (one int per 32-pixel word)
   return ccl_partial_bytes(B) + 2 * ccl_plane_bytes(B, H, W);
 }
 
@@ -515,11 +555,11 @@ extern "C" int cv_ccl_label(const uint8_t* masks, int B, int H, int W, int conne
   cudaStream_t st = (cudaStream_t)stream_;
   int* partial = (int*)workspace;
   uint32_t* bits = (uint32_t*)((uint8_t*)workspace + ccl_partial_bytes(B));
-  int* head = (int*)((uint8_t*)bits + ccl_plane_bytes(B, H, W));
+  int* first = (int*)((uint8_t*)bits + ccl_plane_bytes(B, H, W));
   if (n_components) {
     CVB_CHECK(cudaMemsetAsync(partial, 0, ccl_partial_bytes(B), st));
     CVB_CHECK(cudaMemsetAsync(n_components, 0, (size_t)B * 4, st));
   }
-  return connectivity == 8 ? ccl_run<8>(masks, B, H, W, labels, n_components, partial, bits, head, st)
-                           : ccl_run<4>(masks, B, H, W, labels, n_components, partial, bits, head, st);
+  return connectivity == 8 ? ccl_run<8>(masks, B, H, W, labels, n_components, partial, bits, first, st)
+                           : ccl_run<4>(masks, B, H, W, labels, n_components, partial, bits, first, st);
 }

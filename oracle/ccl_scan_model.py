@@ -8,10 +8,13 @@ seam unions, the single label-writing pass — is validated on the CPU before it
   pass A  one warp per tile of TW = 1024 x TH rows, lane = one 32-pixel word column, rows processed top to bottom:
           a run (maximal horizontal run inside the tile row) takes the label of a run it touches in the row above; a run that
           touches nothing becomes a root (label = its own first pixel); touching two different labels is a union (global
-          union-find on the parent entries, which live in the label image at run-start pixels only).
-          Outputs: bit plane, head[word] = first pixel of the run that enters the word from the left, parent entries.
+          union-find on the parent entries, which live in the label image at run-start pixels).
+          Outputs: bit plane, first[word] = pass A's label of the word's first sub-run (an element of the same component, whether
+          that sub-run starts in the word or entered from the left), parent entries for roots and for the second and later
+          sub-runs of a word only.
   pass B  unions across tile seams (rows y = k TH, columns x = k TW).
-  pass C  every pixel: run start from the bit plane (+ head[]), root by pointer chasing, label = root + 1.  Written once.
+  pass C  every pixel: root by pointer chasing from first[word] (first sub-run of a word) or from the sub-run's own parent
+          entry (further sub-runs), label = root + 1.  Written once.
 """
 from __future__ import annotations
 
@@ -69,7 +72,7 @@ class UF:
             self.L[a] = b + 1
 
 
-def pass_a_tile(bits, head, uf, W, x0, y0, th, conn, words_per_row):
+def pass_a_tile(bits, first, uf, W, x0, y0, th, conn, words_per_row):
     """bits[y][word] already filled.  Processes rows y0 .. y0+th-1 of the tile whose first word column is x0 // 32."""
     c0 = x0 // 32
     nl = min(LANES, words_per_row - c0)
@@ -139,10 +142,14 @@ def pass_a_tile(bits, head, uf, W, x0, y0, th, conn, words_per_row):
                 else:
                     m = y * W + x0 + o * 32 + ostart  # nothing touched: the run is a root, named by its first pixel
                 lab_cur[c][st] = m
-                if not is_head:  # the lane where the run starts writes its parent entry
-                    uf.L[y * W + x0 + c * 32 + st] = m + 1
-                else:
-                    head[y][c0 + c] = y * W + x0 + o * 32 + ostart
+                # the lane where the run starts writes its parent entry — roots and sub-runs after the first of their word only
+                # (UF.find asserts on a pixel without an entry, so a read of a skipped entry fails the model's tests)
+                if not is_head:
+                    first_st = (w[c] & -w[c]).bit_length() - 1
+                    if not vals or st != first_st:
+                        uf.L[y * W + x0 + c * 32 + st] = m + 1
+            if c < nl and w[c]:
+                first[y][c0 + c] = lab_cur[c][(w[c] & -w[c]).bit_length() - 1]
         lab_prev, up = lab_cur, w
 
 
@@ -153,20 +160,21 @@ def label(mask: np.ndarray, conn: int = 8, th: int = 32) -> np.ndarray:
     padded = np.zeros((H, wpr * 32), np.uint8)
     padded[:, :W] = mask != 0
     bits = np.packbits(padded.reshape(H, wpr, 32), axis=2, bitorder="little").view(np.uint32).reshape(H, wpr)
-    head = np.full((H, wpr), -1, np.int64)
+    first = np.full((H, wpr), -1, np.int64)
     uf = UF(H * W)
     for y0 in range(0, H, th):
         for x0 in range(0, W, TW):
-            pass_a_tile(bits, head, uf, W, x0, y0, min(th, H - y0), conn, wpr)
+            pass_a_tile(bits, first, uf, W, x0, y0, min(th, H - y0), conn, wpr)
 
     def start_of(y, c, bit):
-        """first pixel of the tile-row run containing pixel (y, 32 c + bit)"""
+        """label (an element with a parent entry) of the sub-run of word (y, c) containing `bit`: cs_label_of in the kernel"""
         wv = int(bits[y][c])
         st = run_start(wv, bit)
-        tile_c0 = (c * 32 // TW) * (TW // 32)
-        if st == 0 and c > tile_c0 and (int(bits[y][c - 1]) >> 31):
-            return int(head[y][c])
-        return y * W + c * 32 + st
+        if st == (wv & -wv).bit_length() - 1:
+            return int(first[y][c])
+        e = int(uf.L[y * W + c * 32 + st])
+        assert e > 0, "sub-run without a parent entry"
+        return e - 1
 
     # ---- pass B: seams
     for y in range(th, H, th):  # horizontal: row y against row y - 1
@@ -217,7 +225,7 @@ def label(mask: np.ndarray, conn: int = 8, th: int = 32) -> np.ndarray:
     out = np.zeros((H, W), np.int32)
     for y in range(H):
         for c in range(wpr):
-            for st, rm in sub_runs(int(bits[y][c])):
+            for k, (st, rm) in enumerate(sub_runs(int(bits[y][c]))):
                 root = uf.find(start_of(y, c, st))
                 n = run_len(int(bits[y][c]), st)
                 x = c * 32 + st

@@ -7,8 +7,8 @@ from circuitvision_b200 import synth, nodes, _lib
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 S = 4096
 lib = _lib.load()
-masks = np.stack([synth.make_schematic(900 + i, S)[0] for i in range(4)])
-pool = [torch.from_numpy(np.stack([masks[(i + p) % 4] for i in range(B)])).cuda() for p in range(2)]  # 2 x B x 16 MiB
+base = torch.from_numpy(np.stack([synth.make_schematic(900 + i, S)[0] for i in range(8)])).cuda()
+pool = [base[(torch.arange(B, device="cuda") + p) % 8].contiguous() for p in range(2)]  # 2 x B x 16 MiB
 labels = torch.empty((B, S, S), dtype=torch.int32, device="cuda")
 counts = torch.empty((B,), dtype=torch.int32, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
