@@ -129,6 +129,36 @@ __device__ __forceinline__ uint32_t load_word(const uint8_t* __restrict__ im, in
   return w;
 }
 
+// The same in two steps, so that the 32 raw bytes of a row can wait in registers while the row before it is processed (the
+// conversion is the first use of the loaded data: done right after the load, it exposes the whole memory latency every row).
+// `fast` lanes (whole word inside the image, 16-byte aligned rows) hold the raw bytes; the others hold the finished word in a.x.
+struct RawWord {
+  uint4 a, b;
+};
+__device__ __forceinline__ RawWord load_raw(const uint8_t* __restrict__ im, int H, int W, int y, int x, bool fast) {
+  RawWord r;
+  if (fast) {
+    const uint4* p = (const uint4*)(im + (size_t)y * W + x);
+    r.a = __ldg(p);
+    r.b = __ldg(p + 1);
+  } else {
+    r.a = make_uint4(load_word(im, H, W, y, x, false), 0u, 0u, 0u);
+    r.b = make_uint4(0u, 0u, 0u, 0u);
+  }
+  return r;
+}
+__device__ __forceinline__ uint32_t raw_to_word(const RawWord& r, bool fast) {
+  if (!fast) return r.a.x;
+  const uint32_t v[8] = {r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y, r.b.z, r.b.w};
+  uint32_t w = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    uint32_t m = (((v[k] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v[k]) & 0x80808080u;
+    w |= ((m * 0x00204081u) >> 28) << (4 * k);
+  }
+  return w;
+}
+
 // ================================================================================================
 // pass A: warp-sequential scan.  One warp per tile of 1024 x CS_TH pixels, lane = one 32-pixel word column, rows top to
 // bottom.  Model: oracle/ccl_scan_model.py (pass_a_tile) — same names, same order.
@@ -175,16 +205,20 @@ __global__ void __launch_bounds__(CS_WARPS * 32) k_ccl_scan(const uint8_t* __res
   int(*lab)[32 * CS_LSTRIDE] = lab_s[warp];
   uint32_t up = 0, upl = 0, upr = 0;
   const int rows = min(CS_TH, H - y0);
-  // the rows of the tile are walked one after the other (each depends on the labels of the one above): two rows are kept in
-  // flight in registers.  (An up-front prefetch.global.L2 of the whole tile helped the 16-image batch of round 1 and costs
-  // 1-2 % at 128+ images, 7 % with 64-row tiles: removed.)
-  uint32_t w_next = valid ? load_word(im, H, W, y0, x0 + c * 32, vec_ok != 0) : 0u;
-  uint32_t w_next2 = (valid && rows > 1) ? load_word(im, H, W, y0 + 1, x0 + c * 32, vec_ok != 0) : 0u;
+  // the rows of the tile are walked one after the other (each depends on the labels of the one above): row r + 1 waits
+  // converted, row r + 2 as raw bytes whose load was issued a whole row step before its first use.  (An up-front
+  // prefetch.global.L2 of the whole tile helped the 16-image batch of round 1 and costs 1-2 % at 128+ images: removed.)
+  const int xw = x0 + c * 32;
+  const bool fast = valid && vec_ok && xw + 32 <= W;
+  uint32_t w_next = valid ? raw_to_word(load_raw(im, H, W, y0, xw, fast), fast) : 0u;
+  RawWord raw2;
+  raw2.a = raw2.b = make_uint4(0u, 0u, 0u, 0u);
+  if (valid && rows > 1) raw2 = load_raw(im, H, W, y0 + 1, xw, fast);
   for (int r = 0; r < rows; r++) {
     const int y = y0 + r, par = r & 1;
     const uint32_t w = w_next;
-    w_next = w_next2;
-    if (r + 2 < rows) w_next2 = valid ? load_word(im, H, W, y + 2, x0 + c * 32, vec_ok != 0) : 0u;  // two rows in flight
+    w_next = (valid && r + 1 < rows) ? raw_to_word(raw2, fast) : 0u;     // loaded one row step ago
+    if (valid && r + 2 < rows) raw2 = load_raw(im, H, W, y + 2, xw, fast);  // first use one row step from now
     if (valid) bits[(size_t)y * wpr + wc] = w;
     uint32_t wl = __shfl_up_sync(0xffffffffu, w, 1), wr = __shfl_down_sync(0xffffffffu, w, 1);
     if (c == 0) wl = 0u;

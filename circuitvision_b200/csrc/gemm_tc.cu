@@ -372,7 +372,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
         const int col0 = nb * BN + c * 32;
         const int ncols = p.N - col0;  // valid columns of this chunk: >= 32, 16 (N % 32 == 16) or <= 0
         uint8_t* buf = bufs + (nbuf % EPI_BUFS) * GEMM_EPI_BUF;
-        nbuf++;
+        // The staging buffers alternate with the TMA-store groups: wait_group.read<EPI_BUFS - 1> below frees the buffer used
+        // EPI_BUFS uses ago only if every use in between committed exactly one group.  The pooled q chunks of a Q-pooled qkv GEMM
+        // write their result with ordinary stores (no group), so they must not advance the alternation: with nbuf++ here, a
+        // k / v chunk could overwrite a box its predecessor's TMA store was still reading (seen as run-to-run differences of
+        // one attention window, scripts/sam2_determinism_probe.py).
+        if (!(MAP == GEMM_MAP_QPOOL && col0 < e.pool_cols)) nbuf++;
         // residual for the TMA path: this thread's own row, 32 consecutive floats (issued before the TMEM wait)
         float4 rv[8];
         // residual through the staging buffer (fp32 boxes): loaded with lanes ALONG the columns (8 lanes per 128-byte row piece,

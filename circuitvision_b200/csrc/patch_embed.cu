@@ -194,8 +194,9 @@ k_patch_embed(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 6; i++) w[ky][i] = lds32(seg + i * 4);
       }
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&r_empty[s]);
+      // (the raw slot is NOT released here: ld.shared followed by an mbarrier arrive does not order the loads' data return
+      //  before the next bulk copy into the slot — the copy engine overwrote bytes some lanes had not received yet, seen as
+      //  run-to-run differences of a few tokens per ~10 images; the slot is released below, after every word has been consumed)
       tc::mbar_wait(&a_empty[s], ph ^ 1);
       const uint32_t arow = tc::smem_u32(sA + s * PE_A_BYTES) + r * 128;
 #pragma unroll
@@ -218,7 +219,10 @@ k_patch_embed(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       }
       tc::fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&a_full[s]);
+      if (lane == 0) {
+        tc::mbar_arrive(&a_full[s]);
+        tc::mbar_arrive(&r_empty[s]);  // every loaded word has been consumed by the conversions above
+      }
     }
   } else if (warp >= 8) {
     // ===================== epilogue: group g takes the tiles of local parity g (accumulators g and g + 2); thread = token row

@@ -9,6 +9,8 @@
 //     proj GEMM epilogue; one block-diagonal flash-attention kernel (attn_tc.cu) serves windowed / pooled / global;
 //   * input-independent pieces (positional embeddings, dense prompt, layer-0 token self-attention, PE projections,
 //     neck∘conv_s0/s1 products) are folded at load time by the host (circuitvision_b200/sam2_infer.py).
+#include <string.h>
+
 #include <map>
 #include <string>
 #include <vector>
@@ -69,6 +71,13 @@ static int alloc_buf(cv_sam2* h, const char* name, size_t bytes, int dtype) {
   t.dtype = dtype;
   cudaError_t e = cudaMalloc(&t.p, bytes ? bytes : 16);
   if (e != cudaSuccess) return cvb_fail_cuda(e, name);
+  // debug: CVB_SAM2_FILL=<byte> fills every work buffer (or only CVB_SAM2_FILL_ONLY=<name>) at allocation, so that a read of a
+  // buffer that was never written shows up whatever the allocator handed out (scripts/sam2_uninit_probe.py)
+  if (const char* f = getenv("CVB_SAM2_FILL")) {
+    const char* only = getenv("CVB_SAM2_FILL_ONLY");
+    if (!only || !strcmp(only, name)) cudaMemset(t.p, atoi(f), bytes ? bytes : 16);
+    else cudaMemset(t.p, 0, bytes ? bytes : 16);
+  }
   h->buf[name] = t;
   return CV_OK;
 }
@@ -217,6 +226,11 @@ extern "C" int cv_sam2_finalize(cv_sam2* h) {
     snprintf(n, sizeof(n), "X%d", s);
     TRY(alloc_buf(h, n, (size_t)B * (65536 >> (2 * s)) * (E << s) * 4, 0));
   }
+  for (int s = 0; s < 3; s++) {  // 16-bit copies of the stage outputs (operands of the neck's lateral convs)
+    char n[8];
+    snprintf(n, sizeof(n), "XS%d", s);
+    TRY(alloc_buf(h, n, (size_t)B * (65536 >> (2 * s)) * (E << s) * 2, 1));
+  }
   TRY(alloc_buf(h, "s0", (size_t)B * 65536 * 32 * 4, 0));
   TRY(alloc_buf(h, "s1", (size_t)B * 16384 * 64 * 4, 0));
   TRY(alloc_buf(h, "L3", (size_t)B * 1024 * 256 * 4, 0));
@@ -275,7 +289,7 @@ static int gemm(cv_sam2* h, const bf16* A, long long lda, const bf16* W, int M, 
 
 // one Hiera block; X is the fp32 residual stream of the block's stage (updated in place), Xn the next
 // stage's stream for Q-pooled blocks.
-static int run_block(cv_sam2* h, int i, int B, float* X, float* Xn, cudaStream_t st, bool ln1_done = false) {
+static int run_block(cv_sam2* h, int i, int B, float* X, float* Xn, cudaStream_t st, bool ln1_done = false, bf16* x_copy16 = nullptr) {
   const BlockPlan& p = h->plan[i];
   const std::string pre = "b" + std::to_string(i);
   const int ws = p.ws, H = p.H, W = p.W, Cin = p.dim_in, C = p.dim_out;
@@ -289,7 +303,8 @@ static int run_block(cv_sam2* h, int i, int B, float* X, float* Xn, cudaStream_t
   bf16* Hd = BUF<bf16>(h, "Hd");
   // norm1 (+ window partition with zero pad rows)
   if (!ln1_done) {  // (block 0 after the fused patch embedding: "A" already holds norm1(X) in window-major order)
-    TRY(launch_ln_rows(X, T, Cin, WF(h, pre + ".n1.g"), WF(h, pre + ".n1.b"), 1e-6f, B, H, W, ws, h->f16, A, nullptr, st));
+    // (x_copy16: first block of a stage — X is the finished output of the previous stage, which the neck wants as a 16-bit operand)
+    TRY(launch_ln_rows(X, T, Cin, WF(h, pre + ".n1.g"), WF(h, pre + ".n1.b"), 1e-6f, B, H, W, ws, h->f16, A, nullptr, st, x_copy16));
     h->launches++;
   }
   GemmEpilogue e;
@@ -507,7 +522,8 @@ extern "C" int cv_sam2_forward(cv_sam2* h, const void* images, int input_kind, i
     if (patch_embed_supported(E, 1024)) {
       // pixels -> conv -> + pos -> X0 and, when block 0 is an 8 x 8 windowed block of the same width, its norm1 output as well
       const BlockPlan& p0 = h->plan[0];
-      ln1_fused = !p0.pool && p0.ws == 8 && p0.dim_in == E && p0.H == 256 && p0.W == 256;
+      static const int pe_ln_on = getenv("CVB_PATCH_LN") ? atoi(getenv("CVB_PATCH_LN")) : 1;  // A/B switch
+      ln1_fused = pe_ln_on && !p0.pool && p0.ws == 8 && p0.dim_in == E && p0.H == 256 && p0.W == 256;
       PatchEmbedArgs pa;
       pa.img = (const uint8_t*)images; pa.B = B; pa.S = 1024; pa.swap_rb = swap_rb; pa.fp16 = h->f16;
       pa.W = WB(h, "pe.w8"); pa.E = E; pa.pos = WF(h, "pos8"); pa.X0 = X[0];
@@ -532,11 +548,19 @@ extern "C" int cv_sam2_forward(cv_sam2* h, const void* images, int input_kind, i
     TRY(gemm(h, A, 2 * PE_K, WB(h, "pe.w"), B * 65536, E, 2 * PE_K, e, st));
   }
   h->launches++;
+  if (getenv("CVB_SAM2_STOP_AFTER_PE")) return CV_OK;  // debug (scripts/sam2_determinism_probe.py): X0 / A as the patch embedding left them
   // ---- trunk
   int stage = 0;
+  bool have_copy[3] = {false, false, false};
   for (size_t i = 0; i < h->plan.size(); i++) {
     if (h->plan[i].pool) stage++;
-    TRY(run_block(h, (int)i, B, h->plan[i].pool ? X[stage - 1] : X[stage], X[stage], st, i == 0 && ln1_fused));
+    bf16* copy16 = nullptr;
+    static const int copy_on = getenv("CVB_LN_COPY") ? atoi(getenv("CVB_LN_COPY")) : 1;  // A/B switch
+    if (copy_on && h->plan[i].pool && stage >= 1 && stage <= 3) {
+      copy16 = BUF<bf16>(h, stage == 1 ? "XS0" : stage == 2 ? "XS1" : "XS2");
+      have_copy[stage - 1] = true;
+    }
+    TRY(run_block(h, (int)i, B, h->plan[i].pool ? X[stage - 1] : X[stage], X[stage], st, i == 0 && ln1_fused, copy16));
   }
   // ---- neck (level 3 lateral, level 2 lateral + top-down + dense prompt) and the folded conv_s0 / conv_s1
   float* keys32 = BUF<float>(h, "keys32");
@@ -546,26 +570,29 @@ extern "C" int cv_sam2_forward(cv_sam2* h, const void* images, int input_kind, i
     e.bias = WF(h, "neck3.b");
     e.out_f32 = BUF<float>(h, "L3"); e.ld_f32 = 256;
     TRY(gemm(h, A, 8 * E, WB(h, "neck3.w"), B * 1024, 256, 8 * E, e, st));
-    TRY(launch_ln_rows(X[2], (long long)B * 4096, 4 * E, nullptr, nullptr, 0.f, B, 64, 64, 0, h->f16, A, nullptr, st));
+    const bf16* A2 = have_copy[2] ? BUF<bf16>(h, "XS2") : A;
+    if (!have_copy[2]) TRY(launch_ln_rows(X[2], (long long)B * 4096, 4 * E, nullptr, nullptr, 0.f, B, 64, 64, 0, h->f16, A, nullptr, st));
     GemmEpilogue e2;
     e2.bias = WF(h, "neck2.b");
     e2.res = WF(h, "dense"); e2.ld_res = 256; e2.res_row_mod = 4096;  // src = image_embed + dense prompt
     e2.out_f32 = keys32; e2.ld_f32 = 256;
-    TRY(gemm(h, A, 4 * E, WB(h, "neck2.w"), B * 4096, 256, 4 * E, e2, st));
+    TRY(gemm(h, A2, 4 * E, WB(h, "neck2.w"), B * 4096, 256, 4 * E, e2, st));
     TRY(launch_add_nearest2(keys32, BUF<float>(h, "L3"), B, 64, 64, 256, st));
     TRY(launch_ln_rows(keys32, (long long)B * 4096, 256, nullptr, nullptr, 0.f, B, 64, 64, 0, h->f16, BUF<bf16>(h, "keys16"), nullptr, st));
     TRY(sat(h, BUF<bf16>(h, "keys16"), (long long)B * 4096 * 256, st));
-    TRY(launch_ln_rows(X[1], (long long)B * 16384, 2 * E, nullptr, nullptr, 0.f, B, 128, 128, 0, h->f16, A, nullptr, st));
+    const bf16* A1 = have_copy[1] ? BUF<bf16>(h, "XS1") : A;
+    if (!have_copy[1]) TRY(launch_ln_rows(X[1], (long long)B * 16384, 2 * E, nullptr, nullptr, 0.f, B, 128, 128, 0, h->f16, A, nullptr, st));
     GemmEpilogue e3;
     e3.bias = WF(h, "s1.b");
     e3.out_f32 = BUF<float>(h, "s1"); e3.ld_f32 = 64;
-    TRY(gemm(h, A, 2 * E, WB(h, "s1.w"), B * 16384, 64, 2 * E, e3, st));
-    TRY(launch_ln_rows(X[0], (long long)B * 65536, E, nullptr, nullptr, 0.f, B, 256, 256, 0, h->f16, A, nullptr, st));
+    TRY(gemm(h, A1, 2 * E, WB(h, "s1.w"), B * 16384, 64, 2 * E, e3, st));
+    const bf16* A0 = have_copy[0] ? BUF<bf16>(h, "XS0") : A;
+    if (!have_copy[0]) TRY(launch_ln_rows(X[0], (long long)B * 65536, E, nullptr, nullptr, 0.f, B, 256, 256, 0, h->f16, A, nullptr, st));
     GemmEpilogue e4;
     e4.bias = WF(h, "s0.b");
     e4.out_f32 = BUF<float>(h, "s0"); e4.ld_f32 = 32;
-    TRY(gemm(h, A, E, WB(h, "s0.w"), B * 65536, 32, E, e4, st));
-    h->launches += 6;
+    TRY(gemm(h, A0, E, WB(h, "s0.w"), B * 65536, 32, E, e4, st));
+    h->launches += 6 - (int)have_copy[0] - (int)have_copy[1] - (int)have_copy[2];
   }
   // ---- mask decoder
   TRY(decoder_layer(h, 0, B, st));

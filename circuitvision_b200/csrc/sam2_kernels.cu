@@ -358,7 +358,7 @@ template <int L, int V>
 __global__ void __launch_bounds__(256) k_ln_rows_t(const float* __restrict__ X, const float* __restrict__ gamma,
                                                    const float* __restrict__ beta, float eps, int H, int W, int ws, int nwx,
                                                    int nwy, long long n_dst, int fp16, __nv_bfloat16* __restrict__ ob,
-                                                   float* __restrict__ of) {
+                                                   float* __restrict__ of, __nv_bfloat16* __restrict__ raw16) {
   constexpr int C = 4 * L * V, RPW = 32 / L;
   const int lane = threadIdx.x & 31, sub = lane % L;
   const long long r = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + lane / L;
@@ -409,6 +409,9 @@ __global__ void __launch_bounds__(256) k_ln_rows_t(const float* __restrict__ X, 
   for (int k = 0; k < V; k++) {
     const int i = sub + k * L;
     float4 o = v[k];
+    // 16-bit copy of the un-normalised source row, in source order (the neck's lateral conv reads the stage output as a GEMM
+    // operand: one read of the fp32 stream serves both this copy and norm1 of the next stage's first block)
+    if (raw16 && src >= 0) *(uint2*)(raw16 + src * C + i * 4) = make_uint2(tc::pack16(fp16, o.x, o.y), tc::pack16(fp16, o.z, o.w));
     if (gamma && src >= 0) {
       float4 g = __ldg((const float4*)gamma + i), bb = __ldg((const float4*)beta + i);
       o.x = (o.x - mean) * rstd * g.x + bb.x;
@@ -425,15 +428,15 @@ __global__ void __launch_bounds__(256) k_ln_rows_t(const float* __restrict__ X, 
 
 template <int L, int V>
 static int launch_ln_t(const float* X, const float* gamma, const float* beta, float eps, int H, int W, int ws, int nwx, int nwy,
-                       long long n_dst, int fp16, __nv_bfloat16* ob, float* of, cudaStream_t st) {
+                       long long n_dst, int fp16, __nv_bfloat16* ob, float* of, __nv_bfloat16* raw16, cudaStream_t st) {
   const long long rows_per_block = 8 * (32 / L);
   CVB_LAUNCH((k_ln_rows_t<L, V>), dim3((unsigned)((n_dst + rows_per_block - 1) / rows_per_block)), dim3(256), 0, st, X, gamma,
-             beta, eps, H, W, ws, nwx, nwy, n_dst, fp16, ob, of);
+             beta, eps, H, W, ws, nwx, nwy, n_dst, fp16, ob, of, raw16);
   return CV_OK;
 }
 
 int launch_ln_rows(const float* X, long long n_src_rows, int C, const float* gamma, const float* beta, float eps, int B,
-                   int H, int W, int ws, int fp16, __nv_bfloat16* out_bf16, float* out_f32, cudaStream_t st) {
+                   int H, int W, int ws, int fp16, __nv_bfloat16* out_bf16, float* out_f32, cudaStream_t st, __nv_bfloat16* raw16) {
   if ((C & 3) || C > 1536) return cvb_fail(CV_ERR_INVALID, "ln_rows: C must be a multiple of 4 and <= 1536");
   int nwx = 0, nwy = 0;
   long long n_dst = n_src_rows;
@@ -442,18 +445,20 @@ int launch_ln_rows(const float* X, long long n_src_rows, int C, const float* gam
     nwy = (H + ws - 1) / ws;
     n_dst = (long long)B * nwx * nwy * ws * ws;
   }
-  cvb_next_work((double)n_src_rows * C * 4 + (double)n_dst * C * (out_bf16 ? 2 : 0) + (double)n_dst * C * (out_f32 ? 4 : 0));
+  cvb_next_work((double)n_src_rows * C * 4 + (double)n_dst * C * (out_bf16 ? 2 : 0) + (double)n_dst * C * (out_f32 ? 4 : 0) +
+                (double)n_src_rows * C * (raw16 ? 2 : 0));
   if (cvb_profile_on()) {
     char nm[96];
-    snprintf(nm, sizeof(nm), "ln_rows R%lld C%d ws%d%s", n_src_rows, C, ws, gamma ? "" : " cast");
+    snprintf(nm, sizeof(nm), "ln_rows R%lld C%d ws%d%s%s", n_src_rows, C, ws, gamma ? "" : " cast", raw16 ? " +copy" : "");
     cvb_next_name(nm);
   }
 #define CVB_LN_CASE(CC, LL, VV) \
-  if (C == CC) return launch_ln_t<LL, VV>(X, gamma, beta, eps, H, W, ws, nwx, nwy, n_dst, fp16, out_bf16, out_f32, st);
+  if (C == CC) return launch_ln_t<LL, VV>(X, gamma, beta, eps, H, W, ws, nwx, nwy, n_dst, fp16, out_bf16, out_f32, raw16, st);
   CVB_LN_CASE(96, 8, 3) CVB_LN_CASE(192, 16, 3) CVB_LN_CASE(384, 32, 3) CVB_LN_CASE(768, 32, 6) CVB_LN_CASE(256, 16, 4)
   CVB_LN_CASE(64, 8, 2) CVB_LN_CASE(112, 4, 7) CVB_LN_CASE(224, 8, 7) CVB_LN_CASE(448, 16, 7) CVB_LN_CASE(896, 32, 7)
   CVB_LN_CASE(144, 4, 9) CVB_LN_CASE(288, 8, 9) CVB_LN_CASE(576, 16, 9) CVB_LN_CASE(1152, 32, 9)
 #undef CVB_LN_CASE
+  if (raw16) return cvb_fail(CV_ERR_INVALID, "ln_rows: the 16-bit source copy needs one of the templated widths");
   CVB_LAUNCH(k_ln_rows, dim3((unsigned)((n_dst + 7) / 8)), dim3(256), 0, st, X, C, gamma, beta, eps, H, W, ws, nwx, nwy,
              n_dst, fp16, out_bf16, out_f32);
   return CV_OK;

@@ -35,7 +35,7 @@ int launch_preprocess_pages(const uint8_t* pages, const void* geom, int B, int m
 // ---- LayerNorm over the channel dim with optional window partition (zero rows for window padding).
 // ws == 0: identity row order.  gamma == nullptr: plain fp32 -> bf16 cast.  out_f32 optional (normalised, fp32).
 int launch_ln_rows(const float* X, long long n_src_rows, int C, const float* gamma, const float* beta, float eps,
-                   int B, int H, int W, int ws, int fp16, __nv_bfloat16* out_bf16, float* out_f32, cudaStream_t st);
+                   int B, int H, int W, int ws, int fp16, __nv_bfloat16* out_bf16, float* out_f32, cudaStream_t st, __nv_bfloat16* raw16 = nullptr);
 
 // ---- Q pooling: Qp[(b,win,py,px), c] = max_{2x2} QKV[(b,win,2py+dy,2px+dx), c], c < Cq (bf16, window-major)
 int launch_pool_q(const __nv_bfloat16* qkv, long long ld, int n_windows, int ws, int Cq, int fp16, __nv_bfloat16* qp,

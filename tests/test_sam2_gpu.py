@@ -285,3 +285,33 @@ def test_page_flow_reclassify_crop_segment_nodes_netlist(pair):
     assert len(a) == len(b) and all(x[0] == y[0] and x[1] == y[1] and np.array_equal(x[2], y[2]) for x, y in zip(a, b))
     text = "\n".join(A.stringify_line(l) for l in A.generate_netlist_from_nodes(nodes))
     assert text == netlist.netlist_text(rn)
+
+
+@pytest.mark.parametrize("variant,n", [("tiny", 48), ("base_plus", 16)])
+def test_forward_is_bit_deterministic(variant, n):
+    """The same batch three times through one engine: every stage output and the logits are bit-identical.  No kernel on this
+    path uses floating-point atomics, so any difference is a race — round 2 found two this way (scripts/sam2_determinism_probe.py):
+    the fused patch embedding released its raw-pixel ring slot before the loaded words had arrived in registers (a few tokens per
+    ~10 images changed from run to run), and the pooled q chunks of the Q-pooled qkv GEMM advanced the staging-buffer alternation
+    without committing a TMA-store group (a 32 x 32 k / v box could be overwritten while its store was still reading it)."""
+    import numpy as np
+    from circuitvision_b200 import sam2_infer, synth
+    E = {"tiny": 96, "base_plus": 112}[variant]
+    imgs = [synth.make_schematic(40 + i, 1024, render_rgb=True)[2] for i in range(6)]
+    d = torch.from_numpy(np.stack([imgs[i % 6] for i in range(n)])).cuda()
+    m = sam2_infer.build_random_init(variant, device=torch.device("cuda:0"), seed=0, max_batch=n)
+    eng = m.engine()
+    bufs = [("X0", (n, 65536 * E)), ("X1", (n, 16384 * 2 * E)), ("X2", (n, 4096 * 4 * E)), ("X3", (n, 1024 * 8 * E))]
+    snaps = []
+    for _ in range(3):
+        r = eng.forward(d, 0, True, want_high=False, want_low=True, want_mask=False)
+        torch.cuda.synchronize()
+        snap = {"low": r["low"].clone()}
+        for name, shape in bufs:
+            snap[name] = eng.read_buffer(name, shape).clone()
+        snaps.append(snap)
+    for k in (1, 2):
+        for name in snaps[0]:
+            assert torch.equal(snaps[0][name], snaps[k][name]), (variant, name, k)
+    del m, eng, snaps
+    torch.cuda.empty_cache()
