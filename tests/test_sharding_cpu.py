@@ -26,16 +26,19 @@ def test_single_process_passthrough():
     assert run_sharded(list("abc"), lambda xs, r: [x.upper() + str(i) for x, i in zip(xs, r)]) == ["A0", "B1", "C2"]
 
 
-def _worker(rank, world, port, n, q):
+def _worker(rank, world, port, n, q, stream_chunk=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         items = [{"seed": i} for i in range(n)]
 
         def fn(xs, r):  # stand-in for segment + node analysis on this rank's device
-            return [{"image": i, "rank": rank, "nodes": [x["seed"] % 3, i]} for x, i in zip(xs, r)]
+            res = [{"image": i, "rank": rank, "nodes": [x["seed"] % 3, i]} for x, i in zip(xs, r)]
+            if stream_chunk is None:
+                return res
+            return (res[k:k + 3] for k in range(0, len(res), 3))  # an iterator of device batches of 3 images
 
-        full = run_sharded(items, fn)
+        full = run_sharded(items, fn, stream_chunk=stream_chunk)
         dist.barrier()
         if rank == 0:
             q.put(full)
@@ -45,15 +48,15 @@ def _worker(rank, world, port, n, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n", [7, 64])
-def test_two_rank_gloo_gather_in_image_order(n):
+@pytest.mark.parametrize("n,stream_chunk", [(7, None), (64, None), (7, 2), (64, 8), (5, 4)])
+def test_two_rank_gloo_gather_in_image_order(n, stream_chunk):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q, stream_chunk)) for r in range(2)]
     for p in procs:
         p.start()
     full = q.get()
