@@ -248,9 +248,26 @@ def _gemm_bytes(name):
     return M * K * 2 + N * K * 2 + M * N * (2 if "->b" in tag else 4) + (M * N * 4 if "+r" in tag else 0), 2.0 * M * N * K
 
 
+def _fused_bytes(name):
+    """Algorithmic HBM bytes per launch of the non-GEMM tensor kernels, from the shape tag: attention reads
+    Q, K, V and writes O once (16-bit); the fused MLP reads and writes the fp32 rows once; the patch embedding reads the
+    raw pixels and writes X0 (fp32) + norm1 (16-bit)."""
+    m = re.match(r"attn(?:_global)? Mq(\d+) Wq(\d+) Wkv(\d+) h(\d+) d(\d+)", name)
+    if m:
+        Mq, Wq, Wkv, h, d = (int(x) for x in m.groups())
+        return 2.0 * d * h * (2 * Mq + 2 * (Mq // Wq) * Wkv)
+    m = re.match(r"mlp M(\d+) C(\d+)", name)
+    if m:
+        return 8.0 * int(m.group(1)) * int(m.group(2))
+    m = re.match(r"patch_embed M(\d+) E(\d+)", name)
+    if m:
+        return float(m.group(1)) * (12 + 6 * int(m.group(2)))
+    return None
+
+
 def _shape_row(r, steps, tens_peak, hbm_peak):
-    """One launch group of the timed region: achieved rate and — for GEMM shapes, whose algorithmic bytes follow from the
-    shape tag — its fraction of BOTH rooflines."""
+    """One launch group of the timed region: achieved rate and its fraction of BOTH rooflines (algorithmic bytes follow
+    from the shape tag): the windowed-attention and stage-1/2 shapes are HBM-bound, not tensor-bound."""
     row = {"name": r["name"], "launches": r["launches"], "ms_per_step": r["ms"] / steps,
            "rate_T_per_s": r["work"] / max(r["ms"], 1e-9) / 1e9}
     gb = _gemm_bytes(r["name"])
@@ -260,6 +277,9 @@ def _shape_row(r, steps, tens_peak, hbm_peak):
         row["hbm_frac"] = gb[0] / sec / 1e9 / hbm_peak
     elif r["name"].startswith(("attn", "mlp", "patch_embed")):
         row["tensor_frac"] = row["rate_T_per_s"] / tens_peak
+        fb = _fused_bytes(r["name"])
+        if fb:
+            row["hbm_frac"] = fb / sec / 1e9 / hbm_peak
     return row
 
 
