@@ -736,128 +736,91 @@ int launch_tok_self_attn(const float* q, const float* k, const float* v, int B, 
 }
 
 // tokens -> image attention, d == 16.  CTA = (key split, head, image): stages its 128 keys/values of one head in shared
-// memory; thread = (key sub-range, decoder token): an online softmax over 128 / nsub keys with (max, sum, O[16]) in
-// registers, no cross-lane reductions.  With thread = token alone the 38 tokens of the mask decoder left the second
-// warp of every CTA with 6 live lanes (10 240 warp-instructions per split for 38 queries); 4 sub-ranges x 38 tokens
-// fill 152 of 160 lanes (6 400).  A warp straddles at most two sub-ranges: each sub-range's rows are skewed by 16
-// bytes so that the two broadcast addresses of one LDS.128 fall into different banks.  The sub-range partials are
-// merged through shared memory; the partials per (query, split) are merged by k_attn_t2i_combine.
-constexpr int T2I_SPLIT_KEYS = 128;                     // 16 KB of shared memory per CTA
-constexpr int T2I_SM_HALF = T2I_SPLIT_KEYS * 16 + 16;   // keys (or values) of a split + the skew of up to 4 sub-ranges
-__global__ void __launch_bounds__(256) k_attn_t2i_part(const float* __restrict__ q, long long q_img_stride,
-                                                       const float* __restrict__ K, const float* __restrict__ V,
-                                                       long long ld_kv, int T, int Nk, int heads, int nsub,
-                                                       float* __restrict__ part) {
-  __shared__ __align__(16) float sm[2 * T2I_SM_HALF];
-  float* sk = sm;
-  float* sv = sm + T2I_SM_HALF;
+// memory; thread = one decoder token (query) running an online softmax over the split's keys.  Every lane reads the
+// same K/V address (broadcast LDS.128, no bank conflicts) and keeps its (max, sum, O[16]) in registers, so there are no
+// cross-lane reductions at all; the partials per (query, split) are merged by k_attn_t2i_combine.
+constexpr int T2I_SPLIT_KEYS = 128;  // 16 KB of shared memory per CTA -> 14 CTAs per SM
+__global__ void __launch_bounds__(64) k_attn_t2i_part(const float* __restrict__ q, long long q_img_stride,
+                                                      const float* __restrict__ K, const float* __restrict__ V,
+                                                      long long ld_kv, int T, int Nk, int heads, float* __restrict__ part) {
+  __shared__ __align__(16) float sk[T2I_SPLIT_KEYS * 16];
+  __shared__ __align__(16) float sv[T2I_SPLIT_KEYS * 16];
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int nsplit = gridDim.x;
   const int k0 = split * T2I_SPLIT_KEYS;
   const int nk = min(T2I_SPLIT_KEYS, Nk - k0);
-  const int kps = T2I_SPLIT_KEYS / nsub;  // keys per sub-range (a multiple of 8)
-  for (int i = threadIdx.x; i < nk * 4; i += blockDim.x) {
+  for (int i = threadIdx.x; i < nk * 4; i += 64) {
     int j = i >> 2, c = (i & 3) * 4;
     long long row = (long long)b * Nk + k0 + j;
-    const int d = j * 16 + (j / kps) * 4 + c;
-    *(float4*)(sk + d) = *(const float4*)(K + row * ld_kv + h * 16 + c);
-    *(float4*)(sv + d) = *(const float4*)(V + row * ld_kv + h * 16 + c);
+    *(float4*)(sk + j * 16 + c) = *(const float4*)(K + row * ld_kv + h * 16 + c);
+    *(float4*)(sv + j * 16 + c) = *(const float4*)(V + row * ld_kv + h * 16 + c);
   }
   __syncthreads();
-  const int sub = threadIdx.x / T, t = threadIdx.x - sub * T;
-  const bool live = sub < nsub;
+  const int t = threadIdx.x;
+  if (t >= T) return;
   const int C = heads * 16;
+  const float* qp = q + (long long)b * q_img_stride + (long long)t * C + h * 16;
+  // packed fp32x2 arithmetic along the head dimension: q, k, v and the output accumulator are 8 pairs each, so a key
+  // costs 8 + 8 FFMA2 instead of 16 + 16 FFMA (the loop is issue-bound: one thread per query token)
+  uint64_t qv[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) qv[i] = pk2(__ldg(qp + 2 * i) * 0.36067376f, __ldg(qp + 2 * i + 1) * 0.36067376f);  // 1/sqrt(16) * log2(e)
   float m = -INFINITY, l = 0.f;
   uint64_t o[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) o[i] = 0ull;
-  if (live) {
-    const float* qp = q + (long long)b * q_img_stride + (long long)t * C + h * 16;
-    // packed fp32x2 arithmetic along the head dimension: q, k, v and the output accumulator are 8 pairs each, so a key
-    // costs 8 + 8 FFMA2 instead of 16 + 16 FFMA (the loop is issue-bound)
-    uint64_t qv[8];
+  for (int j0 = 0; j0 < nk; j0 += 8) {
+    // 8 keys per step: one rescale per step instead of per key
+    float sc[8], mx = m;
 #pragma unroll
-    for (int i = 0; i < 8; i++) qv[i] = pk2(__ldg(qp + 2 * i) * 0.36067376f, __ldg(qp + 2 * i + 1) * 0.36067376f);  // 1/sqrt(16) * log2(e)
-    const int je = min(sub * kps + kps, nk);
-    const float* skb = sk + sub * 4;
-    const float* svb = sv + sub * 4;
-    for (int j0 = sub * kps; j0 < je; j0 += 8) {
-      // 8 keys per step: one rescale per step instead of per key
-      float sc[8], mx = m;
+    for (int u = 0; u < 8; u++) {
+      float sdot = -INFINITY;
+      if (j0 + u < nk) {
+        const ulonglong2* kr = (const ulonglong2*)(sk + (j0 + u) * 16);
+        uint64_t acc = 0ull;
 #pragma unroll
-      for (int u = 0; u < 8; u++) {
-        float sdot = -INFINITY;
-        if (j0 + u < je) {
-          const ulonglong2* kr = (const ulonglong2*)(skb + (j0 + u) * 16);
-          uint64_t acc = 0ull;
-#pragma unroll
-          for (int c = 0; c < 4; c++) {
-            const ulonglong2 kk = kr[c];
-            acc = fma2(qv[2 * c], kk.x, acc);
-            acc = fma2(qv[2 * c + 1], kk.y, acc);
-          }
-          float a0, a1;
-          up2(acc, a0, a1);
-          sdot = a0 + a1;
+        for (int c = 0; c < 4; c++) {
+          const ulonglong2 kk = kr[c];
+          acc = fma2(qv[2 * c], kk.x, acc);
+          acc = fma2(qv[2 * c + 1], kk.y, acc);
         }
-        sc[u] = sdot;
-        mx = fmaxf(mx, sdot);
+        float a0, a1;
+        up2(acc, a0, a1);
+        sdot = a0 + a1;
       }
-      float alpha;
-      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(alpha) : "f"(m - mx));  // m = -inf -> 0
-      l *= alpha;
-      const uint64_t al2 = pk2(alpha, alpha);
+      sc[u] = sdot;
+      mx = fmaxf(mx, sdot);
+    }
+    float alpha;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(alpha) : "f"(m - mx));  // m = -inf -> 0
+    l *= alpha;
+    const uint64_t al2 = pk2(alpha, alpha);
 #pragma unroll
-      for (int i = 0; i < 8; i++) o[i] = mul2(o[i], al2);
-      m = mx;
+    for (int i = 0; i < 8; i++) o[i] = mul2(o[i], al2);
+    m = mx;
 #pragma unroll
-      for (int u = 0; u < 8; u++) {
-        float pe;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe) : "f"(sc[u] - mx));  // masked keys: ex2(-inf) = 0
-        l += pe;
-        if (j0 + u < je) {
-          const ulonglong2* vr = (const ulonglong2*)(svb + (j0 + u) * 16);
-          const uint64_t pe2 = pk2(pe, pe);
+    for (int u = 0; u < 8; u++) {
+      float pe;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe) : "f"(sc[u] - mx));  // masked keys: ex2(-inf) = 0
+      l += pe;
+      if (j0 + u < nk) {
+        const ulonglong2* vr = (const ulonglong2*)(sv + (j0 + u) * 16);
+        const uint64_t pe2 = pk2(pe, pe);
 #pragma unroll
-          for (int c = 0; c < 4; c++) {
-            const ulonglong2 vv = vr[c];
-            o[2 * c] = fma2(pe2, vv.x, o[2 * c]);
-            o[2 * c + 1] = fma2(pe2, vv.y, o[2 * c + 1]);
-          }
+        for (int c = 0; c < 4; c++) {
+          const ulonglong2 vv = vr[c];
+          o[2 * c] = fma2(pe2, vv.x, o[2 * c]);
+          o[2 * c + 1] = fma2(pe2, vv.y, o[2 * c + 1]);
         }
       }
     }
   }
-  // merge the sub-range partials of each token through shared memory (the staged keys are dead after the barrier)
-  __syncthreads();
-  if (live) {
-    float* sp = sm + threadIdx.x * 18;
-    sp[0] = m;
-    sp[1] = l;
-#pragma unroll
-    for (int i = 0; i < 8; i++) up2(o[i], sp[2 + 2 * i], sp[3 + 2 * i]);
-  }
-  __syncthreads();
-  if ((int)threadIdx.x >= T) return;
-  float mx = -INFINITY;
-  for (int s2 = 0; s2 < nsub; s2++) mx = fmaxf(mx, sm[(s2 * T + t) * 18]);
-  float lt = 0.f, ot[16];
-#pragma unroll
-  for (int i = 0; i < 16; i++) ot[i] = 0.f;
-  for (int s2 = 0; s2 < nsub; s2++) {
-    const float* sp = sm + (s2 * T + t) * 18;
-    float w = 0.f;
-    if (sp[0] != -INFINITY) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(sp[0] - mx));  // an empty sub-range has no weight
-    lt = fmaf(w, sp[1], lt);
-#pragma unroll
-    for (int i = 0; i < 16; i++) ot[i] = fmaf(w, sp[2 + i], ot[i]);
-  }
   // partial in natural-log convention of the combine kernel: stored max is in log2 units -> convert
   float* pp = part + ((((long long)b * heads + h) * T + t) * nsplit + split) * 18;
-  pp[0] = mx * 0.69314718056f;
-  pp[1] = lt;
+  pp[0] = m * 0.69314718056f;
+  pp[1] = l;
 #pragma unroll
-  for (int i = 0; i < 16; i++) pp[2 + i] = ot[i];
+  for (int i = 0; i < 8; i++) up2(o[i], pp[2 + 2 * i], pp[3 + 2 * i]);
 }
 
 __global__ void k_attn_t2i_combine(const float* __restrict__ part, int T, int heads, int nsplit, long long total,
@@ -889,16 +852,11 @@ size_t attn_t2i_scratch_floats(int B, int T, int heads, int d) {
 int launch_attn_t2i(const float* q, long long q_img_stride, const float* K, const float* V, long long ld_kv, int B, int T,
                     int Nk, int heads, int d, float* out, float* scratch, cudaStream_t st) {
   if (d != 16) return cvb_fail(CV_ERR_INVALID, "attn_t2i: head dim must be 16");
-  if (T < 1 || T > 64) return cvb_fail(CV_ERR_INVALID, "attn_t2i: 1..64 query tokens");
   int nsplit = (Nk + T2I_SPLIT_KEYS - 1) / T2I_SPLIT_KEYS;
   if (nsplit > 32) return cvb_fail(CV_ERR_INVALID, "attn_t2i: at most 4096 keys");
   cvb_next_work(4.0 * B * (double)T * Nk * heads * d);
-  // sub-ranges per CTA: as many of {4, 2, 1} as fit 256 threads and the merge area (18 floats per thread over the staged keys)
-  int nsub = 4;
-  while (nsub > 1 && (nsub * T > 256 || nsub * T * 18 > 2 * T2I_SM_HALF)) nsub >>= 1;
-  const int threads = (nsub * T + 31) / 32 * 32;
-  CVB_LAUNCH(k_attn_t2i_part, dim3(nsplit, heads, B), dim3(threads), 0, st, q, q_img_stride, K, V, ld_kv, T, Nk, heads, nsub,
-             scratch);
+  if (T > 64) return cvb_fail(CV_ERR_INVALID, "attn_t2i: at most 64 query tokens");
+  CVB_LAUNCH(k_attn_t2i_part, dim3(nsplit, heads, B), dim3(64), 0, st, q, q_img_stride, K, V, ld_kv, T, Nk, heads, scratch);
   long long total = (long long)B * heads * T * 16;
   CVB_LAUNCH(k_attn_t2i_combine, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, scratch, T, heads, nsplit, total,
              out);
