@@ -359,25 +359,31 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
           for (int it = 0; it < 8; it++) dest[it] = __shfl_sync(0xffffffffu, dmine, it * 4 + sub_row);
         }
       }
+      tc::mbar_wait(&tfull[acc], acc_phase);
+      tc::tc_fence_after();
+      if (ew == 0 && lane == 0) gemm_trace(p, 3, lt);
+#pragma unroll 1
       // BN / 32 chunks over EW / 4 warp groups: with 3 chunks and 2 groups one group would take two chunks of EVERY tile;
       // rotating the start group evens that out over consecutive tiles (the accumulators are double-buffered, so a group
       // that finishes early moves on to the next tile)
       const int c_first = cg_rot;
       if ((BN / 32) % (EW / 4) != 0 && p.rotate) cg_rot = (cg_rot + (EW / 4) - ((BN / 32) % (EW / 4))) % (EW / 4);
-      // Residual of the TMA-store paths, software-pipelined: the rows of chunk c are requested one chunk ahead — those of a
-      // tile's first chunk BEFORE the wait for its accumulator — so their HBM latency (the longest link of the per-chunk
-      // chain of the K <= 384 residual shapes) runs under the MMA wait / the previous chunk's conversion and store.  A
-      // residual element is read only by the tile and chunk that writes it (in-place residual stream), so loading ahead of
-      // other chunks' stores is safe.
-      //   res_staged: lanes ALONG the columns (8 lanes per 128-byte row piece, 4 rows per instruction = 4 L1 wavefronts instead
-      //   of the 32 of a row-per-thread load), handed to the row-owning thread through the staging buffer below;
-      //   otherwise this thread's own row, 32 consecutive floats
-      const bool res_staged = TMA_OUT && OUT == 0 && RES == 1 && p.res_stage;
-      const bool res_pref = p.res_prefetch != 0;
-      float4 rv[8];
-      auto load_rv = [&](int c) {
+      for (int c = c_first; c < BN / 32; c += EW / 4) {
         const int col0 = nb * BN + c * 32;
-        const int ncols = p.N - col0;
+        const int ncols = p.N - col0;  // valid columns of this chunk: >= 32, 16 (N % 32 == 16) or <= 0
+        uint8_t* buf = bufs + (nbuf % EPI_BUFS) * GEMM_EPI_BUF;
+        // The staging buffers alternate with the TMA-store groups: wait_group.read<EPI_BUFS - 1> below frees the buffer used
+        // EPI_BUFS uses ago only if every use in between committed exactly one group.  The pooled q chunks of a Q-pooled qkv GEMM
+        // write their result with ordinary stores (no group), so they must not advance the alternation: with nbuf++ here, a
+        // k / v chunk could overwrite a box its predecessor's TMA store was still reading (seen as run-to-run differences of
+        // one attention window, scripts/sam2_determinism_probe.py).
+        if (!(MAP == GEMM_MAP_QPOOL && col0 < e.pool_cols)) nbuf++;
+        // residual for the TMA path: this thread's own row, 32 consecutive floats (issued before the TMEM wait)
+        float4 rv[8];
+        // residual through the staging buffer (fp32 boxes): loaded with lanes ALONG the columns (8 lanes per 128-byte row piece,
+        // 4 rows per instruction = 4 L1 wavefronts instead of the 32 of a row-per-thread load), handed to the row-owning thread
+        // through the buffer that then carries the result
+        const bool res_staged = TMA_OUT && OUT == 0 && RES == 1 && p.res_stage;
         if (res_staged) {
           const int prow = lane >> 3, pcol = lane & 7;
 #pragma unroll
@@ -397,22 +403,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
             for (int j = 0; j < 8; j++) rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-      };
-      if (res_pref && c_first < BN / 32) load_rv(c_first);
-      tc::mbar_wait(&tfull[acc], acc_phase);
-      tc::tc_fence_after();
-      if (ew == 0 && lane == 0) gemm_trace(p, 3, lt);
-      for (int c = c_first; c < BN / 32; c += EW / 4) {
-        const int col0 = nb * BN + c * 32;
-        const int ncols = p.N - col0;  // valid columns of this chunk: >= 32, 16 (N % 32 == 16) or <= 0
-        uint8_t* buf = bufs + (nbuf % EPI_BUFS) * GEMM_EPI_BUF;
-        // The staging buffers alternate with the TMA-store groups: wait_group.read<EPI_BUFS - 1> below frees the buffer used
-        // EPI_BUFS uses ago only if every use in between committed exactly one group.  The pooled q chunks of a Q-pooled qkv GEMM
-        // write their result with ordinary stores (no group), so they must not advance the alternation: with nbuf++ here, a
-        // k / v chunk could overwrite a box its predecessor's TMA store was still reading (seen as run-to-run differences of
-        // one attention window, scripts/sam2_determinism_probe.py).
-        if (!(MAP == GEMM_MAP_QPOOL && col0 < e.pool_cols)) nbuf++;
-        if (!res_pref) load_rv(c);  // A/B switch (CVB_GEMM_RES_PREF=0): request the residual inside the chunk, as before
         uint32_t v[32];
         tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32, v);
         // SHUFFLE2: this 32-column chunk lies inside one (dy,dx) group; bias/out column = co
@@ -483,7 +473,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
 #pragma unroll
             for (int j = 0; j < 8; j++) { f[4 * j] += rv[j].x; f[4 * j + 1] += rv[j].y; f[4 * j + 2] += rv[j].z; f[4 * j + 3] += rv[j].w; }
           }
-          if (res_pref && c + EW / 4 < BN / 32) load_rv(c + EW / 4);  // rv is dead from here on: the next chunk's rows
           if (MAP == GEMM_MAP_QPOOL && col0 < e.pool_cols) {
             // q columns of a Q-pooled block: the chunk is staged as 16-bit rows (rounding is monotonic, so the maximum of the
             // rounded values is the rounded maximum), then lane (j, cg) = (lane / 4, lane % 4) reduces pooled token j of
@@ -670,8 +659,6 @@ static int launch_cfg(const __nv_bfloat16* A, long long lda, const __nv_bfloat16
   // same-box A/B (10 reps): N384 K1536 843 -> 982 TFLOP/s, N768 K3072 1178 -> 1292, N192 K192 / N384 K384 +9 %; the 96-wide
   // shapes, already at 5.5 TB/s, lose 3 % to the extra shared-memory round trip and keep the direct loads
   p.res_stage = res_stage_on && N >= 128;
-  static const int res_pref_on = getenv("CVB_GEMM_RES_PREF") ? atoi(getenv("CVB_GEMM_RES_PREF")) : 1;
-  p.res_prefetch = res_pref_on && epi.res != nullptr;
   long long tiles = (long long)((p.n_tiles_m + CG - 1) / CG) * (AST ? 1 : p.n_tiles_n);  // AST: work unit = a row block
   const int max_groups = num_sms / CG;
   int grid = (int)(tiles < max_groups ? tiles : max_groups) * CG;

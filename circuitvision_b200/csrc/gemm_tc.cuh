@@ -49,7 +49,6 @@ struct GemmProblem {
   int n_tiles_m, n_tiles_n;
   int rotate;  // epilogue: the column-chunk group a warp takes rotates from tile to tile (balances BN / 32 chunks over EW / 4 groups)
   int res_stage;  // epilogue: fp32 residual loaded lanes-along-columns and passed through the staging buffer
-  int res_prefetch;  // epilogue: residual rows of a chunk requested one chunk ahead (the first chunk's before the accumulator wait)
   unsigned long long* trace;  // debug timeline of CTA 0 (cv_gemm_set_trace): slot = event * 256 + local tile index, else nullptr
 };
 
