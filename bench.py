@@ -57,6 +57,7 @@ def _args():
     ap.add_argument("--total", type=int, default=8192, help="cfg5: schematics in the whole job (sharded over the ranks)")
     ap.add_argument("--operands", default="fp16", choices=["fp16", "bf16"],
                     help="16-bit tensor-core operand format of the SAM 2.1 path (DESIGN.md section 2)")
+    ap.add_argument("--depth", type=int, default=2, help="batches in flight in the e2e pipeline (CropPipeline / MaskPipeline slots)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the cfg3 / cfg4 sub-records of the default run")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with events in the timed region")
@@ -468,10 +469,12 @@ def run_main_workload(ctx, a, workload):
     value = B * a.steps * world / (total_ms / 1e3)
 
     # ---- e2e through the public batch API with pinned host buffers
-    e2e_steps = max(2, min(a.steps, 5))
+    # the same K steps as the resident region (capped at 20): with 5 the pipeline's fill and drain — the first upload before any
+    # compute, the last batch's node analysis + download + host lists after it — were a tenth of the measurement
+    e2e_steps = max(2, min(a.steps, 20))
     if workload == "pipeline":
         from circuitvision_b200.pipeline import CropPipeline
-        pipe = CropPipeline(sam, B, depth=2)
+        pipe = CropPipeline(sam, B, depth=a.depth)
         sink = [0]
 
         def consume(res):
@@ -481,14 +484,14 @@ def run_main_workload(ctx, a, workload):
 
         def run_e2e(steps):
             for i in range(steps):
-                if pipe._inflight == 2:
+                if pipe.inflight == pipe.depth:
                     consume(pipe.collect())
                 p = i % n_pool
                 pipe.submit(h_rgb[p], pool_boxes[p])
-            while pipe._inflight:
+            while pipe.inflight:
                 consume(pipe.collect())
 
-        run_e2e(2)  # warm (allocates the pinned result buffers)
+        run_e2e(max(2, a.depth))  # warm: every slot allocates its pinned result buffers on first use
         ctx.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
