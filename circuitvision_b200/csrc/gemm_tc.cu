@@ -368,6 +368,40 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
       // that finishes early moves on to the next tile)
       const int c_first = cg_rot;
       if ((BN / 32) % (EW / 4) != 0 && p.rotate) cg_rot = (cg_rot + (EW / 4) - ((BN / 32) % (EW / 4))) % (EW / 4);
+      // In-place residual stream (res == out): ask for the residual boxes this warp will add in its NEXT tile to be brought
+      // into L2 now — one bulk-prefetch instruction per 32 x 32 box through the output's tensor map, no registers, no
+      // shared memory.  The row-per-thread residual loads of the K <= 384 shapes then wait for an L2 hit instead of HBM
+      // (ncu: a third of the epilogue warps' stall samples sat on the first use of those loads).  Every residual element
+      // is read by exactly one tile, so nothing is prefetched twice.
+      if (TMA_OUT && OUT == 0 && RES != 0 && p.res_l2pf && lane == 0) {
+        const int t2 = t + tile_stride;
+        if (t2 < n_tiles) {
+          int tm2, nb2;
+          tile_mn(t2, tm2, nb2);
+          const long long r2 = (long long)(tm2 * CG + rank) * GEMM_BM + quad * 32;
+          if (r2 < p.M)
+            for (int c2 = cg_rot; c2 < BN / 32; c2 += EW / 4) {
+              const int col2 = nb2 * BN + c2 * 32;
+              if (col2 < p.N) tc::tma_prefetch_2d(&tmap_out, col2, (int)r2);
+            }
+        }
+      }
+      // window un-partition epilogues (rows scattered by the map, plain stores): every lane prefetches the 128-byte
+      // pieces of its own destination row of the next tile
+      if (!TMA_OUT && MAP != GEMM_MAP_POOL2 && p.res_l2pf && map == GEMM_MAP_UNWINDOW && has_res) {
+        const int t2 = t + tile_stride;
+        if (t2 < n_tiles) {
+          int tm2, nb2;
+          tile_mn(t2, tm2, nb2);
+          const long long m2 = (long long)(tm2 * CG + rank) * GEMM_BM + quad * 32 + lane;
+          const long long d2 = m2 < p.M ? gemm_dest_row(e, map, m2) : -1;
+          if (d2 >= 0) {
+            const float* rp2 = e.res + d2 * e.ld_res + nb2 * BN;
+            for (int c2 = cg_rot; c2 < BN / 32; c2 += EW / 4)
+              if (nb2 * BN + c2 * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp2 + c2 * 32));
+          }
+        }
+      }
       for (int c = c_first; c < BN / 32; c += EW / 4) {
         const int col0 = nb * BN + c * 32;
         const int ncols = p.N - col0;  // valid columns of this chunk: >= 32, 16 (N % 32 == 16) or <= 0
@@ -659,6 +693,12 @@ static int launch_cfg(const __nv_bfloat16* A, long long lda, const __nv_bfloat16
   // same-box A/B (10 reps): N384 K1536 843 -> 982 TFLOP/s, N768 K3072 1178 -> 1292, N192 K192 / N384 K384 +9 %; the 96-wide
   // shapes, already at 5.5 TB/s, lose 3 % to the extra shared-memory round trip and keep the direct loads
   p.res_stage = res_stage_on && N >= 128;
+  static const int res_l2pf_on = getenv("CVB_GEMM_RES_L2PF") ? atoi(getenv("CVB_GEMM_RES_L2PF")) : 1;
+  // same-box A/B (scripts/gpu_ab.sh CVB_GEMM_RES_L2PF, two alternating runs): N192 K192 +res 0.911 -> 0.820 ms (2 launches), N384 K384
+  // +res 0.884 -> 0.772 (4), its windowed form 0.762 -> 0.719 (3), N96 K96 +res 0.912 -> 0.867; the long-K shapes, whose MMA loop is
+  // bound by operand delivery, LOSE to the extra requests (N384 K1536 2.40 -> 2.47 ms over 7 launches, N768 K3072 +5 %): K <= 512 only
+  p.res_l2pf = res_l2pf_on && K <= 512 && epi.res != nullptr && epi.res_row_mod == 0 &&
+               (TMA_OUT ? (OUT == 0 && epi.res == epi.out_f32 && epi.ld_res == epi.ld_f32) : true);
   long long tiles = (long long)((p.n_tiles_m + CG - 1) / CG) * (AST ? 1 : p.n_tiles_n);  // AST: work unit = a row block
   const int max_groups = num_sms / CG;
   int grid = (int)(tiles < max_groups ? tiles : max_groups) * CG;

@@ -49,6 +49,7 @@ struct GemmProblem {
   int n_tiles_m, n_tiles_n;
   int rotate;  // epilogue: the column-chunk group a warp takes rotates from tile to tile (balances BN / 32 chunks over EW / 4 groups)
   int res_stage;  // epilogue: fp32 residual loaded lanes-along-columns and passed through the staging buffer
+  int res_l2pf;   // epilogue: in-place residual (res == out) boxes of a warp's next tile bulk-prefetched into L2
   unsigned long long* trace;  // debug timeline of CTA 0 (cv_gemm_set_trace): slot = event * 256 + local tile index, else nullptr
 };
 
