@@ -461,6 +461,7 @@ def run_main_workload(ctx, a, workload):
     prof = not a.no_profile
     lib.cv_profile_reset()
     lib.cv_profile_enable(1 if prof else 0)
+    ctx.barrier()  # every rank has finished its warm-up: the sampler below sees rank 0's GPU under load, not waiting for the others
     clocks = ClockSampler(ctx.local) if rank == 0 else None
     total_ms = _timed(ctx, step_resident, a.steps, join)
     clk = clocks.stop() if clocks else None
